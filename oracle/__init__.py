@@ -1,0 +1,5 @@
+"""CPU oracle for the IGLU Gridworld step hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this package. The product (gridworld_b200) never does.
+"""

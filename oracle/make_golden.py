@@ -1,0 +1,487 @@
+"""Generate the golden vectors under tests/golden/ by EXECUTING the unmodified reference.
+
+TEST INFRASTRUCTURE ONLY. Run in the build container (where /root/reference exists):
+
+    python oracle/make_golden.py
+
+It imports the Python reference through oracle/refharness (gym stub + numpy.int shim),
+drives it with fixed-seed / scripted action traces, and records the reference's own
+state after every step. Nothing here is an algorithm of ours: every number stored is an
+output of the reference code (gridworld/env.py, core/world.py, tasks/task.py).
+
+Files written (all small, committed):
+  goals.npz          156 real target structures (skills/goals.pkl via Tasks.to_dense), their
+                     Task.__init__ products and maximal_intersection known answers
+  reward_pairs.npz   random (grid, target[, full_grid]) pairs -> Task.maximal_intersection /
+                     argmax_intersection, incl. negative "difference grid" classes
+  traces_walking.npz random + scripted Discrete(18) traces (per-step pose/dy/tis/inventory/
+                     reward/done/grid)
+  traces_flying.npz  flying Dict traces (float32 actions, widened to fp64 for the reference)
+  traces_dict.npz    walking Dict (discretize=False) traces
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, 'refharness'))
+import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+CELLS = 9 * 11 * 11
+
+
+def dense_to_sparse_world(d):
+    """dense [y+1, x+5, z+5] -> list of world-coordinate (x, y, z, colour), the format of
+    Task.starting_grid (reference tasks/task.py:172-173)."""
+    ys, xs, zs = np.nonzero(d)
+    return [(int(x) - 5, int(y) - 1, int(z) - 5, int(d[y, x, z])) for y, x, z in zip(ys, xs, zs)]
+
+
+# ----------------------------------------------------------------------------- reward
+
+def synth_target(rng, rho, support):
+    """SURVEY 8(d) synthetic targets: (u < rho) ? 1 + floor(6 v) : 0 on the full zone or the
+    compact 5x5x5 support (y < 5, 3 <= x, z <= 7)."""
+    u = rng.random_sample((9, 11, 11))
+    v = rng.random_sample((9, 11, 11))
+    t = np.where(u < rho, 1 + np.floor(6 * v), 0).astype(np.int8)
+    if support == 'compact':
+        m = np.zeros((9, 11, 11), bool)
+        m[:5, 3:8, 3:8] = True
+        t = np.where(m, t, 0).astype(np.int8)
+    return t
+
+
+def related_grid(rng, task, target):
+    """A grid that is a rotated + admissibly shifted copy of the target with 10% of the cells
+    re-randomised (SURVEY 8(d) config-4 inputs)."""
+    k = rng.randint(4)
+    adm = task.admissible[k] if len(task.admissible) > k else task.admissible[0]
+    tg = np.asarray(task.target_grids[k] if len(task.admissible) > 1 else task.target_grids[0])
+    dx, dz = adm[rng.randint(len(adm))] if len(adm) else (0, 0)
+    g = np.zeros((9, 11, 11), np.int8)
+    ys, xs, zs = np.nonzero(tg)
+    for y, x, z in zip(ys, xs, zs):
+        gx, gz = x - dx, z - dz
+        if 0 <= gx < 11 and 0 <= gz < 11:
+            g[y, gx, gz] = tg[y, x, z]
+    noise = rng.random_sample(g.shape) < 0.1
+    rnd = np.where(rng.random_sample(g.shape) < 0.3, rng.randint(1, 7, g.shape), 0)
+    return np.where(noise, rnd, g).astype(np.int8)
+
+
+def gen_goals(Task, Tasks):
+    raw = open(os.path.join(load_reference.REFERENCE_ROOT, 'skills', 'goals.pkl'), 'rb').read()
+    goals = pickle.loads(raw)  # opcode-audited in SURVEY section 4: numpy scalars only
+    names = sorted(goals.keys(), key=lambda s: int(s[1:]))
+    rng = np.random.RandomState(7)
+    targets, n_adm, tsize, ka1, ka2, grids, mi, arg = [], [], [], [], [], [], [], []
+    for nm in names:
+        blocks = [tuple(int(v) for v in b) for b in goals[nm]]
+        t = np.asarray(Tasks.to_dense(blocks)).astype(np.int8)
+        task = Task('', t.astype(np.int32))
+        targets.append(t)
+        n_adm.append([len(a) for a in task.admissible])
+        tsize.append(task.target_size)
+        # KA1: grid = rot90(T, -1, (1, 2));  KA2: every 2nd block shifted +1 in x
+        g1 = np.rot90(t, k=-1, axes=(1, 2)).copy()
+        g2 = np.zeros_like(t)
+        for i, (y, x, z) in enumerate(np.argwhere(t)):
+            if i % 2 == 1:
+                if x + 1 <= 10:
+                    g2[y, x + 1, z] = t[y, x, z]
+            else:
+                g2[y, x, z] = t[y, x, z]
+        ka1.append(task.maximal_intersection(g1.astype(np.int32)))
+        ka2.append(task.maximal_intersection(g2.astype(np.int32)))
+        gs = [related_grid(rng, task, t) for _ in range(2)]
+        grids.append(gs)
+        mi.append([task.maximal_intersection(g.astype(np.int32)) for g in gs])
+        arg.append([task.argmax_intersection(g.astype(np.int32)) for g in gs])
+    np.savez_compressed(os.path.join(OUT, 'goals.npz'), names=np.array(names), targets=np.array(targets),
+                        n_adm=np.array(n_adm, np.int32), target_size=np.array(tsize, np.int32),
+                        ka1=np.array(ka1, np.int32), ka2=np.array(ka2, np.int32),
+                        grids=np.array(grids, np.int8), max_int=np.array(mi, np.int32),
+                        argmax=np.array(arg, np.int32))
+    print('goals.npz', len(names), 'structures; KA C1', ka1[0], ka2[0])
+
+
+def gen_reward_pairs(Task):
+    rng = np.random.RandomState(11)
+    rows = []
+    for rho in (0.05, 0.20, 0.50):
+        for support in ('full', 'compact'):
+            for j in range(10):
+                t = synth_target(rng, rho, support)
+                mode = j % 5  # 0,1 plain; 2 difference-grid classes; 3 full_grid; 4 invariant=False
+                full = None
+                invariant = True
+                if mode == 2:  # values in -6..6 like env.py:230 target - init
+                    start = synth_target(rng, rho / 2, support)
+                    t = (t.astype(np.int32) - start).astype(np.int8)
+                if mode == 3:  # full_grid = superset structure (tasks/task.py:63-66)
+                    extra = synth_target(rng, 0.05, 'compact')
+                    full = np.where(t != 0, t, extra).astype(np.int8)
+                if mode == 4:
+                    invariant = False
+                task = Task('', t.astype(np.int32), full_grid=None if full is None else full.astype(np.int32),
+                            invariant=invariant)
+                for g in (synth_target(rng, rho, support), related_grid(rng, task, t)):
+                    if mode == 2:
+                        g = (g.astype(np.int32) - start).astype(np.int8)
+                    rows.append((t, g, full if full is not None else np.zeros_like(t), full is not None,
+                                 invariant, task.maximal_intersection(g.astype(np.int32)),
+                                 task.argmax_intersection(g.astype(np.int32)),
+                                 [len(a) for a in task.admissible] + [0] * (4 - len(task.admissible)),
+                                 task.target_size))
+    # degenerate cases: empty target (all 441 shifts admissible), single block, full-width bar
+    for t in (np.zeros((9, 11, 11), np.int8),):
+        task = Task('', t.astype(np.int32))
+        g = synth_target(rng, 0.2, 'full')
+        rows.append((t, g, np.zeros_like(t), False, True, task.maximal_intersection(g.astype(np.int32)),
+                     task.argmax_intersection(g.astype(np.int32)), [len(a) for a in task.admissible],
+                     task.target_size))
+    # full_grid empty but target not: every shift admissible -> the slices really clip
+    t = synth_target(rng, 0.2, 'full')
+    full = np.zeros_like(t)
+    task = Task('', t.astype(np.int32), full_grid=full.astype(np.int32))
+    for _ in range(3):
+        g = related_grid(rng, Task('', t.astype(np.int32)), t)
+        g = np.roll(g, (rng.randint(-3, 4), rng.randint(-3, 4)), axis=(1, 2))
+        rows.append((t, g, full, True, True, task.maximal_intersection(g.astype(np.int32)),
+                     task.argmax_intersection(g.astype(np.int32)), [len(a) for a in task.admissible],
+                     task.target_size))
+    cols = list(zip(*rows))
+    np.savez_compressed(os.path.join(OUT, 'reward_pairs.npz'), targets=np.array(cols[0], np.int8),
+                        grids=np.array(cols[1], np.int8), fulls=np.array(cols[2], np.int8),
+                        has_full=np.array(cols[3], bool), invariant=np.array(cols[4], bool),
+                        max_int=np.array(cols[5], np.int32), argmax=np.array(cols[6], np.int32),
+                        n_adm=np.array(cols[7], np.int32), target_size=np.array(cols[8], np.int32))
+    print('reward_pairs.npz', len(rows), 'pairs')
+
+
+# ----------------------------------------------------------------------------- traces
+
+class Recorder:
+    FIELDS = ('pos', 'rot', 'dy', 'tis', 'active', 'inventory', 'reward', 'done', 'max_int', 'step_no',
+              'agentPos', 'compass', 'obs_inventory')
+
+    def __init__(self):
+        self.d = {k: [] for k in self.FIELDS}
+        self.grid_steps, self.grid_vals = [], []
+        self.last_grid = None
+
+    def record(self, env, obs, reward, done, t):
+        u = env.unwrapped
+        a = u.agent
+        d = self.d
+        d['pos'].append([float(v) for v in a.position])
+        d['rot'].append([float(v) for v in a.rotation])
+        d['dy'].append(float(a.dy))
+        d['tis'].append(int(a.time_int_steps))
+        d['active'].append(int(a.active_block))
+        d['inventory'].append([int(v) for v in a.inventory])
+        d['reward'].append(float(reward))
+        d['done'].append(bool(done))
+        d['max_int'].append(int(u._synthetic_task.max_int))
+        d['step_no'].append(int(u.step_no))
+        d['agentPos'].append(np.asarray(obs['agentPos'], np.float32))
+        d['compass'].append(np.asarray(obs['compass'], np.float32))
+        d['obs_inventory'].append(np.asarray(obs['inventory'], np.float32))
+        g = u.grid.astype(np.int8).reshape(-1)
+        assert np.array_equal(np.asarray(obs['grid']).reshape(-1), g)
+        if self.last_grid is None or not np.array_equal(g, self.last_grid):
+            self.grid_steps.append(t)  # grid snapshots stored only when the grid changed
+            self.grid_vals.append(g.copy())
+            self.last_grid = g
+
+    def pack(self, prefix, out):
+        d = self.d
+        out[prefix + 'pos'] = np.array(d['pos'], np.float64)
+        out[prefix + 'rot'] = np.array(d['rot'], np.float64)
+        out[prefix + 'dy'] = np.array(d['dy'], np.float64)
+        out[prefix + 'tis'] = np.array(d['tis'], np.int32)
+        out[prefix + 'active'] = np.array(d['active'], np.int32)
+        out[prefix + 'inventory'] = np.array(d['inventory'], np.int32)
+        out[prefix + 'reward'] = np.array(d['reward'], np.float64)
+        out[prefix + 'done'] = np.array(d['done'], bool)
+        out[prefix + 'max_int'] = np.array(d['max_int'], np.int32)
+        out[prefix + 'step_no'] = np.array(d['step_no'], np.int32)
+        out[prefix + 'agentPos'] = np.array(d['agentPos'], np.float32)
+        out[prefix + 'compass'] = np.array(d['compass'], np.float32)
+        out[prefix + 'obs_inventory'] = np.array(d['obs_inventory'], np.float32)
+        out[prefix + 'grid_steps'] = np.array(self.grid_steps, np.int32)
+        out[prefix + 'grid_vals'] = np.array(self.grid_vals, np.int8).reshape(-1, CELLS)
+
+
+def make_env(gym, Task, action_space, target, start, pose, select_and_place=True, max_steps=250, discretize=True,
+             right_scale=1, wrong_scale=0.1):
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False,
+                   select_and_place=select_and_place, action_space=action_space, max_steps=max_steps,
+                   discretize=discretize, right_placement_scale=right_scale, wrong_placement_scale=wrong_scale)
+    sparse = [] if start is None else dense_to_sparse_world(start)
+    task = Task('', np.asarray(target).astype(np.int32), starting_grid=sparse)
+    if pose is not None:
+        env.unwrapped._task = task  # initialize_world() needs a task for its reset
+        env.initialize_world(sparse, tuple(float(v) for v in pose))
+    else:
+        env.set_task(task)
+    return env
+
+
+def run_trace(gym, Task, cfg, actions, conv):
+    """One fresh env per trace (dy / active_block / time_int_steps leak across resets).
+    When the reference reports done, the harness calls reset() before the next step -- the
+    per-env sequence the batched auto-reset reproduces."""
+    env = make_env(gym, Task, cfg['action_space'], cfg['target'], cfg.get('start'), cfg.get('pose'),
+                   cfg.get('select_and_place', True), cfg.get('max_steps', 250), cfg.get('discretize', True),
+                   cfg.get('right_scale', 1), cfg.get('wrong_scale', 0.1))
+    rec = Recorder()
+    done = False
+    n = len(actions[0]) if isinstance(actions, tuple) else len(actions)
+    for t in range(n):
+        if done:
+            env.reset()
+        obs, reward, done, _ = env.step(conv(actions, t))
+        rec.record(env, obs, reward, done, t)
+    return rec
+
+
+def walking_action_mix(rng, n, kind):
+    if kind == 'uniform':
+        return rng.randint(0, 18, n).astype(np.int32)
+    if kind == 'builder':  # look down, place/break/hotbar heavy, some jumps -> towers, falls, exhaustion
+        p = np.array([1, 4, 2, 2, 2, 5, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+        return rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+    if kind == 'runner':  # mostly movement + jumps: walls, zone border, step-ups
+        p = np.array([1, 8, 3, 4, 4, 4, 0.5, 0.5, 0.5, 0.5, 0.5, 0.5, 2, 2, 1, 1, 1, 2], float)
+        return rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+    raise ValueError(kind)
+
+
+def scripted_walking():
+    """Scripted scenarios from SURVEY section 4 (states random actions never reach)."""
+    T2 = np.zeros((9, 11, 11), np.int8)
+    T2[0, 5, 3] = 1
+    T2[1, 5, 3] = 1  # world (0,-1,-2) and (0,0,-2) blue
+    out = []
+    # known-answer physics trace (SURVEY table): free fall, forward, camera, place, break, jump
+    a = [0, 0, 0, 1, 1, 1] + [15] * 9 + [14] * 18 + [17, 16, 5] + [0] * 13
+    out.append(dict(name='ka_physics', cfg=dict(action_space='walking', target=T2, select_and_place=False), a=a))
+    # high fall (time_int_steps 8 and 12)
+    out.append(dict(name='high_fall', cfg=dict(action_space='walking', target=T2, pose=(0, 9.5, 0, 0, 0)),
+                    a=[0] * 24))
+    # wall
+    S = np.zeros((9, 11, 11), np.int8)
+    S[0, 5, 3] = 1
+    S[1, 5, 3] = 1
+    T2b = np.zeros((9, 11, 11), np.int8)
+    T2b[0, 2, 2] = 4
+    T2b[0, 5, 3] = 1
+    out.append(dict(name='wall', cfg=dict(action_space='walking', target=T2b, start=S, pose=(0, -0.25, 0, 0, 0)),
+                    a=[1] * 8 + [3] * 3 + [1] * 3 + [4] * 6 + [1] * 3))
+    # target == start: synthetic target is empty -> target_size 0 -> done on every step
+    out.append(dict(name='target_equals_start', cfg=dict(action_space='walking', target=T2, start=S,
+                                                         pose=(0, -0.25, 0, 0, 0)), a=[1, 0, 17, 16, 3, 0]))
+    # step-up
+    S1 = np.zeros((9, 11, 11), np.int8)
+    S1[0, 5, 3] = 1
+    out.append(dict(name='step_up', cfg=dict(action_space='walking', target=T2, start=S1,
+                                             pose=(0, -0.25, -0.75, 0, 0)), a=[5, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0]))
+    # reward/done with a starting grid (SURVEY: break red start block, useless block, finish)
+    S2 = np.zeros((9, 11, 11), np.int8)
+    S2[0, 6, 6] = 3
+    S2[0, 5, 3] = 1
+    a = [14] * 9 + [13] * 27 + [16] + [12] * 27 + [17, 16] + [1, 1] + [14] * 4 + [17, 17, 0, 0]
+    out.append(dict(name='start_grid_reward', cfg=dict(action_space='walking', target=T2, start=S2,
+                                                       select_and_place=False), a=a))
+    # tower building: look straight down, jump + place under feet repeatedly, then walk off
+    # jump and place under the feet at the apex (only then the overlap test of world.py:324-325
+    # lets the block through), land on it, then try again from the block (rejected: too low)
+    a = [14] * 18 + [5, 0, 0, 0, 0, 17] + [0] * 12 + [5, 0, 0, 0, 0, 17] + [0] * 12 + [1] * 5 + [0] * 10
+    T3 = np.zeros((9, 11, 11), np.int8)
+    T3[0:5, 5, 5] = 1
+    out.append(dict(name='jump_place', cfg=dict(action_space='walking', target=T3, select_and_place=False), a=a))
+    # walk off a 6-block tower: fall with time_int_steps 4 and 8, land, keep walking into the border
+    S4 = np.zeros((9, 11, 11), np.int8)
+    S4[0:6, 5, 5] = 5
+    out.append(dict(name='tower_fall', cfg=dict(action_space='walking', target=T3, start=S4,
+                                                pose=(0, 5.75, 0, 0, 0)), a=[0, 0] + [1] * 6 + [0] * 25 + [16, 14, 14, 16]))
+    # staircase: place a block ahead, jump on it, place the next one higher, ... (random builder
+    # traces seldom get off the floor)
+    a = [14] * 7 + [17] + [5, 1, 1, 1, 1, 1, 0, 0, 0] + [17] + [5, 1, 1, 1, 1, 1, 0, 0, 0] + [17] + [5, 1, 1, 1, 1, 1, 0, 0, 0] \
+        + [13] * 18 + [1] * 6 + [0] * 20
+    out.append(dict(name='staircase', cfg=dict(action_space='walking', target=T3, select_and_place=False), a=a))
+    # leave the padded zone and come back; yaw wrap both ways; pitch clamp
+    a = [1] * 40 + [13] * 80 + [2] * 10 + [12] * 160 + [3] * 40 + [15] * 40 + [14] * 50 + [4] * 60
+    out.append(dict(name='zone_border_yaw_pitch', cfg=dict(action_space='walking', target=T2, max_steps=1000),
+                    a=a))
+    # inventory exhaustion with select_and_place hotbar: place 25 blue blocks in different spots
+    a = [14] * 12
+    for i in range(24):
+        a += [6, 2]
+    a += [7, 2, 8, 2, 16, 16]
+    out.append(dict(name='inventory_exhaustion', cfg=dict(action_space='walking', target=T2, max_steps=1000),
+                    a=a))
+    # ceiling bump: blocks overhead
+    S3 = np.zeros((9, 11, 11), np.int8)
+    S3[3, 5, 5] = 2
+    S3[3, 5, 4] = 2
+    out.append(dict(name='ceiling', cfg=dict(action_space='walking', target=T2, start=S3), a=[0, 0, 0, 5] + [0] * 12
+                    + [1, 5] + [0] * 12))
+    # non multiple-of-5 initial rotation (generic trig path) and odd offsets
+    out.append(dict(name='odd_rotation', cfg=dict(action_space='walking', target=T2,
+                                                  pose=(0.3, -0.25, 0.1, 33.3, -41.7)),
+                    a=[1, 1, 3, 17, 2, 4, 16, 13, 1, 17, 14, 14, 17, 5, 1, 1, 1]))
+    return out
+
+
+def gen_walking(gym, Task):
+    out = {}
+    names = []
+    rng = np.random.RandomState(0)
+    idx = 0
+
+    def add(name, cfg, a):
+        nonlocal idx
+        a = np.asarray(a, np.int32)
+        rec = run_trace(gym, Task, cfg, a, lambda acts, t: int(acts[t]))
+        p = f't{idx}_'
+        out[p + 'actions'] = a
+        out[p + 'target'] = np.asarray(cfg['target'], np.int8)
+        out[p + 'start'] = np.asarray(cfg['start'] if cfg.get('start') is not None else np.zeros((9, 11, 11)), np.int8)
+        out[p + 'pose'] = np.asarray(cfg.get('pose') or (0, 0, 0, 0, 0), np.float64)
+        out[p + 'cfg'] = np.array([int(cfg.get('select_and_place', True)), int(cfg.get('max_steps', 250))], np.int32)
+        out[p + 'scales'] = np.array([cfg.get('right_scale', 1), cfg.get('wrong_scale', 0.1)], np.float64)
+        rec.pack(p, out)
+        names.append(name)
+        idx += 1
+        print('  walking', name, len(a), 'steps; grid changes', len(rec.grid_steps), 'dones', int(np.sum(rec.d['done'])))
+
+    for s in scripted_walking():
+        add(s['name'], s['cfg'], s['a'])
+    for kind, n in (('uniform', 1500), ('builder', 1500), ('runner', 1200)):
+        for rep in range(2):
+            rho = (0.05, 0.2)[rep]
+            target = synth_target(rng, rho, 'compact')
+            start = synth_target(rng, 0.03, 'compact') if rep == 1 else None
+            if start is not None:
+                start[:, 5, 5] = 0  # keep the spawn column free
+                start[2:] = 0
+            cfg = dict(action_space='walking', target=target, start=start, select_and_place=(kind != 'runner'),
+                       max_steps=250 if rep == 0 else 400, right_scale=1 if rep == 0 else 2.0,
+                       wrong_scale=0.1 if rep == 0 else 0.25)
+            add(f'{kind}_{rep}', cfg, walking_action_mix(rng, n, kind))
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'traces_walking.npz'), **out)
+    print('traces_walking.npz', idx, 'traces')
+
+
+def gen_flying(gym, Task):
+    out = {}
+    names = []
+    rng = np.random.RandomState(1)
+    idx = 0
+
+    def conv(acts, t):
+        mv, cam, inv, pl = acts
+        # float32 -> Python float: numpy-2 would otherwise keep float32 arithmetic
+        return {'movement': [float(v) for v in mv[t]], 'camera': [float(v) for v in cam[t]],
+                'inventory': int(inv[t]), 'placement': int(pl[t])}
+
+    def add(name, cfg, n, style):
+        nonlocal idx
+        mv = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        cam = rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+        inv = rng.randint(0, 7, n).astype(np.int32)
+        pl = rng.randint(0, 3, n).astype(np.int32)
+        if style == 'sparse_moves':  # exact zeros in movement components exercise the strafe branches
+            mv[rng.random_sample((n, 3)) < 0.5] = 0
+            cam[rng.random_sample((n, 2)) < 0.5] = 0
+        if style == 'look_down':
+            cam[:, 1] = -np.abs(cam[:, 1])
+            mv[:, 2] *= 0.2
+        acts = (mv, cam, inv, pl)
+        rec = run_trace(gym, Task, cfg, acts, conv)
+        p = f't{idx}_'
+        out[p + 'movement'], out[p + 'camera'], out[p + 'inv'], out[p + 'placement'] = mv, cam, inv, pl
+        out[p + 'target'] = np.asarray(cfg['target'], np.int8)
+        out[p + 'start'] = np.asarray(cfg['start'] if cfg.get('start') is not None else np.zeros((9, 11, 11)), np.int8)
+        out[p + 'pose'] = np.asarray(cfg.get('pose') or (0, 0, 0, 0, 0), np.float64)
+        out[p + 'cfg'] = np.array([int(cfg.get('select_and_place', True)), int(cfg.get('max_steps', 250))], np.int32)
+        out[p + 'scales'] = np.array([cfg.get('right_scale', 1), cfg.get('wrong_scale', 0.1)], np.float64)
+        rec.pack(p, out)
+        names.append(name)
+        idx += 1
+        print('  flying', name, n, 'steps; grid changes', len(rec.grid_steps), 'dones', int(np.sum(rec.d['done'])))
+
+    for i, style in enumerate(('uniform', 'sparse_moves', 'look_down', 'look_down')):
+        target = synth_target(rng, 0.1, 'compact')
+        start = synth_target(rng, 0.05, 'compact') if i >= 2 else None
+        cfg = dict(action_space='flying', target=target, start=start, select_and_place=(i != 1),
+                   pose=(0, 1.5, 0, 0, -30) if i == 3 else None)
+        add(f'{style}_{i}', cfg, 800, style)
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'traces_flying.npz'), **out)
+    print('traces_flying.npz', idx, 'traces')
+
+
+def gen_dict(gym, Task):
+    out = {}
+    names = []
+    rng = np.random.RandomState(2)
+    KEYS = ('forward', 'back', 'left', 'right', 'jump', 'attack', 'use', 'hotbar')
+
+    def conv(acts, t):
+        b, cam = acts
+        a = {k: int(b[t, i]) for i, k in enumerate(KEYS)}
+        a['camera'] = [float(v) for v in cam[t]]
+        return a
+
+    for idx, snap in enumerate((True, False)):
+        n = 800
+        b = (rng.random_sample((n, 8)) < 0.25).astype(np.int32)
+        b[:, 7] = np.where(rng.random_sample(n) < 0.3, rng.randint(1, 7, n), 0)
+        cam = rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+        if snap:  # camera in multiples of 5 -> LUT trig path, combined strafes give +-45/135 deg
+            cam = (np.round(cam / 5) * 5).astype(np.float32)
+        target = synth_target(rng, 0.1, 'compact')
+        cfg = dict(action_space='walking', discretize=False, target=target, select_and_place=bool(idx))
+        rec = run_trace(gym, Task, cfg, (b, cam), conv)
+        p = f't{idx}_'
+        out[p + 'buttons'], out[p + 'camera'] = b, cam
+        out[p + 'target'] = target
+        out[p + 'start'] = np.zeros((9, 11, 11), np.int8)
+        out[p + 'pose'] = np.zeros(5)
+        out[p + 'cfg'] = np.array([int(cfg['select_and_place']), 250], np.int32)
+        out[p + 'scales'] = np.array([1, 0.1], np.float64)
+        rec.pack(p, out)
+        names.append(f'dict_{idx}')
+        print('  dict', idx, n, 'steps; grid changes', len(rec.grid_steps), 'dones', int(np.sum(rec.d['done'])))
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'traces_dict.npz'), **out)
+
+
+def main():
+    load_reference.load()
+    import gym
+    from gridworld.tasks import Task, Tasks
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict']
+    if 'goals' in which:
+        gen_goals(Task, Tasks)
+    if 'pairs' in which:
+        gen_reward_pairs(Task)
+    if 'walking' in which:
+        gen_walking(gym, Task)
+    if 'flying' in which:
+        gen_flying(gym, Task)
+    if 'dict' in which:
+        gen_dict(gym, Task)
+
+
+if __name__ == '__main__':
+    main()
