@@ -1,0 +1,85 @@
+"""ctypes binding of the C ABI declared in include/iglu_b200.h.
+
+The product path has NO CPU fallback: importing this module on a box where the CUDA library is
+missing (and cannot be built) raises, and so does every entry point without a CUDA device.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+CELLS = 1089
+GRID_STRIDE = 1104
+TLIST_MAX = 1096
+
+WALKING_DISCRETE, FLYING, WALKING_DICT = 0, 1, 2
+REWARD_ON_CHANGE, REWARD_EVERY_STEP = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [('action_space', C.c_int32), ('select_and_place', C.c_int32), ('max_steps', C.c_int32),
+                ('auto_reset', C.c_int32), ('reward_mode', C.c_int32), ('write_grid_obs', C.c_int32),
+                ('tlist_cap', C.c_int32), ('reserved', C.c_int32),
+                ('right_placement_scale', C.c_double), ('wrong_placement_scale', C.c_double)]
+
+
+class State(C.Structure):
+    _fields_ = [('n', C.c_int64), ('grid', C.c_void_p), ('init', C.c_void_p), ('target', C.c_void_p),
+                ('pose', C.c_void_p), ('init_pose', C.c_void_p), ('istate', C.c_void_p),
+                ('tlist', C.c_void_p), ('trect', C.c_void_p), ('tmeta', C.c_void_p)]
+
+
+class Obs(C.Structure):
+    _fields_ = [('grid', C.c_void_p), ('target_grid', C.c_void_p), ('agent_pos', C.c_void_p),
+                ('inventory', C.c_void_p), ('compass', C.c_void_p), ('reward', C.c_void_p),
+                ('done', C.c_void_p)]
+
+
+EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_destroy', 'iglu_set_tasks',
+           'iglu_reset', 'iglu_step_walking', 'iglu_step_flying', 'iglu_step_walking_dict',
+           'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count')
+
+_lib = None
+
+
+def library_path():
+    return _build.SO
+
+
+def load():
+    """Loads (building first if stale/missing) libiglu_b200.so. Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = _build.build_library()
+    if not os.path.exists(so):
+        raise RuntimeError(f'{so} is missing: the CUDA extension is required (there is no CPU fallback)')
+    L = C.CDLL(so)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.iglu_abi_version.restype = i32
+    L.iglu_strerror.restype = C.c_char_p
+    L.iglu_strerror.argtypes = [i32]
+    L.iglu_ctx_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.iglu_ctx_destroy.argtypes = [vp]
+    L.iglu_ctx_destroy.restype = None
+    L.iglu_set_tasks.argtypes = [vp, C.POINTER(State), C.POINTER(Obs), vp, vp, vp, vp, i64, vp]
+    L.iglu_reset.argtypes = [vp, C.POINTER(State), C.POINTER(Obs), vp, i32, vp]
+    L.iglu_step_walking.argtypes = [vp, C.POINTER(State), vp, C.POINTER(Obs), vp]
+    L.iglu_step_flying.argtypes = [vp, C.POINTER(State), vp, vp, vp, vp, C.POINTER(Obs), vp]
+    L.iglu_step_walking_dict.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp]
+    L.iglu_step_walking_host.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp, vp, vp]
+    L.iglu_max_intersection.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp]
+    L.iglu_last_launch_count.argtypes = [vp]
+    if L.iglu_abi_version() != 1:
+        raise RuntimeError('libiglu_b200.so ABI version mismatch')
+    _lib = L
+    return L
+
+
+def check(status):
+    if status == 0:
+        return
+    msg = load().iglu_strerror(status).decode()
+    if status == -3:
+        raise ValueError(msg)
+    raise RuntimeError(f'iglu_b200 error {status}: {msg}')

@@ -1,0 +1,56 @@
+"""Builds gridworld_b200/csrc/libiglu_b200.so (sm_100a) in-tree with nvcc.
+
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+SO = os.path.join(CSRC, 'libiglu_b200.so')
+SOURCES = ['iglu_b200.cu']
+HEADERS = ['iglu_physics.cuh', 'iglu_reward.cuh', os.path.join('..', '..', 'include', 'iglu_b200.h')]
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a',
+    '-O3', '-lineinfo', '-std=c++17',
+    '-fmad=false',            # fp64 parity: the reference never fuses a*b+c
+    '--shared', '-Xcompiler', '-fPIC',
+    '-Xptxas', '-v',
+]
+
+
+def _nvcc():
+    for cand in (shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found: the CUDA library cannot be built')
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile the CUDA library if it is missing or stale; returns the path of the .so."""
+    if not force and not needs_build():
+        return SO
+    cmd = [_nvcc()] + NVCC_FLAGS + ['-o', SO] + [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(os.path.join(CSRC, 'build.log'), 'w') as f:
+        f.write(' '.join(cmd) + '\n' + log)
+    if verbose or res.returncode != 0:
+        print(log)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed building libiglu_b200.so (see gridworld_b200/csrc/build.log)')
+    return SO
+
+
+if __name__ == '__main__':
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,240 @@
+// iglu_physics.cuh -- per-env (one thread) World/Agent update in fp64.
+//
+// Restates, in the reference's operation order, gridworld/core/world.py:73-99 (hit_test),
+// 145-201 (sight / motion vectors), 203-262 (update/_update), 264-310 (collide), 312-332
+// (place_or_remove_block), 338-356 (move_camera / movement), 434-456 (step) and the env
+// callbacks gridworld/env.py:136-153.  Compiled with -fmad=false: every mul/add is a separate
+// IEEE operation exactly as CPython evaluates it.  round() is half-even (numba round == rint).
+//
+// Trigonometry: CPython's math.sin/cos/atan2 are glibc's.  The device libm is not bit-identical,
+// so every angle that is an exact multiple of 5 degrees inside [-180, 720] (all angles the
+// Discrete(18) action space can produce from the default pose) is served from a table the HOST
+// filled with glibc at iglu_ctx_create time, keyed by the un-reduced angle.  Other angles take
+// the device sincos/atan2 (<= 2 ulp, pose parity 1e-6 as BASELINE.json states for flying).
+#pragma once
+#include <cstdint>
+
+namespace iglu {
+
+constexpr int CELLS = 1089;
+constexpr int GSTRIDE = 1104;
+constexpr int TRIG_LO = -36;  // table index 0 <-> -180 degrees
+constexpr int TRIG_N = 181;   // ... index 180 <-> 720 degrees
+
+// Filled by iglu_ctx_create (host glibc). g_trig[i] = (sin, cos)(radians(5 * (i + TRIG_LO))).
+__device__ double2 g_trig[TRIG_N];
+// degrees(atan2(s0, s1)) for s0, s1 in {-1, 0, 1}; index (s0 + 1) * 3 + (s1 + 1).
+__device__ double g_strafe_deg[9];
+__device__ double g_jump_speed;  // utils.py:21 sqrt(2 * GRAVITY * MAX_JUMP_HEIGHT)
+
+constexpr double DEG2RAD = 3.14159265358979323846 / 180.0;  // CPython: x * (pi / 180)
+constexpr double RAD2DEG = 180.0 / 3.14159265358979323846;  // CPython: x * (180 / pi)
+
+struct Agent {
+    double x, y, z, yaw, pitch, dy;
+    int tis, active, err;
+    int inv[6];
+};
+
+// The tuple every parse_* returns (world.py:394, 414, 432).
+struct Action {
+    double s0, s1, jump, cam0, cam1;
+    int hotbar;  // 0 = None
+    bool remove, add;
+};
+
+__device__ __forceinline__ void trig_deg(double deg, double &s, double &c) {
+    double k = rint(deg * 0.2);
+    if (k * 5.0 == deg && k >= (double)TRIG_LO && k <= (double)(TRIG_LO + TRIG_N - 1)) {
+        double2 v = g_trig[(int)k - TRIG_LO];
+        s = v.x;
+        c = v.y;
+    } else {
+        sincos(deg * DEG2RAD, &s, &c);
+    }
+}
+
+__device__ __forceinline__ double strafe_degrees(double s0, double s1) {
+    if ((s0 == -1.0 || s0 == 0.0 || s0 == 1.0) && (s1 == -1.0 || s1 == 0.0 || s1 == 1.0))
+        return g_strafe_deg[((int)s0 + 1) * 3 + ((int)s1 + 1)];
+    return atan2(s0, s1) * RAD2DEG;
+}
+
+// `key in self.world` / `self.world[key]`: the 37x37 floor at y = -2 (world.py:60-71, WHITE inside
+// the zone footprint, GREY outside) plus the placed blocks mirrored in grid[y+1, x+5, z+5].
+__device__ __forceinline__ bool world_get(const int8_t *__restrict__ g, int x, int y, int z, int &tex) {
+    if (y == -2) {
+        tex = (abs(x) <= 5 && abs(z) <= 5) ? -1 : 0;
+        return abs(x) <= 18 && abs(z) <= 18;
+    }
+    if ((unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u) {
+        int c = g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)];
+        tex = c;
+        return c != 0;
+    }
+    return false;
+}
+
+__device__ __forceinline__ bool build_zone_i(int x, int y, int z) {
+    return -5 <= x && x <= 5 && -5 <= z && z <= 5 && -1 <= y && y < 8;
+}
+
+// world.py:264-310 collide (FACES order utils.py:156-163: +y, -y, -x, +x, +z, -z)
+__device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px, double &py, double &pz,
+                                        double &agent_dy) {
+    const double pad = 0.25;
+    const int nx = (int)rint(px), ny = (int)rint(py), nz = (int)rint(pz);
+    int tex;
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
+        const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
+        double &p = (axis == 0) ? px : (axis == 1 ? py : pz);
+        const int npi = (axis == 0) ? nx : (axis == 1 ? ny : nz);
+        double d = (p - (double)npi) * (double)sgn;
+        if (d < pad) continue;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int ox = nx, oy = ny - h, oz = nz;
+            if (axis == 0) ox += sgn;
+            else if (axis == 1) oy += sgn;
+            else oz += sgn;
+            if (!world_get(g, ox, oy, oz, tex)) continue;
+            p -= (d - pad) * (double)sgn;
+            if (f < 2) agent_dy = 0.0;
+            break;
+        }
+    }
+}
+
+// world.py:222-262 _update
+__device__ __forceinline__ void update_sub(const int8_t *__restrict__ g, Agent &a, bool flying, double mvx,
+                                           double mvy, double mvz, double dt) {
+    const double speed = flying ? 15.0 : 5.0;
+    const double d = dt * speed;
+    double dx = mvx * d, dy = mvy * d, dz = mvz * d;
+    if (!flying) {
+        a.dy -= dt * 20.0;
+        if (a.dy < -14.0) a.tis = 12;
+        else if (a.dy < -10.0) a.tis = 8;
+        else if (a.dy < -5.0) a.tis = 4;
+        else a.tis = 2;
+        a.dy = a.dy > -50.0 ? a.dy : -50.0;
+    }
+    dy += a.dy * dt;
+    double cx = a.x + dx, cy = a.y + dy, cz = a.z + dz;
+    if (-7.0 <= cx && cx <= 7.0 && -7.0 <= cz && cz <= 7.0 && -3.0 <= cy && cy < 10.0) {
+        collide(g, cx, cy, cz, a.dy);
+        a.x = cx; a.y = cy; a.z = cz;
+    } else if (!flying) {
+        double ux = a.x, uy = a.y + dy, uz = a.z;
+        collide(g, ux, uy, uz, a.dy);
+        a.x = ux; a.y = uy; a.z = uz;
+    }
+}
+
+// world.py:434-456 World.step for one env. `g` = this env's int8 grid (global memory),
+// `init` = its starting grid (only read when has_start, for the block-count bookkeeping),
+// `dsize` = nnz(grid - init), kept incrementally (task.py:110 recomputes it from scratch).
+__device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t *__restrict__ init, bool has_start,
+                                           Agent &a, Action act, bool flying, bool select_and_place, int &dsize) {
+    if (select_and_place && act.hotbar != 0) { act.add = true; act.remove = false; }
+    // movement (world.py:344-356); agent.strafe is [0, 0] on entry because sustain=False
+    const double s0 = act.s0, s1 = act.s1;
+    if (act.jump != 0.0 && a.dy == 0.0) a.dy = g_jump_speed * act.jump;
+    if (flying && act.jump == 0.0) a.dy = 0.0;
+    if (act.hotbar != 0) {
+        if (act.hotbar < 1 || act.hotbar > 6) a.err = 1;  // the reference raises ValueError here
+        else a.active = act.hotbar;
+    }
+    // move_camera (world.py:338-342)
+    a.yaw = a.yaw + act.cam0;
+    {
+        double p = a.pitch + act.cam1;
+        double mn = p < 90.0 ? p : 90.0;
+        a.pitch = mn > -90.0 ? mn : -90.0;
+    }
+    // place_or_remove_block (world.py:312-332)
+    if (act.add != act.remove) {
+        double sp, cp, sy, cy;
+        trig_deg(a.pitch, sp, cp);
+        trig_deg(a.yaw - 90.0, sy, cy);
+        const double vx = cy * cp, vy = sp, vz = sy * cp;  // get_sight_vector (145-161)
+        // hit_test (73-99): 40 samples, step 1/5
+        const double sx = vx / 5.0, syy = vy / 5.0, sz = vz / 5.0;
+        double px = a.x, py = a.y, pz = a.z;
+        int kx = 0, ky = 0, kz = 0, qx = 0, qy = 0, qz = 0, tex = 0;
+        bool has_prev = false, hit = false;
+        for (int i = 0; i < 40; i++) {
+            kx = (int)rint(px); ky = (int)rint(py); kz = (int)rint(pz);
+            bool differs = !has_prev || kx != qx || ky != qy || kz != qz;
+            if (differs && world_get(g, kx, ky, kz, tex)) { hit = true; break; }
+            qx = kx; qy = ky; qz = kz;
+            has_prev = true;
+            px = px + sx; py = py + syy; pz = pz + sz;
+        }
+        int cell = -1, newv = 0;
+        if (act.add) {
+            if (hit && has_prev) {
+                int have = 0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) if (c == a.active - 1) have = a.inv[c];
+                if (have > 0 && build_zone_i(qx, qy, qz)) {
+                    double y = a.y - 1.0 + 0.25;
+                    double bx = (double)qx - 0.5, by = (double)qy, bz = (double)qz - 0.5;
+                    bool inside = bx <= a.x && a.x <= bx + 1.0 && bz <= a.z && a.z <= bz + 1.0 &&
+                                  ((by <= y && y <= by + 1.0) || (by <= (y + 1.0) && (y + 1.0) <= by + 1.0));
+                    if (!inside) {
+                        cell = (qy + 1) * 121 + (qx + 5) * 11 + (qz + 5);
+                        newv = a.active;
+#pragma unroll
+                        for (int c = 0; c < 6; c++) if (c == a.active - 1) a.inv[c] -= 1;
+                    }
+                }
+            }
+        } else if (hit) {
+            if (tex != 0 && tex != -1) {  // not GREY / WHITE floor
+                cell = (ky + 1) * 121 + (kx + 5) * 11 + (kz + 5);
+                newv = 0;
+#pragma unroll
+                for (int c = 0; c < 6; c++) if (c == tex - 1) a.inv[c] += 1;
+            }
+        }
+        if (cell >= 0) {
+            int oldv = g[cell];
+            int iv = has_start ? (int)init[cell] : 0;
+            dsize += (int)(newv != iv) - (int)(oldv != iv);
+            g[cell] = (int8_t)newv;
+        }
+    }
+    // update (world.py:203-220): m = time_int_steps read once, dt = min(1/20, 0.2)
+    {
+        double mvx = 0.0, mvy = 0.0, mvz = 0.0;  // get_motion_vector (163-201)
+        if (s0 != 0.0 || s1 != 0.0) {
+            double sa, ca;
+            trig_deg(a.yaw + strafe_degrees(s0, s1), sa, ca);
+            if (flying) {
+                double sp, cp;
+                trig_deg(a.pitch, sp, cp);
+                double m = cp, dyv = sp;
+                if (s1 != 0.0) { dyv = 0.0; m = 1.0; }
+                if (s0 > 0.0) dyv *= -1.0;
+                mvx = ca * m; mvy = dyv; mvz = sa * m;
+            } else {
+                mvx = ca; mvy = 0.0; mvz = sa;
+            }
+        }
+        const int m = a.tis;
+        const double dt = 0.05 / (double)m;
+        for (int i = 0; i < m; i++) update_sub(g, a, flying, mvx, mvy, mvz, dt);
+        if (flying) a.dy = 0.0;
+    }
+    // world.py:451-456. The iteration cap only matters for |yaw| so large that +-360 no longer
+    // changes it (the reference would spin forever there); it keeps the kernel from hanging.
+    double yaw = a.yaw;
+    for (int it = 0; it < (1 << 16) && yaw > 360.0; it++) yaw -= 360.0;
+    for (int it = 0; it < (1 << 16) && yaw < 0.0; it++) yaw += 360.0;
+    a.yaw = yaw;
+}
+
+}  // namespace iglu

@@ -1,0 +1,393 @@
+"""Batched IGLU Gridworld: N environments resident in HBM, stepped by the sm_100a kernels behind
+the C ABI of include/iglu_b200.h.
+
+This is the batched form of the reference's GridWorld (reference gridworld/env.py:26-303) with
+render=False, vector_state=True. PyTorch only hands out the device tensors; every state update,
+observation and reward is computed by libiglu_b200.so (there is no CPU / eager fallback).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spaces import Box, Dict, Discrete, String
+
+_ACTION_SPACES = {'walking': None, 'flying': _lib.FLYING}
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError('gridworld_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise RuntimeError(f'gridworld_b200 only runs on CUDA devices, got {device!r}')
+    if dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
+def make_action_space(action_space, discretize):
+    """reference gridworld/env.py:56-78"""
+    if action_space == 'walking':
+        if discretize:
+            return Discrete(18)
+        return Dict({
+            'forward': Discrete(2), 'back': Discrete(2), 'left': Discrete(2), 'right': Discrete(2),
+            'jump': Discrete(2), 'attack': Discrete(2), 'use': Discrete(2),
+            'camera': Box(low=-5, high=5, shape=(2,)), 'hotbar': Discrete(7)})
+    if action_space == 'flying':
+        return Dict({
+            'movement': Box(low=-1, high=1, shape=(3,), dtype=np.float32),
+            'camera': Box(low=-5, high=5, shape=(2,), dtype=np.float32),
+            'inventory': Discrete(7), 'placement': Discrete(3)})
+    raise ValueError(f'unknown action_space {action_space!r}')
+
+
+def make_observation_space(vector_state, target_in_obs):
+    """reference gridworld/env.py:79-95 (render=False: no 'pov')"""
+    sp = {'inventory': Box(low=0, high=20, shape=(6,), dtype=np.float32),
+          'compass': Box(low=-180, high=180, shape=(1,), dtype=np.float32),
+          'dialog': String()}
+    if vector_state:
+        sp['agentPos'] = Box(low=np.array([-8, -2, -8, -90, 0], dtype=np.float32),
+                             high=np.array([8, 12, 8, 90, 360], dtype=np.float32), shape=(5,))
+        sp['grid'] = Box(low=-1, high=7, shape=(9, 11, 11), dtype=np.int32)
+    if target_in_obs:
+        sp['target_grid'] = Box(low=-1, high=7, shape=(9, 11, 11), dtype=np.int32)
+    return Dict(sp)
+
+
+class IGLUVecEnv:
+    """N independent IGLU Gridworld envs on one GPU.
+
+    kwargs mirror reference create_env / GridWorld.__init__ (env.py:27-31, 333-338). Additions:
+      num_envs, device, auto_reset (an env that returned done is reset at the start of the next
+      step call and then stepped -- per env this is exactly `reset(); step(a)` on the reference),
+      reward_mode ('on_change' = the reference's gate, 'every_step' = evaluate maximal_intersection
+      on every step; outputs are identical), grid_obs (materialise the int32 obs['grid'] each step).
+
+    step() returns device tensors that alias persistent buffers: a policy reads them in place.
+    """
+
+    def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
+                 select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
+                 target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
+                 grid_obs=True, render=False, tlist_cap=_lib.TLIST_MAX):
+        if render:
+            raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
+        if reward_mode not in ('on_change', 'every_step'):
+            raise ValueError("reward_mode must be 'on_change' or 'every_step'")
+        self.device = _require_cuda(device)
+        self.num_envs = n = int(num_envs)
+        if n <= 0:
+            raise ValueError('num_envs must be positive')
+        self.action_space_type = action_space
+        self.discretize = bool(discretize)
+        self.action_space = make_action_space(action_space, discretize)
+        self.observation_space = make_observation_space(vector_state, target_in_obs)
+        self.vector_state = bool(vector_state)
+        self.target_in_obs = bool(target_in_obs)
+        self.select_and_place = bool(select_and_place)
+        self.max_steps = int(max_steps)
+        self.right_placement_scale = right_placement_scale
+        self.wrong_placement_scale = wrong_placement_scale
+        self.auto_reset = bool(auto_reset)
+        self.reward_mode = reward_mode
+        self.grid_obs = bool(grid_obs) and self.vector_state
+        if action_space == 'flying':
+            kind = _lib.FLYING
+        else:
+            kind = _lib.WALKING_DISCRETE if discretize else _lib.WALKING_DICT
+        self._kind = kind
+        self._L = _lib.load()
+        self._tasks_set = False
+
+        dev = self.device
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        # ---- state (layout documented in include/iglu_b200.h) ----
+        self._grid = z(n, _lib.GRID_STRIDE, dtype=torch.int8)
+        self._init = z(n, _lib.GRID_STRIDE, dtype=torch.int8)
+        self._target = z(n, _lib.GRID_STRIDE, dtype=torch.int8)
+        self._pose = z(6, n, dtype=torch.float64)
+        self._init_pose = z(5, n, dtype=torch.float64)
+        self._istate = z(8, n, dtype=torch.int32)
+        self._tlist = z(n, int(tlist_cap), dtype=torch.int16)
+        self._trect = z(n, 16, dtype=torch.int8)
+        self._tmeta = z(8, n, dtype=torch.int32)
+        # ---- observations / results ----
+        self._obs_grid = z(n, 9, 11, 11, dtype=torch.int32) if self.grid_obs else None
+        self._obs_target = z(n, 9, 11, 11, dtype=torch.int32) if self.target_in_obs else None
+        self._obs_pos = z(n, 5, dtype=torch.float32)
+        self._obs_inv = z(n, 6, dtype=torch.float32)
+        self._obs_compass = z(n, 1, dtype=torch.float32)
+        self._reward = z(n, dtype=torch.float64)
+        self._done = z(n, dtype=torch.uint8)
+        self._actions_dev = z(n, dtype=torch.int32)
+
+        p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        self._st = _lib.State(n, p(self._grid), p(self._init), p(self._target), p(self._pose),
+                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._trect),
+                              p(self._tmeta))
+        self._ob = _lib.Obs(p(self._obs_grid), p(self._obs_target), p(self._obs_pos), p(self._obs_inv),
+                            p(self._obs_compass), p(self._reward), p(self._done))
+        cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
+                          _lib.REWARD_EVERY_STEP if reward_mode == 'every_step' else _lib.REWARD_ON_CHANGE,
+                          int(self.grid_obs), int(tlist_cap), 0,
+                          float(right_placement_scale), float(wrong_placement_scale))
+        self._ctx = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self._L.iglu_ctx_create(C.byref(cfg), C.byref(self._ctx)))
+        self.gpu_launches = 0  # kernels launched by this env so far
+
+    def __del__(self):
+        ctx = getattr(self, '_ctx', None)
+        if ctx is not None and ctx.value and getattr(self, '_L', None) is not None:
+            self._L.iglu_ctx_destroy(ctx)
+            self._ctx = None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, x, dtype, shape):
+        t = torch.as_tensor(x)
+        if t.dtype != dtype or t.device != self.device:
+            t = t.to(device=self.device, dtype=dtype)
+        t = t.contiguous()
+        if tuple(t.shape) != tuple(shape):
+            t = t.reshape(shape)
+        return t
+
+    def _count(self):
+        self.gpu_launches += self._L.iglu_last_launch_count(self._ctx)
+
+    # ------------------------------------------------------------------ tasks
+    def set_tasks(self, targets, starts=None, init_poses=None, env_idx=None, reset=True):
+        """Batched env.set_task / initialize_world (reference env.py:155-193).
+
+        targets : int8 [k, 9, 11, 11] dense target grids (dense index [y+1, x+5, z+5])
+        starts  : int8 [k, 9, 11, 11] dense starting grids or None (= starting_grid [])
+        init_poses : float64 [k, 5] (x, y, z, yaw, pitch) or None
+        env_idx : int [k] destination envs (default: envs 0..k-1, k must equal num_envs then)
+        """
+        t = torch.as_tensor(targets)
+        k = t.shape[0]
+        t = self._dev(t, torch.int8, (k, _lib.CELLS))
+        s = None if starts is None else self._dev(starts, torch.int8, (k, _lib.CELLS))
+        ip = None if init_poses is None else self._dev(init_poses, torch.float64, (k, 5))
+        idx = None
+        if env_idx is None:
+            if k != self.num_envs:
+                raise ValueError('set_tasks without env_idx needs one target per env')
+        else:
+            idx = self._dev(env_idx, torch.int32, (k,))
+        pp = lambda a: None if a is None else a.data_ptr()  # noqa: E731
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.iglu_set_tasks(self._ctx, C.byref(self._st), C.byref(self._ob), pp(t), pp(s),
+                                              pp(ip), pp(idx), k, self._stream()))
+            self._count()
+        self._tasks_set = True
+        if reset:
+            mask = None
+            if idx is not None:
+                mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device)
+                mask[idx.long()] = 1
+            return self.reset(mask)
+        return None
+
+    def _check_task(self):
+        if not self._tasks_set:
+            _lib.check(-3)  # ValueError with the reference's message (env.py:199-201)
+
+    def reset(self, mask=None, hard=False):
+        """Batched GridWorld.reset (reference env.py:206-261) for envs with mask != 0 (None = all)."""
+        self._check_task()
+        m = None if mask is None else self._dev(mask, torch.uint8, (self.num_envs,))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.iglu_reset(self._ctx, C.byref(self._st), C.byref(self._ob),
+                                          None if m is None else m.data_ptr(), int(hard), self._stream()))
+            self._count()
+        return self.observation()
+
+    # ------------------------------------------------------------------ step
+    def observation(self):
+        obs = {'inventory': self._obs_inv, 'compass': self._obs_compass}
+        if self.vector_state:
+            obs['agentPos'] = self._obs_pos
+            obs['grid'] = self._obs_grid if self.grid_obs else self.grid
+        if self.target_in_obs:
+            obs['target_grid'] = self._obs_target
+        return obs
+
+    def step(self, actions):
+        """Batched GridWorld.step (reference env.py:268-303).
+
+        walking (discretize=True): int32 [n]; flying: dict(movement f32 [n,3], camera f32 [n,2],
+        inventory int [n], placement int [n]); walking (discretize=False): dict with the nine
+        reference keys, each [n] (camera [n,2]).
+        Returns (obs dict of device tensors, reward float64 [n], done bool [n], {}).
+        """
+        self._check_task()
+        n = self.num_envs
+        L, st, ob = self._L, C.byref(self._st), C.byref(self._ob)
+        with torch.cuda.device(self.device):
+            if self._kind == _lib.WALKING_DISCRETE:
+                a = self._dev(actions, torch.int32, (n,))
+                _lib.check(L.iglu_step_walking(self._ctx, st, a.data_ptr(), ob, self._stream()))
+            elif self._kind == _lib.FLYING:
+                mv = self._dev(actions['movement'], torch.float32, (n, 3))
+                cam = self._dev(actions['camera'], torch.float32, (n, 2))
+                inv = self._dev(actions['inventory'], torch.int32, (n,))
+                pl = self._dev(actions['placement'], torch.int32, (n,))
+                _lib.check(L.iglu_step_flying(self._ctx, st, mv.data_ptr(), cam.data_ptr(), inv.data_ptr(),
+                                              pl.data_ptr(), ob, self._stream()))
+            else:
+                if isinstance(actions, dict):
+                    keys = ('forward', 'back', 'left', 'right', 'jump', 'attack', 'use', 'hotbar')
+                    b = torch.stack([self._dev(actions[k], torch.int32, (n,)) for k in keys], dim=1)
+                    cam = actions['camera']
+                else:
+                    b, cam = actions
+                b = self._dev(b, torch.int32, (n, 8))
+                cam = self._dev(cam, torch.float32, (n, 2))
+                _lib.check(L.iglu_step_walking_dict(self._ctx, st, b.data_ptr(), cam.data_ptr(), ob,
+                                                    self._stream()))
+            self._count()
+        return self.observation(), self._reward, self._done.view(torch.bool), {}
+
+    def step_host(self, actions_host, reward_host, done_host):
+        """End-to-end host-buffer step (walking Discrete): actions int32 [n] in (pinned) host memory are
+        copied to the device, the step runs, reward (float64 [n]) / done (uint8 [n]) are copied back
+        into the given host tensors and the stream is synchronised. Observations stay on the device."""
+        self._check_task()
+        if self._kind != _lib.WALKING_DISCRETE:
+            raise NotImplementedError('step_host is provided for the Discrete(18) action space')
+        for t, dt in ((actions_host, torch.int32), (reward_host, torch.float64), (done_host, torch.uint8)):
+            if t.device.type != 'cpu' or t.dtype != dt or not t.is_contiguous() or t.numel() != self.num_envs:
+                raise ValueError('step_host needs contiguous CPU tensors of dtype int32 / float64 / uint8, [n]')
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.iglu_step_walking_host(self._ctx, C.byref(self._st), actions_host.data_ptr(),
+                                                      self._actions_dev.data_ptr(), C.byref(self._ob),
+                                                      reward_host.data_ptr(), done_host.data_ptr(),
+                                                      self._stream()))
+            self._count()
+        return reward_host, done_host
+
+    # ------------------------------------------------------------------ state views (in place)
+    @property
+    def grid(self):
+        """int8 [n, 9, 11, 11] view of the resident voxel state (env.grid)."""
+        return self._grid[:, :_lib.CELLS].view(self.num_envs, 9, 11, 11)
+
+    @property
+    def target_grid(self):
+        return self._target[:, :_lib.CELLS].view(self.num_envs, 9, 11, 11)
+
+    @property
+    def starting_grid(self):
+        return self._init[:, :_lib.CELLS].view(self.num_envs, 9, 11, 11)
+
+    @property
+    def position(self):
+        return self._pose[0:3].t()
+
+    @property
+    def rotation(self):
+        """(yaw, pitch) per env, fp64."""
+        return self._pose[3:5].t()
+
+    @property
+    def dy(self):
+        return self._pose[5]
+
+    @property
+    def inventory(self):
+        w = self._istate[0:3].t().contiguous().view(torch.int16)
+        return w.view(self.num_envs, 6).to(torch.int32)
+
+    @property
+    def active_block(self):
+        return self._istate[3] & 0xFF
+
+    @property
+    def time_int_steps(self):
+        return (self._istate[3] >> 8) & 0xFF
+
+    @property
+    def error_flags(self):
+        """1 where the reference would have raised ValueError('Bad inventory id') (world.py:354-355)."""
+        return (self._istate[3] >> 24) & 0xFF
+
+    @property
+    def step_no(self):
+        return self._istate[4]
+
+    @property
+    def max_int(self):
+        """_synthetic_task.max_int per env."""
+        return self._istate[6]
+
+    @property
+    def target_size(self):
+        return self._tmeta[1]
+
+    def set_agent_state(self, env_idx, position=None, rotation=None, dy=None, time_int_steps=None,
+                        active_block=None):
+        """Overwrites carried agent state (tests / checkpoint restore)."""
+        i = int(env_idx)
+        if position is not None:
+            self._pose[0:3, i] = torch.as_tensor(position, dtype=torch.float64)
+        if rotation is not None:
+            self._pose[3:5, i] = torch.as_tensor(rotation, dtype=torch.float64)
+        if dy is not None:
+            self._pose[5, i] = float(dy)
+        w3 = int(self._istate[3, i])
+        if time_int_steps is not None:
+            w3 = (w3 & ~0xFF00) | (int(time_int_steps) << 8)
+        if active_block is not None:
+            w3 = (w3 & ~0xFF) | int(active_block)
+        self._istate[3, i] = w3
+
+    def state_dict(self):
+        keys = ('_grid', '_init', '_target', '_pose', '_init_pose', '_istate', '_tlist', '_trect', '_tmeta')
+        return {k[1:]: getattr(self, k).clone() for k in keys}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            getattr(self, '_' + k).copy_(v)
+        self._tasks_set = True
+
+
+def make_vec(num_envs, device='cuda', **kwargs):
+    """Batched counterpart of gym.make('IGLUGridworld-v0', ...) (reference env.py:333-362)."""
+    kwargs.pop('size_reward', None)
+    kwargs.pop('render_size', None)
+    kwargs.pop('name', None)
+    kwargs.pop('fake', None)
+    return IGLUVecEnv(num_envs, device=device, **kwargs)
+
+
+def max_intersection(grids, targets, full_grids=None, invariant=True, return_argmax=False, device='cuda'):
+    """Task(target, full_grid=full, invariant=invariant).maximal_intersection(grid) for a batch of pairs
+    (reference gridworld/tasks/task.py:9-72, 147-161), on the GPU. Inputs: int8-convertible
+    [k, 9, 11, 11]. Returns int32 [k] (and int32 [k, 3] = (dx, dz, rot) like argmax_intersection)."""
+    dev = _require_cuda(device)
+    L = _lib.load()
+    g = torch.as_tensor(grids)
+    k = g.shape[0] if g.dim() == 4 else 1
+
+    def prep(x):
+        if x is None:
+            return None
+        return torch.as_tensor(x).to(device=dev, dtype=torch.int8).reshape(k, _lib.CELLS).contiguous()
+
+    g, t, f = prep(grids), prep(targets), prep(full_grids)
+    out = torch.zeros(k, dtype=torch.int32, device=dev)
+    arg = torch.zeros(k, 3, dtype=torch.int32, device=dev) if return_argmax else None
+    with torch.cuda.device(dev):
+        _lib.check(L.iglu_max_intersection(g.data_ptr(), t.data_ptr(), None if f is None else f.data_ptr(),
+                                           int(bool(invariant)), out.data_ptr(),
+                                           None if arg is None else arg.data_ptr(), k,
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return (out, arg) if return_argmax else out

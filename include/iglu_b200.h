@@ -1,0 +1,173 @@
+/*
+ * iglu_b200.h -- C ABI of the B200-native IGLU Gridworld step path.
+ *
+ * The reference (iglu-contest/gridworld) is pure Python and has no FFI: its boundary for
+ * this path is the gym surface GridWorld.set_task / reset / step (reference
+ * gridworld/env.py:155-166, 206-261, 268-303) which calls World.step
+ * (gridworld/core/world.py:434-456) and Task.step_intersection / maximal_intersection
+ * (gridworld/tasks/task.py:103-119, 147-161).  This header is the C boundary a maintainer
+ * binds with ctypes directly under that surface; each entry point
+ * names the reference interface it replaces.
+ *
+ * Conventions
+ *  - Every pointer in iglu_state / iglu_obs and every array argument is DEVICE memory owned by
+ *    the caller (PyTorch hands the tensors out) unless the name ends in _host.  The library
+ *    allocates nothing persistent except the small iglu_ctx (config copy + trig tables).
+ *  - All work is enqueued on the caller's stream (a cudaStream_t passed as void*); device-
+ *    buffer entry points never synchronise, so they are CUDA-graph capturable.  *_host entry
+ *    points copy host<->device on that stream and synchronise it before returning.
+ *  - Return value: IGLU_OK (0) or a negative iglu_status; iglu_strerror() describes it.
+ *  - Grids are int8, cell (y, x, z) of env i at  i * IGLU_GRID_STRIDE + y*121 + x*11 + z
+ *    (dense index = [y+1, x+5, z+5] of the world block (x, y, z), reference env.py:136-142);
+ *    IGLU_GRID_STRIDE = 1104 pads the 1089 cells to a 16-byte multiple (pad bytes are zero).
+ *  - Arrays declared [k][n] are structure-of-arrays: component c of env i at  c * n + i.
+ */
+#ifndef IGLU_B200_H
+#define IGLU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGLU_ABI_VERSION 1
+#define IGLU_CELLS 1089       /* 9 * 11 * 11, reference tasks/task.py:3-5 */
+#define IGLU_GRID_STRIDE 1104 /* bytes between consecutive envs in int8 grid state */
+#define IGLU_TLIST_MAX 1096   /* max entries (uint16) per env in the target block list */
+
+typedef enum iglu_status {
+    IGLU_OK = 0,
+    IGLU_ERR_INVALID_ARG = -1,
+    IGLU_ERR_CUDA = -2,
+    IGLU_ERR_NO_TASK = -3,   /* reference env.py:199-201, 271-275 ValueError('Task is not initialized! ...') */
+    IGLU_ERR_UNSUPPORTED = -4
+} iglu_status;
+
+/* reference env.py:56-78 action spaces */
+typedef enum iglu_action_space {
+    IGLU_WALKING_DISCRETE = 0, /* Discrete(18), world.py:360-394 */
+    IGLU_FLYING = 1,           /* Dict(movement, camera, inventory, placement), world.py:416-432 */
+    IGLU_WALKING_DICT = 2      /* Dict of buttons + camera (discretize=False), world.py:396-414 */
+} iglu_action_space;
+
+typedef enum iglu_reward_mode {
+    IGLU_REWARD_ON_CHANGE = 0, /* evaluate maximal_intersection only when the block count changed
+                                  (the reference's gate, task.py:110-112) */
+    IGLU_REWARD_EVERY_STEP = 1 /* evaluate it on every step (BASELINE config 2); the result is still
+                                  committed only when the gate fires, so outputs are identical */
+} iglu_reward_mode;
+
+/* kwargs of the reference's create_env / GridWorld.__init__ (env.py:27-31, 333-338) that reach
+ * the step path, plus the batched additions (auto_reset, reward_mode, write_grid_obs). */
+typedef struct iglu_config {
+    int32_t action_space;       /* iglu_action_space */
+    int32_t select_and_place;   /* env.py:28 / world.py:444-446 */
+    int32_t max_steps;          /* env.py:28, 292 */
+    int32_t auto_reset;         /* 1: an env whose previous step returned done is reset (env.py:206-261)
+                                   at the start of the next step call, then stepped */
+    int32_t reward_mode;        /* iglu_reward_mode */
+    int32_t write_grid_obs;     /* 1: materialise obs['grid'] int32[n,9,11,11] every step (env.py:288) */
+    int32_t tlist_cap;          /* entries per env in iglu_state.tlist (multiple of 8, <= IGLU_TLIST_MAX) */
+    int32_t reserved;
+    double right_placement_scale; /* env.py:29, 296 */
+    double wrong_placement_scale; /* env.py:29, 294 */
+} iglu_config;
+
+/* Per-env state resident in HBM (reference: Agent world.py:8-29, GridWorld env.py:32-55,
+ * the synthetic Task env.py:227-232 / task.py:34-45). */
+typedef struct iglu_state {
+    int64_t n;
+    int8_t *grid;      /* [n][IGLU_GRID_STRIDE]  env.grid */
+    int8_t *init;      /* [n][IGLU_GRID_STRIDE]  dense starting grid (_synthetic_init_grid) */
+    int8_t *target;    /* [n][IGLU_GRID_STRIDE]  task.target_grid */
+    double *pose;      /* [6][n]  x, y, z, yaw, pitch, dy  (agent.position, rotation, dy) */
+    double *init_pose; /* [5][n]  x, y, z, yaw, pitch      (initial_position / initial_rotation) */
+    int32_t *istate;   /* [8][n]  w0..w2: inventory 6 x int16; w3: active | tis<<8 | done_prev<<16 | err<<24;
+                                  w4: step_no; w5: nnz(grid - init) (task.prev_grid_size); w6: max_int;
+                                  w7: reserved */
+    uint16_t *tlist;   /* [n][tlist_cap]  non-zero cells of (target - init), rotation 0:
+                                  y | x<<4 | z<<8 | (value & 15)<<12 */
+    int8_t *trect;     /* [n][16]  per rotation r: dx_lo, dx_hi, dz_lo, dz_hi of the admissible shifts
+                                  (task.py:57-72; always a rectangle) */
+    int32_t *tmeta;    /* [8][n]  w0: number of tlist entries; w1: target_size (task.py:35);
+                                  w2..w4: inventory after reset, 6 x int16 (env.py:243-246);
+                                  w5: 1 if the starting grid is non-empty; w6: 1 once a task is set; w7: reserved */
+} iglu_state;
+
+/* Observation / result buffers (reference env.py:283-303). They persist between steps and are
+ * overwritten in place; a policy can read them directly. target_grid is written by
+ * iglu_set_tasks (it never changes between steps). Any pointer may be NULL = not wanted,
+ * except reward and done. */
+typedef struct iglu_obs {
+    int32_t *grid;        /* [n][1089] int32   obs['grid'] */
+    int32_t *target_grid; /* [n][1089] int32   obs['target_grid'] (target_in_obs=True) */
+    float *agent_pos;     /* [n][5]  x, y, z, pitch, yaw   obs['agentPos'] */
+    float *inventory;     /* [n][6]                        obs['inventory'] */
+    float *compass;       /* [n][1]  yaw - 180             obs['compass'] */
+    double *reward;       /* [n]     env.py:293-296 (fp64 so that +-0.1 * k is exact as in Python) */
+    uint8_t *done;        /* [n]     env.py:292 */
+} iglu_obs;
+
+typedef struct iglu_ctx iglu_ctx;
+
+int iglu_abi_version(void);
+const char *iglu_strerror(int status);
+
+/* GridWorld.__init__ (env.py:27-115): copies the config, builds the libm trig tables. */
+int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out);
+void iglu_ctx_destroy(iglu_ctx *ctx);
+
+/* GridWorld.set_task / initialize_world (env.py:155-193) + Task.__init__ of the synthetic task
+ * (env.py:227-232, task.py:9-72) for `count` envs.
+ *   target, start : device int8 [count][1089] dense (start may be NULL = empty starting grid [])
+ *   init_pose     : device double [count][5] (x, y, z, yaw, pitch) or NULL = (0,0,0,0,0)
+ *   env_idx       : device int32 [count] destination env of each row, or NULL = rows 0..count-1
+ * Fills state.target/init/tlist/trect/tmeta (+ obs.target_grid). Does NOT reset; call iglu_reset. */
+int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const int8_t *target,
+                   const int8_t *start, const double *init_pose, const int32_t *env_idx, int64_t count,
+                   void *stream);
+
+/* GridWorld.reset (env.py:206-261) for the envs with mask[i] != 0 (mask NULL = all): grid <- start,
+ * pose <- initial pose, inventory, step_no, task bookkeeping; writes the reset observation
+ * (agentPos and compass are zeros there, env.py:249-254). agent.dy / time_int_steps / active_block
+ * are NOT reset (reference behaviour); pass hard != 0 to also reset those (fresh-env state). */
+int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const uint8_t *mask, int hard,
+               void *stream);
+
+/* GridWorld.step (env.py:268-303) for all n envs, Discrete(18) actions (device int32 [n]). */
+int iglu_step_walking(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions, const iglu_obs *obs,
+                      void *stream);
+
+/* GridWorld.step with the flying Dict action (env.py:71-78): movement f32 [n][3], camera f32 [n][2],
+ * inventory int32 [n] (0 = none), placement int32 [n] (0 none, 1 place, 2 break). */
+int iglu_step_flying(iglu_ctx *ctx, const iglu_state *st, const float *movement, const float *camera,
+                     const int32_t *inventory, const int32_t *placement, const iglu_obs *obs, void *stream);
+
+/* GridWorld.step with the walking Dict action (env.py:60-70, discretize=False): buttons int32 [n][8] =
+ * forward, back, left, right, jump, attack, use, hotbar; camera f32 [n][2]. */
+int iglu_step_walking_dict(iglu_ctx *ctx, const iglu_state *st, const int32_t *buttons, const float *camera,
+                           const iglu_obs *obs, void *stream);
+
+/* Host-buffer form of iglu_step_walking: actions_host int32 [n] (pinned or pageable) is copied to the
+ * device scratch `actions_dev`, the step runs, reward/done are copied back into reward_host /
+ * done_host, and the stream is synchronised. This is the call bench.py's e2e number times. */
+int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
+                           int32_t *actions_dev, const iglu_obs *obs, double *reward_host, uint8_t *done_host,
+                           void *stream);
+
+/* Stateless Task(target, full_grid=full, invariant=invariant).maximal_intersection(grid)
+ * (task.py:9-72, 147-161) for `count` independent pairs (BASELINE config 4).
+ *   grids, targets, fulls : device int8 [count][1089] dense (fulls may be NULL)
+ *   out                   : device int32 [count]
+ *   argmax                : device int32 [count][3] = (dx, dz, rot) of task.py:121-136, or NULL */
+int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int invariant,
+                          int32_t *out, int32_t *argmax, int64_t count, void *stream);
+
+/* Number of kernels the last step call on this ctx launched (bench.py's gpu_launches claim). */
+int iglu_last_launch_count(const iglu_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IGLU_B200_H */

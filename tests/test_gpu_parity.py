@@ -1,0 +1,399 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`). They call the CUDA path through the C ABI
+(via gridworld_b200's ctypes binding) and compare with (a) the golden vectors recorded from the
+executed reference and (b) the C oracle on the same seeded inputs.
+
+Bars: grids / inventories / rewards / done / step counters / max_int bit-exact; pose (fp64 position,
+rotation, dy) bit-exact on the Discrete(18) path (libm trig table), within 1e-6 on paths that use the
+device sincos/atan2 (flying, non-multiple-of-5 angles), as BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests import golden_io as G
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL = 1e-6
+
+
+def _make(tr, kind, n=1, **kw):
+    import gridworld_b200 as gw
+    if kind == 'flying':
+        space, disc = 'flying', True
+    elif kind == 'dict':
+        space, disc = 'walking', False
+    else:
+        space, disc = 'walking', True
+    return gw.make_vec(n, action_space=space, discretize=disc, select_and_place=tr['select_and_place'],
+                       max_steps=tr['max_steps'], right_placement_scale=tr['right_scale'],
+                       wrong_placement_scale=tr['wrong_scale'], auto_reset=True, **kw)
+
+
+def _replay_gpu(tr, kind, reward_mode='on_change', exact_pose=True):
+    env = _make(tr, kind, reward_mode=reward_mode)
+    dev = env.device
+    env.set_tasks(tr['target'][None], tr['start'][None], tr['pose'][None])
+    T = tr['n']
+    a = tr['actions']
+    if kind == 'walking':
+        acts = torch.as_tensor(a['actions'], device=dev).view(T, 1)
+    elif kind == 'flying':
+        mv = torch.as_tensor(a['movement'], device=dev).view(T, 1, 3)
+        cam = torch.as_tensor(a['camera'], device=dev).view(T, 1, 2)
+        inv = torch.as_tensor(a['inv'], device=dev).view(T, 1)
+        pl = torch.as_tensor(a['placement'], device=dev).view(T, 1)
+    else:
+        bt = torch.as_tensor(a['buttons'], device=dev).view(T, 1, 8)
+        cam = torch.as_tensor(a['camera'], device=dev).view(T, 1, 2)
+    H = dict(pose=torch.zeros(T, 6, dtype=torch.float64, device=dev),
+             ist=torch.zeros(T, 8, dtype=torch.int32, device=dev),
+             reward=torch.zeros(T, dtype=torch.float64, device=dev),
+             done=torch.zeros(T, dtype=torch.uint8, device=dev),
+             grid=torch.zeros(T, 1089, dtype=torch.int8, device=dev),
+             ogrid=torch.zeros(T, 1089, dtype=torch.int32, device=dev),
+             apos=torch.zeros(T, 5, dtype=torch.float32, device=dev),
+             comp=torch.zeros(T, dtype=torch.float32, device=dev),
+             oinv=torch.zeros(T, 6, dtype=torch.float32, device=dev))
+    for t in range(T):
+        if kind == 'walking':
+            obs, r, d, _ = env.step(acts[t])
+        elif kind == 'flying':
+            obs, r, d, _ = env.step({'movement': mv[t], 'camera': cam[t], 'inventory': inv[t], 'placement': pl[t]})
+        else:
+            obs, r, d, _ = env.step((bt[t], cam[t]))
+        H['pose'][t] = env._pose[:, 0]
+        H['ist'][t] = env._istate[:, 0]
+        H['reward'][t] = r[0]
+        H['done'][t] = env._done[0]
+        H['grid'][t] = env.grid[0].reshape(-1)
+        H['ogrid'][t] = obs['grid'][0].reshape(-1)
+        H['apos'][t] = obs['agentPos'][0]
+        H['comp'][t] = obs['compass'][0, 0]
+        H['oinv'][t] = obs['inventory'][0]
+    H = {k: v.cpu().numpy() for k, v in H.items()}
+    nm = tr['name']
+    # integers first: they localise a divergence best
+    gold_grid = np.stack([G.grid_at(tr, t) for t in range(T)])
+    bad = np.nonzero((H['grid'] != gold_grid).any(axis=1))[0]
+    assert len(bad) == 0, f'{nm}: grid differs first at step {bad[0]}'
+    assert np.array_equal(H['ogrid'], gold_grid.astype(np.int32)), nm
+    inv16 = H['ist'][:, 0:3].copy().view(np.int16).reshape(T, 6).astype(np.int32)
+    assert np.array_equal(inv16, tr['inventory']), nm
+    assert np.array_equal(H['ist'][:, 3] & 0xFF, tr['active']), nm
+    assert np.array_equal((H['ist'][:, 3] >> 8) & 0xFF, tr['tis']), nm
+    assert np.array_equal(H['ist'][:, 4], tr['step_no']), nm
+    assert np.array_equal(H['ist'][:, 6], tr['max_int']), nm
+    assert np.array_equal(H['done'].astype(bool), tr['done']), nm
+    assert np.array_equal(H['reward'], tr['reward']), nm
+    gold_pose = np.concatenate([tr['pos'], tr['rot'], tr['dy'][:, None]], axis=1)
+    if exact_pose:
+        bad = np.nonzero((H['pose'] != gold_pose).any(axis=1))[0]
+        assert len(bad) == 0, f'{nm}: pose differs first at step {bad[0]}: {H["pose"][bad[0]]} vs {gold_pose[bad[0]]}'
+        assert np.array_equal(H['apos'], tr['agentPos']), nm
+        assert np.array_equal(H['comp'], tr['compass'][:, 0]), nm
+    else:
+        assert np.abs(H['pose'] - gold_pose).max() <= POSE_TOL, nm
+        assert np.abs(H['apos'] - tr['agentPos']).max() <= 1e-4, nm
+    assert np.array_equal(H['oinv'], tr['obs_inventory']), nm
+    return H
+
+
+@pytest.mark.parametrize('tr', G.walking_traces(), ids=lambda t: t['name'])
+def test_walking_golden(tr):
+    _replay_gpu(tr, 'walking', exact_pose=tr['name'] != 'odd_rotation')
+
+
+@pytest.mark.parametrize('tr', G.walking_traces()[-6:], ids=lambda t: t['name'])
+def test_walking_golden_reward_every_step(tr):
+    """Evaluating maximal_intersection on every step must not change any output."""
+    _replay_gpu(tr, 'walking', reward_mode='every_step')
+
+
+@pytest.mark.parametrize('tr', G.flying_traces(), ids=lambda t: t['name'])
+def test_flying_golden(tr):
+    _replay_gpu(tr, 'flying', exact_pose=False)
+
+
+@pytest.mark.parametrize('tr', G.dict_traces(), ids=lambda t: t['name'])
+def test_walking_dict_golden(tr):
+    _replay_gpu(tr, 'dict', exact_pose=False)
+
+
+# ------------------------------------------------------------------------- reward kernel
+
+def test_reward_goals():
+    import gridworld_b200 as gw
+    z = G.load('goals.npz')
+    T = z['targets']
+    g1 = np.stack([np.rot90(t, k=-1, axes=(1, 2)) for t in T]).copy()
+    assert np.array_equal(gw.max_intersection(g1, T).cpu().numpy(), z['ka1'])
+    assert np.array_equal(gw.max_intersection(T, T).cpu().numpy(), z['target_size'])
+    for j in range(z['grids'].shape[1]):
+        mi, arg = gw.max_intersection(z['grids'][:, j], T, return_argmax=True)
+        assert np.array_equal(mi.cpu().numpy(), z['max_int'][:, j])
+        assert np.array_equal(arg.cpu().numpy(), z['argmax'][:, j])
+
+
+def test_reward_pairs_golden():
+    import gridworld_b200 as gw
+    z = G.load('reward_pairs.npz')
+    for inv in (True, False):
+        for hf in (True, False):
+            sel = np.nonzero((z['invariant'] == inv) & (z['has_full'] == hf))[0]
+            if len(sel) == 0:
+                continue
+            mi, arg = gw.max_intersection(z['grids'][sel], z['targets'][sel], z['fulls'][sel] if hf else None,
+                                          invariant=inv, return_argmax=True)
+            assert np.array_equal(mi.cpu().numpy(), z['max_int'][sel]), (inv, hf)
+            assert np.array_equal(arg.cpu().numpy(), z['argmax'][sel]), (inv, hf)
+
+
+def _synth(rng, n, rho, support, classes=6):
+    u = rng.random_sample((n, 9, 11, 11))
+    t = np.where(u < rho, rng.randint(1, classes + 1, (n, 9, 11, 11)), 0).astype(np.int8)
+    if support == 'compact':
+        m = np.zeros((9, 11, 11), bool)
+        m[:5, 3:8, 3:8] = True
+        t = np.where(m[None], t, 0).astype(np.int8)
+    return t
+
+
+@pytest.mark.parametrize('rho', [0.05, 0.2, 0.5])
+@pytest.mark.parametrize('support', ['full', 'compact'])
+def test_reward_vs_oracle_random(rho, support):
+    """config-4 style sweep at a size the C oracle finishes in seconds."""
+    import gridworld_b200 as gw
+    rng = np.random.RandomState(int(rho * 100) + (7 if support == 'full' else 13))
+    n = 3000
+    T = _synth(rng, n, rho, support)
+    Gd = _synth(rng, n, rho, support)
+    # half of the grids: the target itself rotated by k and with 10% noise (high scores)
+    for i in range(0, n, 2):
+        g = np.rot90(T[i], k=-rng.randint(4), axes=(1, 2)).copy()
+        noise = rng.random_sample(g.shape) < 0.1
+        Gd[i] = np.where(noise, Gd[i], g)
+    want, warg = O.max_intersection(Gd, T, threads=8, return_argmax=True)
+    got, garg = gw.max_intersection(Gd, T, return_argmax=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(garg.cpu().numpy(), warg)
+    # difference-grid classes (-6..6) as produced by env.py:230/290
+    S = _synth(rng, n, rho / 2, support)
+    Td = (T.astype(np.int16) - S).astype(np.int8)
+    Gdd = (Gd.astype(np.int16) - S).astype(np.int8)
+    want = O.max_intersection(Gdd, Td, threads=8)
+    got = gw.max_intersection(Gdd, Td)
+    assert np.array_equal(got.cpu().numpy(), want)
+    # full_grid rectangles (clipping path) and invariant=False
+    F = np.where(T != 0, T, _synth(rng, n, 0.02, 'full')).astype(np.int8)
+    want = O.max_intersection(Gd[:500], T[:500], F[:500], threads=8)
+    got = gw.max_intersection(Gd[:500], T[:500], F[:500])
+    assert np.array_equal(got.cpu().numpy(), want)
+    Z = np.zeros_like(T[:200])
+    want = O.max_intersection(Gd[:200], T[:200], Z, threads=8)
+    got = gw.max_intersection(Gd[:200], T[:200], Z)
+    assert np.array_equal(got.cpu().numpy(), want)
+    want = O.max_intersection(Gd[:500], T[:500], invariant=False, threads=8)
+    got = gw.max_intersection(Gd[:500], T[:500], invariant=False)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_reward_properties_full_size():
+    """1M pairs (BASELINE config 4 size): size-independent properties of maximal_intersection."""
+    import gridworld_b200 as gw
+    n = 1_000_000
+    gen = torch.Generator(device='cuda').manual_seed(1234)
+    u = torch.rand(n, 9, 11, 11, device='cuda', generator=gen)
+    col = torch.randint(1, 7, (n, 9, 11, 11), device='cuda', generator=gen, dtype=torch.int8)
+    T = torch.where(u < 0.2, col, torch.zeros_like(col))
+    size = (T != 0).flatten(1).sum(1).to(torch.int32)
+    # (1) a grid equal to the target scores target_size; (2) so does any y-rotation of it
+    assert torch.equal(gw.max_intersection(T, T), size)
+    R = torch.rot90(T, k=1, dims=(2, 3)).contiguous()
+    assert torch.equal(gw.max_intersection(R, T), size)
+    # (3) bounded by target_size and by the grid's block count; (4) empty grid scores 0
+    Gd = torch.where(torch.rand(n, 9, 11, 11, device='cuda', generator=gen) < 0.2, col.flip(0), torch.zeros_like(col))
+    mi = gw.max_intersection(Gd, T)
+    assert bool((mi <= size).all()) and bool((mi >= 0).all())
+    assert bool((mi <= (Gd != 0).flatten(1).sum(1)).all())
+    assert int(gw.max_intersection(torch.zeros_like(T[:1000]), T[:1000]).abs().sum()) == 0
+    # (5) compact targets: translating the grid by an admissible shift keeps the score
+    m = torch.zeros(9, 11, 11, dtype=torch.bool, device='cuda')
+    m[:5, 3:8, 3:8] = True
+    Tc = torch.where(m, T, torch.zeros_like(T))[:200_000]
+    Gc = torch.where(m, Gd, torch.zeros_like(Gd))[:200_000]
+    base = gw.max_intersection(Gc, Tc)
+    shifted = torch.roll(Gc, shifts=(2, -3), dims=(2, 3))  # support stays inside the zone: no wrap
+    assert torch.equal(gw.max_intersection(shifted, Tc), base)
+
+
+# ------------------------------------------------------------------------- batched env vs the C oracle
+
+def _tasks(rng, n):
+    T = _synth(rng, n, 0.12, 'compact')
+    S = _synth(rng, n, 0.04, 'compact')
+    S[:, 2:] = 0
+    S[:, :, 5, 5] = 0
+    S[::3] = 0  # a third of the envs start empty
+    poses = np.zeros((n, 5))
+    poses[::5, 0] = rng.randint(-8, 9, len(poses[::5])) * 0.25
+    poses[::5, 2] = rng.randint(-8, 9, len(poses[::5])) * 0.25
+    poses[::5, 3] = rng.randint(0, 72, len(poses[::5])) * 5.0
+    poses[::7, 4] = rng.randint(-18, 19, len(poses[::7])) * 5.0
+    return T, S, poses
+
+
+@pytest.mark.parametrize('reward_mode', ['on_change', 'every_step'])
+def test_walking_batch_vs_oracle(reward_mode):
+    import gridworld_b200 as gw
+    n, steps = 2048, 400
+    rng = np.random.RandomState(3)
+    T, S, poses = _tasks(rng, n)
+    env = gw.make_vec(n, action_space='walking', max_steps=100, auto_reset=True, reward_mode=reward_mode)
+    env.set_tasks(T, S, poses)
+    orc = O.OracleBatch(n, 'walking', max_steps=100, threads=8)
+    orc.set_tasks(T, S, poses)
+    p = np.array([1, 5, 2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+    for t in range(steps):
+        a = rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+        _, r, d, _ = env.step(a)
+        ro, do = orc.step_walking(a, auto_reset=True)
+        assert np.array_equal(r.cpu().numpy(), ro), t
+        assert np.array_equal(d.cpu().numpy(), do), t
+        if t % 25 == 24 or t == steps - 1:
+            s = orc.state()
+            assert np.array_equal(env.grid.cpu().numpy(), s['grid']), t
+            assert np.array_equal(env.position.cpu().numpy(), s['pos']), t
+            assert np.array_equal(env.rotation.cpu().numpy(), s['rot']), t
+            assert np.array_equal(env.dy.cpu().numpy(), s['dy']), t
+            assert np.array_equal(env.inventory.cpu().numpy(), s['inventory']), t
+            assert np.array_equal(env.max_int.cpu().numpy(), s['max_int']), t
+            assert np.array_equal(env.step_no.cpu().numpy(), s['step_no']), t
+            assert np.array_equal(env.time_int_steps.cpu().numpy(), s['tis']), t
+            o = orc.obs()
+            ob = env.observation()
+            assert np.array_equal(ob['grid'].cpu().numpy(), o['grid']), t
+            assert np.array_equal(ob['agentPos'].cpu().numpy(), o['agentPos']), t
+            assert np.array_equal(ob['compass'].cpu().numpy(), o['compass']), t
+            assert np.array_equal(ob['inventory'].cpu().numpy(), o['inventory']), t
+
+
+def test_flying_batch_vs_oracle():
+    import gridworld_b200 as gw
+    n, steps = 1024, 300
+    rng = np.random.RandomState(5)
+    T, S, poses = _tasks(rng, n)
+    env = gw.make_vec(n, action_space='flying', max_steps=120, auto_reset=True, target_in_obs=True)
+    env.set_tasks(T, S, poses)
+    orc = O.OracleBatch(n, 'flying', max_steps=120, threads=8)
+    orc.set_tasks(T, S, poses)
+    bad_envs = np.zeros(n, bool)  # envs where a measure-zero rounding flip made the traces diverge
+    for t in range(steps):
+        mv = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        mv[rng.random_sample((n, 3)) < 0.3] = 0
+        cam = rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+        inv = rng.randint(0, 7, n).astype(np.int32)
+        pl = rng.randint(0, 3, n).astype(np.int32)
+        obs, r, d, _ = env.step({'movement': mv, 'camera': cam, 'inventory': inv, 'placement': pl})
+        ro, do = orc.step_flying(mv, cam, inv, pl, auto_reset=True)
+        s = orc.state()
+        pos_err = np.abs(env.position.cpu().numpy() - s['pos']).max(axis=1)
+        grid_bad = (env.grid.cpu().numpy() != s['grid']).reshape(n, -1).any(axis=1)
+        bad_envs |= (pos_err > POSE_TOL) | grid_bad
+        ok = ~bad_envs
+        assert np.array_equal(r.cpu().numpy()[ok], ro[ok]), t
+        assert np.array_equal(d.cpu().numpy()[ok], do[ok]), t
+    # device sincos/atan2 differ from glibc by <= 2 ulp: trajectories agree to 1e-6 except where a
+    # discontinuity (round-half, zone gate) flips; that must stay a vanishing fraction
+    assert bad_envs.mean() <= 0.002, bad_envs.sum()
+    assert np.array_equal(obs['target_grid'].cpu().numpy(), T.astype(np.int32))
+
+
+def test_sharding_is_concatenation():
+    """Multi-GPU layout = contiguous env blocks with no exchange: stepping two half-size envs must equal
+    the full-size env (the indexing test of SURVEY 8(e)); uses one device."""
+    import gridworld_b200 as gw
+    n = 4096
+    rng = np.random.RandomState(9)
+    T, S, poses = _tasks(rng, n)
+    full = gw.make_vec(n, max_steps=60, reward_mode='every_step')
+    full.set_tasks(T, S, poses)
+    h = n // 2
+    parts = [gw.make_vec(h, max_steps=60, reward_mode='every_step') for _ in range(2)]
+    parts[0].set_tasks(T[:h], S[:h], poses[:h])
+    parts[1].set_tasks(T[h:], S[h:], poses[h:])
+    for t in range(150):
+        a = torch.as_tensor(rng.randint(0, 18, n).astype(np.int32), device='cuda')
+        _, r, d, _ = full.step(a)
+        r0 = parts[0].step(a[:h])[1]
+        r1 = parts[1].step(a[h:])[1]
+        assert torch.equal(r, torch.cat([r0, r1])), t
+    assert torch.equal(full.grid, torch.cat([parts[0].grid, parts[1].grid]))
+    assert torch.equal(full._pose, torch.cat([parts[0]._pose, parts[1]._pose], dim=1))
+
+
+def test_full_size_invariants():
+    """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
+    import gridworld_b200 as gw
+    n = 65536
+    rng = np.random.RandomState(1)
+    T = _synth(rng, n, 0.2, 'compact')
+    env = gw.make_vec(n, max_steps=250, reward_mode='every_step')
+    env.set_tasks(T)
+    dev = env.device
+    total_r = torch.zeros(n, dtype=torch.float64, device=dev)
+    for t in range(300):
+        a = torch.randint(0, 18, (n,), device=dev, dtype=torch.int32)
+        obs, r, d, _ = env.step(a)
+        total_r += r
+        if t % 50 == 49:
+            g = env.grid
+            nblk = (g != 0).flatten(1).sum(1)
+            inv = env.inventory
+            # blocks in the world + blocks in the inventory is conserved (start empty: 120)
+            assert bool(((inv.sum(1) + nblk) == 120).all())
+            # per colour too
+            for c in range(1, 7):
+                assert bool((((g == c).flatten(1).sum(1)) + inv[:, c - 1] == 20).all())
+            assert torch.equal(obs['grid'], g.to(torch.int32))
+            assert bool((env.max_int <= env.target_size).all())
+            # cached max_int equals a fresh stateless evaluation (empty start: never stale)
+            assert torch.equal(gw.max_intersection(g, T).to(torch.int32), env.max_int)
+            p = env.position
+            assert bool((p[:, 0].abs() <= 7.25).all() and (p[:, 2].abs() <= 7.25).all())
+            assert bool((env.step_no >= 1).all() and (env.step_no <= 250).all())
+    assert int(env.error_flags.sum()) == 0
+
+
+def test_dropin_gym_surface():
+    """gym.make('IGLUGridworld-v0', ...) surface at N = 1 against the golden known-answer trace."""
+    import gridworld_b200 as gw
+    tr = [t for t in G.walking_traces() if t['name'] == 'ka_physics'][0]
+    env = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False,
+                  select_and_place=False, action_space='walking')
+    with pytest.raises(ValueError):
+        env.step(0)
+    sparse = [(0, -1, -2, 1), (0, 0, -2, 1)]
+    env.set_task(gw.Task('', gw.Tasks.to_dense(sparse), starting_grid=[]))
+    obs = env.reset()
+    assert obs['agentPos'].tolist() == [0, 0, 0, 0, 0] and obs['grid'].dtype == np.int32
+    assert obs['grid'].shape == (9, 11, 11) and obs['inventory'].tolist() == [20.] * 6
+    for t, a in enumerate(tr['actions']['actions']):
+        obs, r, done, info = env.step(int(a))
+        assert r == tr['reward'][t] and done == bool(tr['done'][t]) and info == {}
+        assert list(env.agent.position) == tr['pos'][t].tolist()
+        assert np.array_equal(obs['agentPos'], tr['agentPos'][t])
+        assert np.array_equal(obs['grid'].reshape(-1), G.grid_at(tr, t).astype(np.int32))
+    assert env.action_space.n == 18
+    assert set(env.observation_space.spaces) == {'inventory', 'compass', 'dialog', 'agentPos', 'grid'}
+    # flying + target_in_obs surface
+    fenv = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=True, action_space='flying',
+                   target_in_obs=True)
+    fenv.set_task(gw.Task('hello', gw.Tasks.to_dense(sparse), starting_grid=[(1, -1, 1, 3)]))
+    obs = fenv.reset()
+    assert obs['dialog'] == 'hello' and obs['inventory'].tolist() == [20, 20, 19, 20, 20, 20]
+    assert obs['target_grid'][0, 5, 3] == 1 and obs['grid'][0, 6, 6] == 3
+    obs, r, done, _ = fenv.step({'movement': np.array([1, 0, 0], np.float32), 'camera': np.zeros(2, np.float32),
+                                 'inventory': 0, 'placement': 0})
+    assert abs(fenv.agent.position[2] - 0.75) < 1e-12  # strafe[0] > 0 moves +z at 15 units/s

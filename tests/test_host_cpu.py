@@ -1,0 +1,105 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol of include/iglu_b200.h,
+the host layer fails loudly without a CUDA device, host task objects follow the reference's
+Task.__init__ products, ctypes struct layouts match the header."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import golden_io as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gridworld_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, 'include', 'iglu_b200.h')).read()
+    declared = set(re.findall(r'\b(iglu_[a-z_]+)\s*\(', header))
+    declared -= {'iglu_ctx'}
+    assert declared == set(_lib.EXPORTS)
+    for sym in declared:
+        assert getattr(lib, sym) is not None
+    assert lib.iglu_abi_version() == 1
+    assert lib.iglu_strerror(0) == b'ok'
+    assert b'Task is not initialized' in lib.iglu_strerror(-3)
+
+
+def test_struct_layouts_match_header():
+    from gridworld_b200 import _lib
+    assert C.sizeof(_lib.Config) == 8 * 4 + 2 * 8
+    assert C.sizeof(_lib.State) == 8 * 10
+    assert C.sizeof(_lib.Obs) == 8 * 7
+    assert _lib.GRID_STRIDE % 16 == 0 and _lib.GRID_STRIDE >= _lib.CELLS
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    import gridworld_b200 as gw
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        gw.make_vec(4)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        gw.make('IGLUGridworld-v0', render=False)
+    with pytest.raises(RuntimeError):
+        gw.max_intersection(np.zeros((1, 9, 11, 11)), np.zeros((1, 9, 11, 11)))
+    with pytest.raises(NotImplementedError):
+        gw.GridWorld(render=True)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, 'gridworld_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, re.M), f
+                assert 'libiglu_oracle' not in src and 'iglu_oracle' not in src, f
+
+
+def test_host_task_matches_reference_products():
+    """Task.admissible / target_grids (closed forms) against the reference's Task.__init__ outputs."""
+    import gridworld_b200 as gw
+    z = G.load('goals.npz')
+    for i in range(0, len(z['targets']), 7):
+        t = gw.Task('', z['targets'][i].astype(np.int32))
+        assert [len(a) for a in t.admissible] == z['n_adm'][i].tolist()
+        assert t.target_size == z['target_size'][i]
+    zp = G.load('reward_pairs.npz')
+    for i in range(len(zp['max_int'])):
+        full = zp['fulls'][i].astype(np.int32) if zp['has_full'][i] else None
+        t = gw.Task('', zp['targets'][i].astype(np.int32), full_grid=full, invariant=bool(zp['invariant'][i]))
+        n_adm = [len(a) for a in t.admissible]
+        assert n_adm + [0] * (4 - len(n_adm)) == zp['n_adm'][i].tolist()
+    t = gw.Task('', z['targets'][0].astype(np.int32))
+    r1 = t.target_grids[1]
+    for x in range(11):
+        for zz in range(11):
+            assert np.array_equal(r1[:, zz, 10 - x], z['targets'][0][:, x, zz])  # task.py:52-53
+
+
+def test_to_dense_to_sparse():
+    import gridworld_b200 as gw
+    d = gw.Tasks.to_dense([(0, -1, -2, 1), (5, 7, 5, 6)])
+    assert d.shape == (9, 11, 11) and d[0, 5, 3] == 1 and d[8, 10, 10] == 6
+    sp = gw.Tasks.to_sparse(np.asarray(d))
+    assert sorted(sp) == sorted([(0 - 5, 5 - 1, 3 - 5, 1), (8 - 5, 10 - 1, 10 - 5, 6)])  # axis-0-as-x quirk
+    np.random.seed(0)
+    rt = gw.RandomTasks(max_blocks=4, height_levels=2, num_colors=3)
+    assert rt.target_size == 8 and rt.target_grid.shape == (9, 11, 11)
+
+
+def test_spaces():
+    from gridworld_b200.vec_env import make_action_space, make_observation_space
+    assert make_action_space('walking', True).n == 18
+    fl = make_action_space('flying', True)
+    assert set(fl.spaces) == {'movement', 'camera', 'inventory', 'placement'}
+    wd = make_action_space('walking', False)
+    assert set(wd.spaces) == {'forward', 'back', 'left', 'right', 'jump', 'attack', 'use', 'camera', 'hotbar'}
+    ob = make_observation_space(True, True)
+    assert ob['grid'].shape == (9, 11, 11) and ob['grid'].dtype == np.int32
+    assert ob['agentPos'].shape == (5,) and ob['target_grid'].shape == (9, 11, 11)
+    assert fl.contains(fl.sample())
