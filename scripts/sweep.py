@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Throughput sweep (not the bench contract): step-path variants and the stateless reward kernel
+(BASELINE configs 2-4) timed with CUDA events. Prints one JSON object per line; copy into profiles/."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gridworld_b200 as gw  # noqa: E402
+from bench import synth_targets  # noqa: E402
+
+
+def time_steps(env, step_fn, K=300, W=20):
+    for t in range(W):
+        step_fn(t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        step_fn(W + t)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / K
+
+
+def walking(n, support, rho, reward_mode, inplace, K=300):
+    env = gw.make_vec(n, action_space='walking', max_steps=250, reward_mode=reward_mode, grid_obs=not inplace)
+    env.set_tasks(synth_targets(n, rho, support, 1235).cuda())
+    acts = torch.randint(0, 18, (64, n), device='cuda', dtype=torch.int32)
+    ms = time_steps(env, lambda t: env.step(acts[t % 64]), K=K)
+    return {'kind': 'walking', 'envs': n, 'support': support, 'rho': rho, 'reward_mode': reward_mode,
+            'inplace': inplace, 'ms_per_step': ms, 'env_steps_per_sec': n / ms * 1e3}
+
+
+def flying(n, K=200):
+    env = gw.make_vec(n, action_space='flying', max_steps=250, target_in_obs=True, reward_mode='on_change')
+    env.set_tasks(synth_targets(n, 0.2, 'compact', 1236).cuda())
+    mv = torch.rand(16, n, 3, device='cuda') * 2 - 1
+    cam = torch.rand(16, n, 2, device='cuda') * 10 - 5
+    inv = torch.randint(0, 7, (16, n), device='cuda', dtype=torch.int32)
+    pl = torch.randint(0, 3, (16, n), device='cuda', dtype=torch.int32)
+    ms = time_steps(env, lambda t: env.step({'movement': mv[t % 16], 'camera': cam[t % 16],
+                                             'inventory': inv[t % 16], 'placement': pl[t % 16]}), K=K)
+    return {'kind': 'flying+target_in_obs', 'envs': n, 'ms_per_step': ms, 'env_steps_per_sec': n / ms * 1e3}
+
+
+def reward_only(n, support, rho, reps=5):
+    T = synth_targets(n, rho, support, 1237).cuda()
+    Gd = synth_targets(n, rho, support, 1238).cuda()
+    h = n // 2  # half the grids: rotated copy of the target
+    Gd[:h] = torch.rot90(T[:h], k=1, dims=(2, 3))
+    gw.max_intersection(Gd, T)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        gw.max_intersection(Gd, T)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {'kind': 'max_intersection', 'pairs': n, 'support': support, 'rho': rho, 'ms': ms,
+            'evals_per_sec': n / ms * 1e3}
+
+
+if __name__ == '__main__':
+    which = sys.argv[1:] or ['walking', 'flying', 'reward']
+    if 'walking' in which:
+        for rm in ('every_step', 'on_change'):
+            for inplace in (False, True):
+                print(json.dumps(walking(65536, 'compact', 0.2, rm, inplace)), flush=True)
+        print(json.dumps(walking(65536, 'full', 0.2, 'every_step', False)), flush=True)
+        print(json.dumps(walking(1048576, 'compact', 0.2, 'on_change', True, K=50)), flush=True)
+        print(json.dumps(walking(1048576, 'compact', 0.2, 'every_step', False, K=30)), flush=True)
+    if 'flying' in which:
+        print(json.dumps(flying(262144)), flush=True)
+    if 'reward' in which:
+        for rho in (0.05, 0.2, 0.5):
+            for support in ('full', 'compact'):
+                print(json.dumps(reward_only(1_000_000, support, rho)), flush=True)

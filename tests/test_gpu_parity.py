@@ -218,14 +218,17 @@ def test_reward_properties_full_size():
     assert bool((mi <= size).all()) and bool((mi >= 0).all())
     assert bool((mi <= (Gd != 0).flatten(1).sum(1)).all())
     assert int(gw.max_intersection(torch.zeros_like(T[:1000]), T[:1000]).abs().sum()) == 0
-    # (5) compact targets: translating the grid by an admissible shift keeps the score
+    # (5) the score only depends on the target up to an in-zone XZ translation (the admissible shifts
+    #     enumerate every in-zone translate of every rotation): move a compact target, same result
     m = torch.zeros(9, 11, 11, dtype=torch.bool, device='cuda')
     m[:5, 3:8, 3:8] = True
     Tc = torch.where(m, T, torch.zeros_like(T))[:200_000]
-    Gc = torch.where(m, Gd, torch.zeros_like(Gd))[:200_000]
+    Gc = Gd[:200_000]
     base = gw.max_intersection(Gc, Tc)
-    shifted = torch.roll(Gc, shifts=(2, -3), dims=(2, 3))  # support stays inside the zone: no wrap
-    assert torch.equal(gw.max_intersection(shifted, Tc), base)
+    moved = torch.roll(Tc, shifts=(2, -3), dims=(2, 3))  # support stays inside the zone: no wrap
+    assert torch.equal(gw.max_intersection(Gc, moved), base)
+    # (6) ... and up to a y-rotation of the target
+    assert torch.equal(gw.max_intersection(Gc, torch.rot90(Tc, k=1, dims=(2, 3)).contiguous()), base)
 
 
 # ------------------------------------------------------------------------- batched env vs the C oracle
