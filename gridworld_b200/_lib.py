@@ -11,6 +11,8 @@ from . import build as _build
 CELLS = 1089
 GRID_STRIDE = 1104
 TLIST_MAX = 1096
+TLIST_HDR = 8
+TLIST_ROW_MAX = TLIST_HDR + TLIST_MAX
 
 WALKING_DISCRETE, FLYING, WALKING_DICT = 0, 1, 2
 REWARD_ON_CHANGE, REWARD_EVERY_STEP = 0, 1
@@ -26,7 +28,7 @@ class Config(C.Structure):
 class State(C.Structure):
     _fields_ = [('n', C.c_int64), ('grid', C.c_void_p), ('init', C.c_void_p), ('target', C.c_void_p),
                 ('pose', C.c_void_p), ('init_pose', C.c_void_p), ('istate', C.c_void_p),
-                ('tlist', C.c_void_p), ('trect', C.c_void_p), ('tmeta', C.c_void_p)]
+                ('tlist', C.c_void_p), ('tmeta', C.c_void_p)]
 
 
 class Obs(C.Structure):

@@ -1,11 +1,13 @@
 // iglu_b200.cu -- sm_100a kernels + C ABI (include/iglu_b200.h) of the IGLU Gridworld step path.
 //
-// One warp owns 32 consecutive envs:
+// k_step: one warp owns 32 consecutive envs ("group"), persistent CTAs loop over groups.
 //   phase A (one thread per env): auto-reset, action parse, World.step in fp64 (iglu_physics.cuh),
 //            small observations (agentPos / inventory / compass);
-//   phase B (warp-cooperative, one env at a time): stage the env's int8 grid in shared memory with
-//            16-byte loads, widen it into the int32 obs['grid'] with coalesced stores, and evaluate
-//            Task.maximal_intersection (iglu_reward.cuh) when required;
+//   phase B (warp-cooperative, one env at a time): the env's int8 grid and its target block list are
+//            brought into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) through a
+//            4-deep per-warp ring that is filled BEFORE phase A, so the HBM latency hides behind the
+//            physics; the grid is widened into the int32 obs['grid'] with 16-byte streaming stores and
+//            Task.maximal_intersection is evaluated (iglu_reward.cuh) when required;
 //   phase C (one thread per env): Task.step_intersection bookkeeping, reward, done (task.py:103-119,
 //            env.py:290-296).
 // No collective, no host round trip; every entry point only enqueues work on the caller's stream.
@@ -23,7 +25,24 @@ namespace iglu {
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr size_t SMEM_BYTES = SPREAD_N * sizeof(unsigned long long) + WARPS_PER_CTA * sizeof(WarpScratch);
+constexpr int NB = 4;        // TMA ring depth per warp
+constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
+constexpr int TL_PRE = 64;   // target blocks prefetched with the header (longer lists are read from global)
+
+struct __align__(16) Slot {
+    uint32_t grid[GSTRIDE / 4];        // int8 grid of one env (1089 cells + zero pad)
+    uint16_t trow[TL_HDR + TL_PRE];    // rectangle header + first target blocks
+};
+
+struct __align__(16) WarpScratch {
+    Slot slot[NB];
+    uint32_t init[GSTRIDE / 4];        // starting grid (only for envs that have one)
+    EvalScratch es;
+    unsigned long long bar[NB];        // mbarriers of the ring
+};
+
+constexpr size_t TABLE_BYTES = SPREAD_N * sizeof(unsigned long long);
+constexpr size_t SMEM_BYTES = TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpScratch);
 
 struct StepParams {
     iglu_state st;
@@ -37,33 +56,85 @@ struct StepParams {
     const int32_t *buttons;    // walking dict [n][8]
 };
 
-__device__ __forceinline__ int16_t lo16(int w) { return (int16_t)(w & 0xFFFF); }
-__device__ __forceinline__ int16_t hi16(int w) { return (int16_t)((unsigned)w >> 16); }
-__device__ __forceinline__ int pack16(int a, int b) { return (a & 0xFFFF) | (b << 16); }
+// ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Cooperative 16-byte copy of one env's padded grid (69 x int4) global -> shared.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    }
+}
+
+__device__ __forceinline__ int pack16(int a, int b) { return (a & 0xFFFF) | (b << 16); }
+__device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xFFFF); }
+__device__ __forceinline__ int hi16(int w) { return (int)(int16_t)((unsigned)w >> 16); }
+
+// Cooperative 16-byte copy of one env's padded grid (69 x int4) global -> shared (generic proxy).
 __device__ __forceinline__ void load_grid_smem(uint32_t *dst, const int8_t *src, int lane) {
     const int4 *s = reinterpret_cast<const int4 *>(src);
     int4 *d = reinterpret_cast<int4 *>(dst);
     for (int q = lane; q < GSTRIDE / 16; q += 32) d[q] = s[q];
 }
 
+// Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element
+// e0 of the obs array (4-byte aligned only); the body is written as 16-byte streaming stores.
+__device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, int64_t e0, const uint32_t *sg,
+                                               int lane) {
+    const int8_t *sg8 = reinterpret_cast<const int8_t *>(sg);
+    int32_t *og = obs_grid + e0;
+    const int h = (int)((4 - (e0 & 3)) & 3);  // elements before the first 16-byte boundary
+    if (lane < h) og[lane] = (int32_t)sg8[lane];
+    const int nbody = (CELLS - h) >> 2;
+    int4 *o4 = reinterpret_cast<int4 *>(og + h);
+    for (int m = lane; m < nbody; m += 32) {
+        const uint32_t w = __funnelshift_r(sg[m], sg[m + 1], 8 * h);  // bytes h + 4m .. h + 4m + 3
+        int4 v;
+        v.x = (int)__byte_perm(w, 0, 0x8880);  // sign-extend byte 0
+        v.y = (int)__byte_perm(w, 0, 0x9991);
+        v.z = (int)__byte_perm(w, 0, 0xAAA2);
+        v.w = (int)__byte_perm(w, 0, 0xBBB3);
+        __stcs(o4 + m, v);
+    }
+    const int t0 = h + 4 * nbody;
+    if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
-    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + SPREAD_N * sizeof(unsigned long long));
+    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpScratch &ws = scratch[wid];
-    const bool need_table = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
-    // In ON_CHANGE mode few envs evaluate; the table is still needed, build it once per CTA.
     build_spread_table(tbl, threadIdx.x, CTA_THREADS);
-    (void)need_table;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NB; s++) mbar_init(&ws.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     const int64_t n = p.st.n;
     const int64_t ngroups = (n + 31) / 32;
     const bool flying = KIND == IGLU_FLYING;
+    const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    const bool grid_obs = p.cfg.write_grid_obs && p.obs.grid != nullptr;
+    const bool early = grid_obs || every_step;  // the set of envs phase B touches is known before phase A
+    const int cap = p.cfg.tlist_cap;
+    uint32_t seq_issue = 0, seq_cons = 0;  // ring sequence numbers (warp-uniform, live across groups)
 
     for (int64_t grp = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; grp < ngroups;
          grp += (int64_t)gridDim.x * WARPS_PER_CTA) {
@@ -72,9 +143,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         const int64_t ii = valid ? i : n - 1;  // clamp: invalid lanes read a real env, write nothing
 
         // ------------------------------------------------------------- phase A
-        int w[8], tm[8];
+        int w[7], tm[6];
 #pragma unroll
-        for (int c = 0; c < 8; c++) w[c] = p.st.istate[c * n + ii];
+        for (int c = 0; c < 7; c++) w[c] = p.st.istate[c * n + ii];
 #pragma unroll
         for (int c = 0; c < 6; c++) tm[c] = p.st.tmeta[c * n + ii];
         const int nblk = tm[0], target_size = tm[1];
@@ -82,8 +153,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         Agent a;
         a.x = p.st.pose[0 * n + ii]; a.y = p.st.pose[1 * n + ii]; a.z = p.st.pose[2 * n + ii];
         a.yaw = p.st.pose[3 * n + ii]; a.pitch = p.st.pose[4 * n + ii]; a.dy = p.st.pose[5 * n + ii];
-        a.inv[0] = lo16(w[0]); a.inv[1] = hi16(w[0]); a.inv[2] = lo16(w[1]);
-        a.inv[3] = hi16(w[1]); a.inv[4] = lo16(w[2]); a.inv[5] = hi16(w[2]);
+        a.inv01 = w[0]; a.inv23 = w[1]; a.inv45 = w[2];
         a.active = w[3] & 0xFF; a.tis = (w[3] >> 8) & 0xFF; a.err = (w[3] >> 24) & 0xFF;
         const bool done_prev = ((w[3] >> 16) & 0xFF) != 0;
         int step_no = w[4], dsize = w[5], max_int = w[6];
@@ -91,22 +161,49 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         // auto-reset (env.py:206-261): grid <- starting grid, cooperatively, 16 bytes per lane
         const bool do_reset = valid && p.cfg.auto_reset && done_prev;
         unsigned rm = __ballot_sync(0xffffffffu, do_reset);
-        while (rm) {
-            int j = __ffs(rm) - 1;
-            rm &= rm - 1;
-            int64_t ej = grp * 32 + j;
-            bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
-            int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
-            const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
-            for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
+        if (rm) {
+            while (rm) {
+                const int j = __ffs(rm) - 1;
+                rm &= rm - 1;
+                const int64_t ej = grp * 32 + j;
+                const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
+                int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
+                const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
+                for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
+            }
+            // the TMA reads below go through the async proxy: order them after these generic-proxy writes
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
         }
-        __syncwarp();
         if (do_reset) {
             a.x = p.st.init_pose[0 * n + i]; a.y = p.st.init_pose[1 * n + i]; a.z = p.st.init_pose[2 * n + i];
             a.yaw = p.st.init_pose[3 * n + i]; a.pitch = p.st.init_pose[4 * n + i];
-            a.inv[0] = lo16(tm[2]); a.inv[1] = hi16(tm[2]); a.inv[2] = lo16(tm[3]);
-            a.inv[3] = hi16(tm[3]); a.inv[4] = lo16(tm[4]); a.inv[5] = hi16(tm[4]);
+            a.inv01 = tm[2]; a.inv23 = tm[3]; a.inv45 = tm[4];
             step_no = 0; dsize = 0; max_int = 0;  // dy / tis / active survive (reference quirk)
+        }
+
+        // ring producer: lane 0 issues the bulk copies of env j of this group into the next slot
+        auto issue = [&](int j) {
+            const int nbj = __shfl_sync(0xffffffffu, nblk, j);
+            if (lane == 0) {
+                const int64_t ej = grp * 32 + j;
+                Slot &sl = ws.slot[seq_issue % NB];
+                unsigned long long *bar = &ws.bar[seq_issue % NB];
+                const uint32_t tbytes = (uint32_t)((2 * (TL_HDR + min(nbj, TL_PRE)) + 15) & ~15);
+                mbar_expect_tx(bar, GSTRIDE + tbytes);
+                tma_load(sl.grid, p.st.grid + ej * GSTRIDE, GSTRIDE, bar);
+                tma_load(sl.trow, p.st.tlist + ej * cap, tbytes, bar);
+            }
+            seq_issue++;
+        };
+        unsigned pend = 0, todo = 0;
+        if (early) {
+            todo = pend = __ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0));
+            for (int f = 0; f < NB && pend; f++) {
+                issue(__ffs(pend) - 1);
+                pend &= pend - 1;
+            }
         }
 
         Action act;
@@ -151,10 +248,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         }
 
         const int dsize_old = dsize;
+        int edit_cell = -1, edit_val = 0;
         if (valid) {
             step_no += 1;  // env.py:276
             world_step(p.st.grid + i * GSTRIDE, p.st.init + i * GSTRIDE, has_start, a, act, flying,
-                       p.cfg.select_and_place != 0, dsize);
+                       p.cfg.select_and_place != 0, dsize, edit_cell, edit_val);
             p.st.pose[0 * n + i] = a.x; p.st.pose[1 * n + i] = a.y; p.st.pose[2 * n + i] = a.z;
             p.st.pose[3 * n + i] = a.yaw; p.st.pose[4 * n + i] = a.pitch; p.st.pose[5 * n + i] = a.dy;
             // env.py:283-289 (float32 casts round to nearest even)
@@ -165,43 +263,54 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
             }
             if (p.obs.inventory) {
                 float *iv = p.obs.inventory + 6 * i;
-#pragma unroll
-                for (int c = 0; c < 6; c++) iv[c] = (float)a.inv[c];
+                iv[0] = (float)lo16(a.inv01); iv[1] = (float)hi16(a.inv01); iv[2] = (float)lo16(a.inv23);
+                iv[3] = (float)hi16(a.inv23); iv[4] = (float)lo16(a.inv45); iv[5] = (float)hi16(a.inv45);
             }
             if (p.obs.compass) p.obs.compass[i] = (float)(a.yaw - 180.0);
         }
-        __syncwarp();  // grid edits of phase A are visible to the whole warp below
+        __syncwarp();
 
         // ------------------------------------------------------------- phase B
         const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
-        const bool want_eval = valid && nblk > 0 &&
-                               (p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP ? true : changed);
-        const bool want_grid = valid && p.cfg.write_grid_obs && p.obs.grid != nullptr;
-        int mi_eval = 0;
-        unsigned cm = __ballot_sync(0xffffffffu, want_eval || want_grid);
+        const bool want_eval = valid && nblk > 0 && (every_step || changed);
         const unsigned em = __ballot_sync(0xffffffffu, want_eval);
         const unsigned hm = __ballot_sync(0xffffffffu, has_start);
-        while (cm) {
-            const int j = __ffs(cm) - 1;
-            cm &= cm - 1;
+        if (!early) {
+            todo = pend = em;
+            for (int f = 0; f < NB && pend; f++) {
+                issue(__ffs(pend) - 1);
+                pend &= pend - 1;
+            }
+        }
+        int mi_eval = 0;
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
             const int64_t ej = grp * 32 + j;
             const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
-            load_grid_smem(ws.grid, p.st.grid + ej * GSTRIDE, lane);
+            Slot &sl = ws.slot[seq_cons % NB];
             if (ev && hs) load_grid_smem(ws.init, p.st.init + ej * GSTRIDE, lane);
+            mbar_wait(&ws.bar[seq_cons % NB], (seq_cons / NB) & 1u);
+            // The copy may have raced with this step's edit of the same env: apply it to the staged grid.
+            const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
+            const int evl = __shfl_sync(0xffffffffu, edit_val, j);
+            if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
             __syncwarp();
-            if (p.cfg.write_grid_obs && p.obs.grid != nullptr) {
-                int32_t *og = p.obs.grid + ej * CELLS;
-                const int8_t *sg = reinterpret_cast<const int8_t *>(ws.grid);
-                for (int c = lane; c < CELLS; c += 32) og[c] = (int32_t)sg[c];
-            }
+            if (grid_obs) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
             if (ev) {
-                build_rows(ws, hs, lane);
+                build_rows(ws.es, sl.grid, ws.init, hs, lane);
                 const int nb = __shfl_sync(0xffffffffu, nblk, j);
-                int r = eval_max_intersection<false>(ws, tbl, p.st.tlist + ej * p.cfg.tlist_cap, nb,
-                                                     p.st.trect + ej * 16, 4, lane, nullptr);
+                const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
+                const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
+                const int r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
                 if (lane == j) mi_eval = r;
             }
-            __syncwarp();
+            __syncwarp();  // every lane is done with the slot before it is refilled
+            seq_cons++;
+            if (pend) {
+                issue(__ffs(pend) - 1);
+                pend &= pend - 1;
+            }
         }
 
         // ------------------------------------------------------------- phase C
@@ -215,9 +324,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
                                              : (double)right * p.cfg.right_placement_scale;
             p.obs.reward[i] = reward;
             p.obs.done[i] = (uint8_t)done;
-            p.st.istate[0 * n + i] = pack16(a.inv[0], a.inv[1]);
-            p.st.istate[1 * n + i] = pack16(a.inv[2], a.inv[3]);
-            p.st.istate[2 * n + i] = pack16(a.inv[4], a.inv[5]);
+            p.st.istate[0 * n + i] = a.inv01;
+            p.st.istate[1 * n + i] = a.inv23;
+            p.st.istate[2 * n + i] = a.inv45;
             p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
             p.st.istate[4 * n + i] = step_no;
             p.st.istate[5 * n + i] = dsize;
@@ -244,6 +353,7 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
     const int8_t *s = start ? start + row * CELLS : nullptr;
     int8_t *gt = st.target + e * GSTRIDE, *gi = st.init + e * GSTRIDE;
     uint16_t *tl = st.tlist + e * cfg.tlist_cap;
+    const int room = cfg.tlist_cap - TL_HDR;
     int nout = 0, xmin = 10, xmax = 0, zmin = 10, zmax = 0, any_start = 0;
     int cnt[6] = {0, 0, 0, 0, 0, 0};
     for (int c0 = 0; c0 < GSTRIDE; c0 += 32) {
@@ -263,7 +373,7 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
         if (d != 0) {
             const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
             const int pos = nout + __popc(m & ((1u << lane) - 1u));
-            if (pos < cfg.tlist_cap) tl[pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((d & 15) << 12));
+            if (pos < room) tl[TL_HDR + pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((d & 15) << 12));
             xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
         }
         nout += __popc(m);
@@ -271,11 +381,8 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
     xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
     zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
     if (lane == 0) {
-        int8_t rc[16];
-        rects_from_bbox(xmin, xmax, zmin, zmax, rc);
-#pragma unroll
-        for (int k = 0; k < 16; k++) st.trect[e * 16 + k] = rc[k];
-        st.tmeta[0 * n + e] = min(nout, cfg.tlist_cap);
+        *reinterpret_cast<int4 *>(tl) = rects_from_bbox(xmin, xmax, zmin, zmax);
+        st.tmeta[0 * n + e] = min(nout, room);
         st.tmeta[1 * n + e] = nout;  // target_size = nnz(target - init)
         st.tmeta[2 * n + e] = pack16(20 - cnt[0], 20 - cnt[1]);
         st.tmeta[3 * n + e] = pack16(20 - cnt[2], 20 - cnt[3]);
@@ -338,10 +445,12 @@ __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, cons
 // ------------------------------------------------------------------ stateless reward sweep
 // Task(target, full_grid, invariant).maximal_intersection(grid) per pair (BASELINE config 4).
 struct __align__(16) PairScratch {
+    uint32_t grid[GSTRIDE / 4];
     uint16_t list[IGLU_TLIST_MAX];
+    EvalScratch es;
 };
 
-template <bool CLIP>
+template <bool CLIP, bool WANT_KEY>
 __global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
                                                                      const int8_t *__restrict__ fulls,
@@ -349,14 +458,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_
                                                                      int32_t *__restrict__ argmax, int64_t count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
-    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + SPREAD_N * sizeof(unsigned long long));
-    PairScratch *pscratch = reinterpret_cast<PairScratch *>(scratch + WARPS_PER_CTA);
+    PairScratch *scratch = reinterpret_cast<PairScratch *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpScratch &ws = scratch[wid];
-    uint16_t *list = pscratch[wid].list;
+    PairScratch &ps = scratch[wid];
     build_spread_table(tbl, threadIdx.x, CTA_THREADS);
     __syncthreads();
-    int8_t *sg = reinterpret_cast<int8_t *>(ws.grid);
+    int8_t *sg = reinterpret_cast<int8_t *>(ps.grid);
     for (int64_t pr = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; pr < count;
          pr += (int64_t)gridDim.x * WARPS_PER_CTA) {
         const int8_t *g = grids + pr * CELLS, *t = targets + pr * CELLS;
@@ -377,7 +484,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_
                 const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
                 if (tv != 0) {
                     const int pos = nout + __popc(m & ((1u << lane) - 1u));
-                    list[pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((tv & 15) << 12));
+                    ps.list[pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((tv & 15) << 12));
                 }
                 if (bv != 0) { xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z); }
             }
@@ -385,22 +492,19 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_
         }
         xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
         zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
-        int8_t rc[16];
-        int n_rot = 4;
+        int4 rc = make_int4(0, 0, 0, 0);  // task.py:59-60 admissible = [[(0, 0)]]
+        int n_rot = 1;
         if (invariant) {
-            rects_from_bbox(xmin, xmax, zmin, zmax, rc);
-        } else {  // task.py:59-60 admissible = [[(0, 0)]]
-#pragma unroll
-            for (int k = 0; k < 16; k++) rc[k] = 0;
-            n_rot = 1;
+            rc = rects_from_bbox(xmin, xmax, zmin, zmax);
+            n_rot = 4;
         }
         __syncwarp();
-        build_rows(ws, false, lane);
+        build_rows(ps.es, ps.grid, ps.grid, false, lane);
         int key = -1;
-        int best = eval_max_intersection<CLIP>(ws, tbl, list, nout, rc, n_rot, lane, argmax ? &key : nullptr);
+        const int best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);
         if (lane == 0) {
             out[pr] = best;
-            if (argmax) {
+            if (WANT_KEY) {
                 int k = 0, dx = 0, dz = 0;
                 if (key >= 0) { k = key / 441; int r = key - k * 441; dx = r / 21 - 10; dz = r % 21 - 10; }
                 argmax[3 * pr + 0] = dx; argmax[3 * pr + 1] = dz; argmax[3 * pr + 2] = k;
@@ -442,7 +546,8 @@ extern "C" const char *iglu_strerror(int status) {
 extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!cfg || !out) return IGLU_ERR_INVALID_ARG;
     if (cfg->action_space < 0 || cfg->action_space > 2) return IGLU_ERR_INVALID_ARG;
-    if (cfg->tlist_cap <= 0 || cfg->tlist_cap > IGLU_TLIST_MAX || (cfg->tlist_cap & 7)) return IGLU_ERR_INVALID_ARG;
+    if (cfg->tlist_cap < TL_HDR + TL_PRE || cfg->tlist_cap > IGLU_TLIST_ROW_MAX || (cfg->tlist_cap & 7))
+        return IGLU_ERR_INVALID_ARG;
     iglu_ctx *c = new iglu_ctx();
     c->cfg = *cfg;
     c->last_launches = 0;
@@ -484,7 +589,7 @@ extern "C" int iglu_last_launch_count(const iglu_ctx *ctx) { return ctx ? ctx->l
 
 static bool state_ok(const iglu_state *st, const iglu_obs *obs) {
     return st && obs && st->n > 0 && st->grid && st->init && st->target && st->pose && st->init_pose &&
-           st->istate && st->tlist && st->trect && st->tmeta && obs->reward && obs->done;
+           st->istate && st->tlist && st->tmeta && obs->reward && obs->done;
 }
 
 extern "C" int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const int8_t *target,
@@ -572,6 +677,17 @@ extern "C" int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const
     return check(cudaStreamSynchronize(s));
 }
 
+template <bool CLIP, bool WANT_KEY>
+static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int invariant, int32_t *out,
+                     int32_t *argmax, int64_t count, unsigned grid, size_t smem, cudaStream_t s) {
+    int rc = check(cudaFuncSetAttribute(k_max_intersection<CLIP, WANT_KEY>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (rc) return rc;
+    k_max_intersection<CLIP, WANT_KEY><<<grid, CTA_THREADS, smem, s>>>(grids, targets, fulls, invariant, out,
+                                                                        argmax, count);
+    return check(cudaPeekAtLastError());
+}
+
 extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls,
                                      int invariant, int32_t *out, int32_t *argmax, int64_t count,
                                      void *stream) {
@@ -579,21 +695,16 @@ extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets,
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return IGLU_ERR_CUDA;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IGLU_ERR_CUDA;
-    const size_t smem = SMEM_BYTES + WARPS_PER_CTA * sizeof(PairScratch);
+    const size_t smem = TABLE_BYTES + WARPS_PER_CTA * sizeof(PairScratch);
     const int64_t ctas = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     const int64_t resident = (int64_t)sms * 2;
     const unsigned grid = (unsigned)(ctas < resident ? ctas : resident);
-    int rc;
-    if (fulls && invariant) {
-        rc = check(cudaFuncSetAttribute(k_max_intersection<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (rc) return rc;
-        k_max_intersection<true><<<grid, CTA_THREADS, smem, (cudaStream_t)stream>>>(grids, targets, fulls, invariant,
-                                                                                    out, argmax, count);
-    } else {
-        rc = check(cudaFuncSetAttribute(k_max_intersection<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (rc) return rc;
-        k_max_intersection<false><<<grid, CTA_THREADS, smem, (cudaStream_t)stream>>>(grids, targets, fulls, invariant,
-                                                                                     out, argmax, count);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool clip = fulls && invariant;
+    if (clip) {
+        return argmax ? launch_mi<true, true>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s)
+                      : launch_mi<true, false>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s);
     }
-    return check(cudaPeekAtLastError());
+    return argmax ? launch_mi<false, true>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s)
+                  : launch_mi<false, false>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s);
 }

@@ -11,6 +11,12 @@
 // Discrete(18) action space can produce from the default pose) is served from a table the HOST
 // filled with glibc at iglu_ctx_create time, keyed by the un-reduced angle.  Other angles take
 // the device sincos/atan2 (<= 2 ulp, pose parity 1e-6 as BASELINE.json states for flying).
+//
+// Memory-level parallelism: the voxel lookups of the ray cast and of collide() do not depend on
+// each other's results (sample positions and the 12 neighbour cells are known up front), only the
+// decisions do.  They are therefore issued as batches of independent predicated loads and the
+// reference's sequential logic then runs on the gathered bits -- same results, one memory latency
+// per batch instead of one per lookup.
 #pragma once
 #include <cstdint>
 
@@ -33,8 +39,22 @@ constexpr double RAD2DEG = 180.0 / 3.14159265358979323846;  // CPython: x * (180
 struct Agent {
     double x, y, z, yaw, pitch, dy;
     int tis, active, err;
-    int inv[6];
+    int inv01, inv23, inv45;  // inventory, six int16 packed as stored in istate w0..w2
 };
+
+__device__ __forceinline__ int inv_get(const Agent &a, int i) {
+    int w = i < 2 ? a.inv01 : (i < 4 ? a.inv23 : a.inv45);
+    return (int)(int16_t)((unsigned)w >> (16 * (i & 1)));
+}
+__device__ __forceinline__ void inv_add(Agent &a, int i, int delta) {
+    int w = i < 2 ? a.inv01 : (i < 4 ? a.inv23 : a.inv45);
+    const int sh = 16 * (i & 1);
+    const int v = ((int)(int16_t)((unsigned)w >> sh) + delta) & 0xFFFF;
+    w = (w & ~(0xFFFF << sh)) | (v << sh);
+    if (i < 2) a.inv01 = w;
+    else if (i < 4) a.inv23 = w;
+    else a.inv45 = w;
+}
 
 // The tuple every parse_* returns (world.py:394, 414, 432).
 struct Action {
@@ -60,19 +80,19 @@ __device__ __forceinline__ double strafe_degrees(double s0, double s1) {
     return atan2(s0, s1) * RAD2DEG;
 }
 
-// `key in self.world` / `self.world[key]`: the 37x37 floor at y = -2 (world.py:60-71, WHITE inside
-// the zone footprint, GREY outside) plus the placed blocks mirrored in grid[y+1, x+5, z+5].
-__device__ __forceinline__ bool world_get(const int8_t *__restrict__ g, int x, int y, int z, int &tex) {
-    if (y == -2) {
-        tex = (abs(x) <= 5 && abs(z) <= 5) ? -1 : 0;
-        return abs(x) <= 18 && abs(z) <= 18;
-    }
-    if ((unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u) {
-        int c = g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)];
-        tex = c;
-        return c != 0;
-    }
-    return false;
+// `key in self.world`: the 37x37 floor at y = -2 (world.py:60-71) plus the placed blocks mirrored
+// in grid[y+1, x+5, z+5] (env.py:136-142).  Branch-free: one predicated byte load.
+__device__ __forceinline__ bool world_has(const int8_t *__restrict__ g, int x, int y, int z) {
+    const bool in_zone = (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
+    const int c = in_zone ? (int)g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)] : 0;
+    const bool floor_hit = y == -2 && abs(x) <= 18 && abs(z) <= 18;
+    return floor_hit || c != 0;
+}
+
+// `self.world[key]` for a key known to be present: WHITE (-1) / GREY (0) floor or the block colour.
+__device__ __forceinline__ int world_tex(const int8_t *__restrict__ g, int x, int y, int z) {
+    if (y == -2) return (abs(x) <= 5 && abs(z) <= 5) ? -1 : 0;
+    return (int)g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)];
 }
 
 __device__ __forceinline__ bool build_zone_i(int x, int y, int z) {
@@ -84,25 +104,32 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
                                         double &agent_dy) {
     const double pad = 0.25;
     const int nx = (int)rint(px), ny = (int)rint(py), nz = (int)rint(pz);
-    int tex;
+    // gather the 12 neighbour cells (6 faces x 2 heights) first: independent loads
+    unsigned solid = 0;
 #pragma unroll
     for (int f = 0; f < 6; f++) {
         const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
         const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
-        double &p = (axis == 0) ? px : (axis == 1 ? py : pz);
-        const int npi = (axis == 0) ? nx : (axis == 1 ? ny : nz);
-        double d = (p - (double)npi) * (double)sgn;
-        if (d < pad) continue;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int ox = nx, oy = ny - h, oz = nz;
             if (axis == 0) ox += sgn;
             else if (axis == 1) oy += sgn;
             else oz += sgn;
-            if (!world_get(g, ox, oy, oz, tex)) continue;
+            solid |= (unsigned)world_has(g, ox, oy, oz) << (2 * f + h);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
+        const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
+        double &p = (axis == 0) ? px : (axis == 1 ? py : pz);
+        const int npi = (axis == 0) ? nx : (axis == 1 ? ny : nz);
+        const double d = (p - (double)npi) * (double)sgn;
+        if (d < pad) continue;
+        if ((solid >> (2 * f)) & 3u) {  // either height hits: same adjustment, then break
             p -= (d - pad) * (double)sgn;
             if (f < 2) agent_dy = 0.0;
-            break;
         }
     }
 }
@@ -136,8 +163,12 @@ __device__ __forceinline__ void update_sub(const int8_t *__restrict__ g, Agent &
 // world.py:434-456 World.step for one env. `g` = this env's int8 grid (global memory),
 // `init` = its starting grid (only read when has_start, for the block-count bookkeeping),
 // `dsize` = nnz(grid - init), kept incrementally (task.py:110 recomputes it from scratch).
+// edit_cell / edit_val report the single cell this step changed (-1 = none).
 __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t *__restrict__ init, bool has_start,
-                                           Agent &a, Action act, bool flying, bool select_and_place, int &dsize) {
+                                           Agent &a, Action act, bool flying, bool select_and_place, int &dsize,
+                                           int &edit_cell, int &edit_val) {
+    edit_cell = -1;
+    edit_val = 0;
     if (select_and_place && act.hotbar != 0) { act.add = true; act.remove = false; }
     // movement (world.py:344-356); agent.strafe is [0, 0] on entry because sustain=False
     const double s0 = act.s0, s1 = act.s1;
@@ -160,26 +191,38 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         trig_deg(a.pitch, sp, cp);
         trig_deg(a.yaw - 90.0, sy, cy);
         const double vx = cy * cp, vy = sp, vz = sy * cp;  // get_sight_vector (145-161)
-        // hit_test (73-99): 40 samples, step 1/5
+        // hit_test (73-99): 40 samples, step 1/5; lookups gathered 8 at a time
         const double sx = vx / 5.0, syy = vy / 5.0, sz = vz / 5.0;
         double px = a.x, py = a.y, pz = a.z;
-        int kx = 0, ky = 0, kz = 0, qx = 0, qy = 0, qz = 0, tex = 0;
+        int kx = 0, ky = 0, kz = 0, qx = 0, qy = 0, qz = 0;
         bool has_prev = false, hit = false;
-        for (int i = 0; i < 40; i++) {
-            kx = (int)rint(px); ky = (int)rint(py); kz = (int)rint(pz);
-            bool differs = !has_prev || kx != qx || ky != qy || kz != qz;
-            if (differs && world_get(g, kx, ky, kz, tex)) { hit = true; break; }
-            qx = kx; qy = ky; qz = kz;
-            has_prev = true;
-            px = px + sx; py = py + syy; pz = pz + sz;
+        for (int i0 = 0; i0 < 40 && !hit; i0 += 8) {
+            int bx[8], by[8], bz[8];
+            unsigned solid = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                bx[j] = (int)rint(px); by[j] = (int)rint(py); bz[j] = (int)rint(pz);
+                solid |= (unsigned)world_has(g, bx[j], by[j], bz[j]) << j;
+                px = px + sx; py = py + syy; pz = pz + sz;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (!hit) {
+                    kx = bx[j]; ky = by[j]; kz = bz[j];
+                    const bool differs = !has_prev || kx != qx || ky != qy || kz != qz;
+                    if (differs && ((solid >> j) & 1u)) {
+                        hit = true;
+                    } else {
+                        qx = kx; qy = ky; qz = kz;
+                        has_prev = true;
+                    }
+                }
+            }
         }
         int cell = -1, newv = 0;
         if (act.add) {
             if (hit && has_prev) {
-                int have = 0;
-#pragma unroll
-                for (int c = 0; c < 6; c++) if (c == a.active - 1) have = a.inv[c];
-                if (have > 0 && build_zone_i(qx, qy, qz)) {
+                if (inv_get(a, a.active - 1) > 0 && build_zone_i(qx, qy, qz)) {
                     double y = a.y - 1.0 + 0.25;
                     double bx = (double)qx - 0.5, by = (double)qy, bz = (double)qz - 0.5;
                     bool inside = bx <= a.x && a.x <= bx + 1.0 && bz <= a.z && a.z <= bz + 1.0 &&
@@ -187,17 +230,16 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
                     if (!inside) {
                         cell = (qy + 1) * 121 + (qx + 5) * 11 + (qz + 5);
                         newv = a.active;
-#pragma unroll
-                        for (int c = 0; c < 6; c++) if (c == a.active - 1) a.inv[c] -= 1;
+                        inv_add(a, a.active - 1, -1);
                     }
                 }
             }
         } else if (hit) {
+            const int tex = world_tex(g, kx, ky, kz);
             if (tex != 0 && tex != -1) {  // not GREY / WHITE floor
                 cell = (ky + 1) * 121 + (kx + 5) * 11 + (kz + 5);
                 newv = 0;
-#pragma unroll
-                for (int c = 0; c < 6; c++) if (c == tex - 1) a.inv[c] += 1;
+                if (tex >= 1 && tex <= 6) inv_add(a, tex - 1, 1);
             }
         }
         if (cell >= 0) {
@@ -205,6 +247,8 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
             int iv = has_start ? (int)init[cell] : 0;
             dsize += (int)(newv != iv) - (int)(oldv != iv);
             g[cell] = (int8_t)newv;
+            edit_cell = cell;
+            edit_val = newv;
         }
     }
     // update (world.py:203-220): m = time_int_steps read once, dt = min(1/20, 0.2)

@@ -16,8 +16,8 @@
 //     the rectangle at once (bit j <-> dz = dz_lo + j);
 //   * the <= 11 one-bit results are added into eleven 5-bit counters packed in one 64-bit register
 //     through a 2048-entry spread table in shared memory (one LDS.64 + one 64-bit add per block),
-//     flushed to 32-bit counters every 31 blocks;
-//   * when fewer than 17 work items exist the blocks are split over lane groups and combined with
+//     flushed to 32-bit counters after every chunk of <= 28 blocks;
+//   * when at most 16 work items exist the blocks are split over lane groups and combined with
 //     shuffles; the final max over lanes is __reduce_max_sync.
 #pragma once
 #include <cstdint>
@@ -27,15 +27,15 @@ namespace iglu {
 constexpr int ROWS_PER_CLASS = 99;               // 9 y-levels x 11 x-rows
 constexpr int NROWS = 16 * ROWS_PER_CLASS;       // 4-bit class codes
 constexpr int ROWS_WORDS = NROWS / 2;            // uint16 rows packed in uint32 words (792)
-constexpr int LIST_CHUNK = 64;                   // target blocks expanded per pass
+constexpr int LIST_CHUNK = 28;                   // target blocks per pass (<= 31 adds per 5-bit field)
+constexpr int LIST_CAP = 32;                     // chunk padded up to a multiple of 4*G <= 32
 constexpr int SPREAD_N = 2048;
+constexpr uint32_t DUMMY_ENTRY = 2 * 50;         // row 50 of class 0 (never set), shift 0 -> adds nothing
 
-// Per-warp shared-memory scratch (16-byte aligned pieces).
-struct __align__(16) WarpScratch {
-    uint32_t grid[GSTRIDE / 4];          // int8 grid of the current env (1089 cells + zero pad)
-    uint32_t init[GSTRIDE / 4];          // starting grid (only when the env has one)
-    uint32_t rows[ROWS_WORDS];           // z-reversed occupancy rows, two uint16 per word
-    uint32_t list[4][LIST_CHUNK];        // expanded target blocks per rotation
+// Per-warp scratch for one evaluation.
+struct __align__(16) EvalScratch {
+    uint32_t rows[ROWS_WORDS];      // z-reversed occupancy rows, two uint16 per word
+    uint32_t list[4][LIST_CAP];     // expanded target blocks per rotation
 };
 
 // spread table: bit j of v -> bit 5*j of the result (eleven 5-bit fields in a uint64).
@@ -48,80 +48,88 @@ __device__ __forceinline__ void build_spread_table(unsigned long long *tbl, int 
     }
 }
 
-// Pack the (difference) grid held in ws.grid (minus ws.init when has_init) into ws.rows.
-__device__ __forceinline__ void build_rows(WarpScratch &ws, bool has_init, int lane) {
-    for (int w = lane; w < ROWS_WORDS; w += 32) ws.rows[w] = 0u;
+// Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows. Both are 16-byte aligned
+// shared-memory copies of GSTRIDE bytes whose pad bytes (cells >= 1089) are zero.
+__device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid, const uint32_t *init,
+                                           bool has_init, int lane) {
+    int4 *rz = reinterpret_cast<int4 *>(es.rows);
+    for (int q = lane; q < ROWS_WORDS / 4; q += 32) rz[q] = make_int4(0, 0, 0, 0);
     __syncwarp();
-    for (int w = lane; w < (CELLS + 3) / 4; w += 32) {
-        uint32_t gv = ws.grid[w];
-        uint32_t iv = has_init ? ws.init[w] : 0u;
-        if ((gv | iv) == 0u) continue;
+    const int4 *g4 = reinterpret_cast<const int4 *>(grid);
+    const int4 *i4 = reinterpret_cast<const int4 *>(init);
+    for (int q = lane; q < GSTRIDE / 16; q += 32) {
+        const int4 gv = g4[q];
+        int4 iv = make_int4(0, 0, 0, 0);
+        if (has_init) iv = i4[q];
+        if ((gv.x | gv.y | gv.z | gv.w | iv.x | iv.y | iv.z | iv.w) == 0) continue;
+        const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
+        const uint32_t iw[4] = {(uint32_t)iv.x, (uint32_t)iv.y, (uint32_t)iv.z, (uint32_t)iv.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int d = (int)(int8_t)(gv >> (8 * j)) - (int)(int8_t)(iv >> (8 * j));
-            int cell = 4 * w + j;
-            if (d != 0 && cell < CELLS) {
-                int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
-                int row = (d & 15) * ROWS_PER_CLASS + y * 11 + x;
-                atomicOr(&ws.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
+        for (int w = 0; w < 4; w++) {
+            if ((gw[w] | iw[w]) == 0u) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int d = (int)(int8_t)(gw[w] >> (8 * j)) - (int)(int8_t)(iw[w] >> (8 * j));
+                const int cell = 16 * q + 4 * w + j;
+                if (d != 0 && cell < CELLS) {
+                    const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
+                    const int row = (d & 15) * ROWS_PER_CLASS + y * 11 + x;
+                    atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
+                }
             }
         }
     }
     __syncwarp();
 }
 
-struct Rects {
-    int dx_lo[4], dx_hi[4], dz_lo[4], dz_hi[4];
-    int n_rot;
-};
-
 // Rectangles of the four rotations from the rotation-0 bounding box of the non-zero cells
 // (x_min..x_max, z_min..z_max; empty = (10, 0, 10, 0) which yields all 441 shifts, task.py:67-72).
-__device__ __forceinline__ void rects_from_bbox(int xmin, int xmax, int zmin, int zmax, int8_t out[16]) {
+// Packed as 16 int8 in an int4: per rotation dx_lo, dx_hi, dz_lo, dz_hi.
+__device__ __forceinline__ int4 rects_from_bbox(int xmin, int xmax, int zmin, int zmax) {
+    int r[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        out[4 * k + 0] = (int8_t)(xmax - 10);
-        out[4 * k + 1] = (int8_t)xmin;
-        out[4 * k + 2] = (int8_t)(zmax - 10);
-        out[4 * k + 3] = (int8_t)zmin;
+        r[k] = ((xmax - 10) & 0xFF) | ((xmin & 0xFF) << 8) | (((zmax - 10) & 0xFF) << 16) | ((zmin & 0xFF) << 24);
         // rotate the box: x' = z, z' = 10 - x  (task.py:52-53)
-        int nxmin = zmin, nxmax = zmax, nzmin = 10 - xmax, nzmax = 10 - xmin;
+        const int nxmin = zmin, nxmax = zmax, nzmin = 10 - xmax, nzmax = 10 - xmin;
         xmin = nxmin; xmax = nxmax; zmin = nzmin; zmax = nzmax;
     }
+    return make_int4(r[0], r[1], r[2], r[3]);
 }
 
-// Evaluate max intersection for the env whose rows are in ws.rows.
-//   tlist : nblk packed target blocks (y | x<<4 | z<<8 | code<<12), global or shared memory
-//   rc    : 16 int8 rectangle bounds; n_rot rotations are evaluated
+__device__ __forceinline__ int rect_byte(int w, int i) { return (int)(int8_t)((unsigned)w >> (8 * i)); }
+
+// Evaluate max intersection for the env whose rows are in es.rows.
+//   tlist : nblk packed target blocks (y | x<<4 | z<<8 | code<<12), shared or global memory
+//   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
 //   CLIP  : true when shifts may move target cells outside the grid (full_grid rectangles)
-// Returns (warp-uniform) best count; if key_out != nullptr also the first (rot, dx, dz) reaching
-// it in the reference's iteration order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if best == 0.
-template <bool CLIP>
-__device__ __forceinline__ int eval_max_intersection(WarpScratch &ws, const unsigned long long *__restrict__ tbl,
-                                                     const uint16_t *__restrict__ tlist, int nblk,
-                                                     const int8_t *__restrict__ rc, int n_rot, int lane,
-                                                     int *key_out) {
-    // ---- enumerate work items (k, dx, dz-chunk of <= 11) ----
+// Returns (warp-uniform) best count; if WANT_KEY also the first (rot, dx, dz) reaching it in the
+// reference's iteration order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if best == 0.
+template <bool CLIP, bool WANT_KEY>
+__device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsigned long long *__restrict__ tbl,
+                                                     const uint16_t *__restrict__ tlist, int nblk, int4 rc,
+                                                     int n_rot, int lane, int *key_out) {
+    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
+    // ---- enumerate work items (k, dx[, dz-chunk of <= 11 when CLIP]) ----
     int nx[4], nch[4], base[5];
     base[0] = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        int wx = (int)rc[4 * k + 1] - (int)rc[4 * k + 0] + 1;
-        int wz = (int)rc[4 * k + 3] - (int)rc[4 * k + 2] + 1;
+        const int wx = rect_byte(rw[k], 1) - rect_byte(rw[k], 0) + 1;
+        const int wz = rect_byte(rw[k], 3) - rect_byte(rw[k], 2) + 1;
         nx[k] = (k < n_rot && wx > 0 && wz > 0) ? wx : 0;
         nch[k] = CLIP ? (wz + 10) / 11 : 1;
         base[k + 1] = base[k] + nx[k] * nch[k];
     }
     const int T = base[4];
-    int best = 0;  // packed (count << 12 | 4095 - key) when key_out, else count
-    if (T == 0 || nblk == 0) {
-        if (key_out) *key_out = -1;
-        return 0;
-    }
+    if (WANT_KEY) *key_out = -1;
+    if (T == 0 || nblk == 0) return 0;
     int ppad = 32;
-    if (T <= 16) { ppad = 1; while (ppad < T) ppad <<= 1; }
-    const int G = 32 / ppad;
+    if (T <= 16) { ppad = 4; while (ppad < T) ppad <<= 1; }
+    const int G = 32 / ppad;  // 1, 2, 4 or 8 lane groups share the blocks of one work item
     const int p = lane & (ppad - 1), g = lane / ppad;
+    const unsigned char *rows8 = reinterpret_cast<const unsigned char *>(es.rows);
+    int best = 0;  // WANT_KEY: count << 12 | 4095 - key
 
     for (int pass0 = 0; pass0 < T; pass0 += 32) {
         const int item = pass0 + p;
@@ -129,66 +137,75 @@ __device__ __forceinline__ int eval_max_intersection(WarpScratch &ws, const unsi
         int k = 0;
 #pragma unroll
         for (int q = 1; q < 4; q++) if (item >= base[q]) k = q;
-        int local = item - base[k];
-        int nchk = 1, nxk = 1, dxlo = 0, dzlo0 = 0, dzhi = 0;
+        int rk = rw[0], nchk = nch[0], basek = base[0];
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (q == k) { nchk = nch[q]; nxk = nx[q]; dxlo = rc[4 * q]; dzlo0 = rc[4 * q + 2]; dzhi = rc[4 * q + 3]; }
-        (void)nxk;
+        for (int q = 1; q < 4; q++) if (q == k) { rk = rw[q]; nchk = nch[q]; basek = base[q]; }
+        const int local = item - basek;
         const int ch = CLIP ? local % nchk : 0;
-        const int dx = dxlo + (CLIP ? local / nchk : local);
-        const int dzlo = dzlo0 + 11 * ch;
-        int W = dzhi - dzlo + 1;
+        const int dx = rect_byte(rk, 0) + (CLIP ? local / nchk : local);
+        const int dzlo = rect_byte(rk, 2) + 11 * ch;
+        int W = rect_byte(rk, 3) - dzlo + 1;
         if (W > 11) W = 11;
-        const int cz = 10 + dzlo;  // shift = cz - z_k
+        const int cz = 10 + dzlo;  // CLIP: shift = cz - z_k
+        const uint32_t *mylist = es.list[k];
 
         int cnt[11];
 #pragma unroll
         for (int j = 0; j < 11; j++) cnt[j] = 0;
-        unsigned long long acc = 0ull;
-        int nacc = 0;
 
         for (int c0 = 0; c0 < nblk; c0 += LIST_CHUNK) {
             const int cn = min(LIST_CHUNK, nblk - c0);
-            // expand the chunk for the four rotations: rowoff2 | z_k << 12 | x_k << 16
-            for (int i = lane; i < 4 * cn; i += 32) {
-                int kk = i / cn, b = i - kk * cn;
-                uint32_t e = tlist[c0 + b];
-                int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
-                int xk = (kk == 0) ? x : (kk == 1) ? z : (kk == 2) ? 10 - x : 10 - z;
-                int zk = (kk == 0) ? z : (kk == 1) ? 10 - x : (kk == 2) ? 10 - z : x;
-                ws.list[kk][b] = (uint32_t)((code * ROWS_PER_CLASS + y * 11 + xk) * 2) | (zk << 12) | (xk << 16);
+            const int cnp = (cn + 4 * G - 1) & ~(4 * G - 1);  // padded with entries that add nothing
+            // expand: lane b computes the four rotated entries of block b
+            {
+                uint32_t e0 = DUMMY_ENTRY, e1 = DUMMY_ENTRY, e2 = DUMMY_ENTRY, e3 = DUMMY_ENTRY;
+                if (lane < cn) {
+                    const uint32_t e = tlist[c0 + lane];
+                    const int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
+                    const int rb = (code * ROWS_PER_CLASS + y * 11) * 2;
+                    if (CLIP) {  // rowoff2 | z_k << 12 | x_k << 16
+                        e0 = (uint32_t)(rb + 2 * x) | (z << 12) | (x << 16);
+                        e1 = (uint32_t)(rb + 2 * z) | ((10 - x) << 12) | (z << 16);
+                        e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 - z) << 12) | ((10 - x) << 16);
+                        e3 = (uint32_t)(rb + 2 * (10 - z)) | (x << 12) | ((10 - z) << 16);
+                    } else {  // rowoff2 | shift << 16 with shift = 10 + dz_lo(k) - z_k
+                        e0 = (uint32_t)(rb + 2 * x) | ((10 + rect_byte(rw[0], 2) - z) << 16);
+                        e1 = (uint32_t)(rb + 2 * z) | ((10 + rect_byte(rw[1], 2) - (10 - x)) << 16);
+                        e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 + rect_byte(rw[2], 2) - (10 - z)) << 16);
+                        e3 = (uint32_t)(rb + 2 * (10 - z)) | ((10 + rect_byte(rw[3], 2) - x) << 16);
+                    }
+                }
+                es.list[0][lane] = e0; es.list[1][lane] = e1; es.list[2][lane] = e2; es.list[3][lane] = e3;
             }
             __syncwarp();
             if (valid) {
-                const unsigned char *rows8 = reinterpret_cast<const unsigned char *>(ws.rows);
-                for (int b = g; b < cn; b += G) {
-                    uint32_t e = ws.list[k][b];
-                    int roff = (int)(e & 0xFFFu) - 2 * dx;
-                    int sh = cz - (int)((e >> 12) & 15u);
-                    uint32_t v;
-                    if (CLIP) {
-                        int xs = (int)(e >> 16) - dx;
-                        uint32_t R = ((unsigned)xs <= 10u) ? *reinterpret_cast<const unsigned short *>(rows8 + roff) : 0u;
-                        v = sh >= 0 ? (sh > 31 ? 0u : R >> sh) : (sh < -31 ? 0u : R << (-sh));
-                        v &= 0x7FFu;
-                    } else {
-                        uint32_t R = *reinterpret_cast<const unsigned short *>(rows8 + roff);
-                        v = R >> sh;
-                    }
-                    acc += tbl[v];
-                    if (++nacc == 31) {
+                unsigned long long acc = 0ull;
+                for (int b = g; b < cnp; b += 4 * G) {
 #pragma unroll
-                        for (int j = 0; j < 11; j++) cnt[j] += (int)((acc >> (5 * j)) & 31ull);
-                        acc = 0ull;
-                        nacc = 0;
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t e = mylist[b + u * G];
+                        uint32_t v;
+                        if (CLIP) {
+                            const int roff = (int)(e & 0xFFFu) - 2 * dx;
+                            const int sh = cz - (int)((e >> 12) & 15u);
+                            const int xs = (int)(e >> 16) - dx;
+                            const uint32_t R = ((unsigned)xs <= 10u)
+                                                   ? *reinterpret_cast<const unsigned short *>(rows8 + roff) : 0u;
+                            v = sh >= 0 ? (sh > 31 ? 0u : R >> sh) : (sh < -31 ? 0u : R << (-sh));
+                            v &= 0x7FFu;
+                        } else {
+                            const uint32_t e2 = e - 2u * (uint32_t)dx;  // row offset never borrows
+                            const uint32_t R = *reinterpret_cast<const unsigned short *>(rows8 + (e2 & 0xFFFFu));
+                            v = R >> (e2 >> 16);
+                        }
+                        acc += tbl[v];
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 11; j++) cnt[j] += (int)((acc >> (5 * j)) & 31ull);
             }
             __syncwarp();
         }
-#pragma unroll
-        for (int j = 0; j < 11; j++) cnt[j] += (int)((acc >> (5 * j)) & 31ull);
         // combine the block slices of the G lane groups
         for (int s = ppad; s < 32; s <<= 1) {
 #pragma unroll
@@ -199,15 +216,15 @@ __device__ __forceinline__ int eval_max_intersection(WarpScratch &ws, const unsi
 #pragma unroll
             for (int j = 0; j < 11; j++) {
                 if (j < W) {
-                    int sc = key_out ? ((cnt[j] << 12) | (4095 - (kbase + j))) : cnt[j];
+                    const int sc = WANT_KEY ? ((cnt[j] << 12) | (4095 - (kbase + j))) : cnt[j];
                     best = max(best, sc);
                 }
             }
         }
     }
     best = __reduce_max_sync(0xffffffffu, best);
-    if (key_out) {
-        int count = best >> 12;
+    if (WANT_KEY) {
+        const int count = best >> 12;
         *key_out = count > 0 ? 4095 - (best & 4095) : -1;
         return count;
     }

@@ -73,7 +73,7 @@ class IGLUVecEnv:
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
-                 grid_obs=True, render=False, tlist_cap=_lib.TLIST_MAX):
+                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX):
         if render:
             raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
         if reward_mode not in ('on_change', 'every_step'):
@@ -112,8 +112,10 @@ class IGLUVecEnv:
         self._pose = z(6, n, dtype=torch.float64)
         self._init_pose = z(5, n, dtype=torch.float64)
         self._istate = z(8, n, dtype=torch.int32)
-        self._tlist = z(n, int(tlist_cap), dtype=torch.int16)
-        self._trect = z(n, 16, dtype=torch.int8)
+        tlist_cap = _lib.TLIST_HDR + max(64, (int(max_target_blocks) + 7) // 8 * 8)
+        if tlist_cap > _lib.TLIST_ROW_MAX:
+            raise ValueError(f'max_target_blocks must be <= {_lib.TLIST_MAX}')
+        self._tlist = z(n, tlist_cap, dtype=torch.int16)
         self._tmeta = z(8, n, dtype=torch.int32)
         # ---- observations / results ----
         self._obs_grid = z(n, 9, 11, 11, dtype=torch.int32) if self.grid_obs else None
@@ -127,8 +129,7 @@ class IGLUVecEnv:
 
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._st = _lib.State(n, p(self._grid), p(self._init), p(self._target), p(self._pose),
-                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._trect),
-                              p(self._tmeta))
+                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._tmeta))
         self._ob = _lib.Obs(p(self._obs_grid), p(self._obs_target), p(self._obs_pos), p(self._obs_inv),
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
@@ -350,7 +351,7 @@ class IGLUVecEnv:
         self._istate[3, i] = w3
 
     def state_dict(self):
-        keys = ('_grid', '_init', '_target', '_pose', '_init_pose', '_istate', '_tlist', '_trect', '_tmeta')
+        keys = ('_grid', '_init', '_target', '_pose', '_init_pose', '_istate', '_tlist', '_tmeta')
         return {k[1:]: getattr(self, k).clone() for k in keys}
 
     def load_state_dict(self, sd):

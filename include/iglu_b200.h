@@ -34,7 +34,9 @@ extern "C" {
 #define IGLU_ABI_VERSION 1
 #define IGLU_CELLS 1089       /* 9 * 11 * 11, reference tasks/task.py:3-5 */
 #define IGLU_GRID_STRIDE 1104 /* bytes between consecutive envs in int8 grid state */
-#define IGLU_TLIST_MAX 1096   /* max entries (uint16) per env in the target block list */
+#define IGLU_TLIST_MAX 1096   /* max target blocks (uint16 entries) per env */
+#define IGLU_TLIST_HDR 8      /* uint16 slots at the start of a tlist row holding the 16-byte rectangle header */
+#define IGLU_TLIST_ROW_MAX (IGLU_TLIST_HDR + IGLU_TLIST_MAX) /* 1104 uint16 = 2208 bytes per row */
 
 typedef enum iglu_status {
     IGLU_OK = 0,
@@ -68,7 +70,8 @@ typedef struct iglu_config {
                                    at the start of the next step call, then stepped */
     int32_t reward_mode;        /* iglu_reward_mode */
     int32_t write_grid_obs;     /* 1: materialise obs['grid'] int32[n,9,11,11] every step (env.py:288) */
-    int32_t tlist_cap;          /* entries per env in iglu_state.tlist (multiple of 8, <= IGLU_TLIST_MAX) */
+    int32_t tlist_cap;          /* uint16 slots per row of iglu_state.tlist: multiple of 8, >= 72,
+                                   <= IGLU_TLIST_ROW_MAX; holds IGLU_TLIST_HDR + max target blocks */
     int32_t reserved;
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
@@ -86,10 +89,11 @@ typedef struct iglu_state {
     int32_t *istate;   /* [8][n]  w0..w2: inventory 6 x int16; w3: active | tis<<8 | done_prev<<16 | err<<24;
                                   w4: step_no; w5: nnz(grid - init) (task.prev_grid_size); w6: max_int;
                                   w7: reserved */
-    uint16_t *tlist;   /* [n][tlist_cap]  non-zero cells of (target - init), rotation 0:
+    uint16_t *tlist;   /* [n][tlist_cap]  row = 16-byte header + block list of the synthetic task.
+                                  header: 16 int8, per rotation r: dx_lo, dx_hi, dz_lo, dz_hi of the admissible
+                                  shifts (task.py:57-72; always a rectangle);
+                                  then the non-zero cells of (target - init), rotation 0, ascending cell index:
                                   y | x<<4 | z<<8 | (value & 15)<<12 */
-    int8_t *trect;     /* [n][16]  per rotation r: dx_lo, dx_hi, dz_lo, dz_hi of the admissible shifts
-                                  (task.py:57-72; always a rectangle) */
     int32_t *tmeta;    /* [8][n]  w0: number of tlist entries; w1: target_size (task.py:35);
                                   w2..w4: inventory after reset, 6 x int16 (env.py:243-246);
                                   w5: 1 if the starting grid is non-empty; w6: 1 once a task is set; w7: reserved */
@@ -123,7 +127,7 @@ void iglu_ctx_destroy(iglu_ctx *ctx);
  *   target, start : device int8 [count][1089] dense (start may be NULL = empty starting grid [])
  *   init_pose     : device double [count][5] (x, y, z, yaw, pitch) or NULL = (0,0,0,0,0)
  *   env_idx       : device int32 [count] destination env of each row, or NULL = rows 0..count-1
- * Fills state.target/init/tlist/trect/tmeta (+ obs.target_grid). Does NOT reset; call iglu_reset. */
+ * Fills state.target/init/tlist/tmeta (+ obs.target_grid). Does NOT reset; call iglu_reset. */
 int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const int8_t *target,
                    const int8_t *start, const double *init_pose, const int32_t *env_idx, int64_t count,
                    void *stream);
