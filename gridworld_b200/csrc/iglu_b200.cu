@@ -102,10 +102,10 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
     for (int m = lane; m < nbody; m += 32) {
         const uint32_t w = __funnelshift_r(sg[m], sg[m + 1], 8 * h);  // bytes h + 4m .. h + 4m + 3
         int4 v;
-        v.x = (int)__byte_perm(w, 0, 0x8880);  // sign-extend byte 0
-        v.y = (int)__byte_perm(w, 0, 0x9991);
-        v.z = (int)__byte_perm(w, 0, 0xAAA2);
-        v.w = (int)__byte_perm(w, 0, 0xBBB3);
+        v.x = (int)(int8_t)(w);  // sign-extend each byte
+        v.y = (int)(int8_t)(w >> 8);
+        v.z = (int)(int8_t)(w >> 16);
+        v.w = (int)(int8_t)(w >> 24);
         __stcs(o4 + m, v);
     }
     const int t0 = h + 4 * nbody;

@@ -36,6 +36,7 @@ constexpr uint32_t DUMMY_ENTRY = 2 * 50;         // row 50 of class 0 (never set
 struct __align__(16) EvalScratch {
     uint32_t rows[ROWS_WORDS];      // z-reversed occupancy rows, two uint16 per word
     uint32_t list[4][LIST_CAP];     // expanded target blocks per rotation
+    uint32_t planes[16];            // per class code: bit y set when the grid has a block on that level
 };
 
 // spread table: bit j of v -> bit 5*j of the result (eleven 5-bit fields in a uint64).
@@ -54,6 +55,7 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
                                            bool has_init, int lane) {
     int4 *rz = reinterpret_cast<int4 *>(es.rows);
     for (int q = lane; q < ROWS_WORDS / 4; q += 32) rz[q] = make_int4(0, 0, 0, 0);
+    if (lane < 16) es.planes[lane] = 0u;
     __syncwarp();
     const int4 *g4 = reinterpret_cast<const int4 *>(grid);
     const int4 *i4 = reinterpret_cast<const int4 *>(init);
@@ -75,6 +77,7 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
                     const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
                     const int row = (d & 15) * ROWS_PER_CLASS + y * 11 + x;
                     atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
+                    atomicOr(&es.planes[d & 15], 1u << y);
                 }
             }
         }
@@ -103,79 +106,81 @@ __device__ __forceinline__ int rect_byte(int w, int i) { return (int)(int8_t)((u
 //   tlist : nblk packed target blocks (y | x<<4 | z<<8 | code<<12), shared or global memory
 //   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
 //   CLIP  : true when shifts may move target cells outside the grid (full_grid rectangles)
+// Target blocks whose (class, y) plane holds no grid block cannot match under any shift; they are
+// dropped while the list is expanded (es.planes, filled by build_rows), so the cost follows the
+// number of target blocks that CAN match rather than the target size.
 // Returns (warp-uniform) best count; if WANT_KEY also the first (rot, dx, dz) reaching it in the
 // reference's iteration order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if best == 0.
 template <bool CLIP, bool WANT_KEY>
 __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsigned long long *__restrict__ tbl,
                                                      const uint16_t *__restrict__ tlist, int nblk, int4 rc,
                                                      int n_rot, int lane, int *key_out) {
-    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
-    // ---- enumerate work items (k, dx[, dz-chunk of <= 11 when CLIP]) ----
-    int nx[4], nch[4], base[5];
-    base[0] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int wx = rect_byte(rw[k], 1) - rect_byte(rw[k], 0) + 1;
-        const int wz = rect_byte(rw[k], 3) - rect_byte(rw[k], 2) + 1;
-        nx[k] = (k < n_rot && wx > 0 && wz > 0) ? wx : 0;
-        nch[k] = CLIP ? (wz + 10) / 11 : 1;
-        base[k + 1] = base[k] + nx[k] * nch[k];
-    }
-    const int T = base[4];
     if (WANT_KEY) *key_out = -1;
-    if (T == 0 || nblk == 0) return 0;
-    int ppad = 32;
-    if (T <= 16) { ppad = 4; while (ppad < T) ppad <<= 1; }
-    const int G = 32 / ppad;  // 1, 2, 4 or 8 lane groups share the blocks of one work item
-    const int p = lane & (ppad - 1), g = lane / ppad;
+    if (nblk == 0) return 0;
+    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
+    // ---- work items: lane -> (rotation k, dx index, block-slice g); s = ceil(log2(max dx count)) ----
+    int nxmax = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) nxmax = max(nxmax, rect_byte(rw[k], 1) - rect_byte(rw[k], 0) + 1);
+    const int s = nxmax <= 1 ? 0 : (nxmax <= 2 ? 1 : (nxmax <= 4 ? 2 : 3));
+    const int G = 8 >> s;                      // lane groups sharing the blocks of one work item
+    const int dxi0 = lane & ((1 << s) - 1);
+    const int k = (lane >> s) & 3;
+    const int g = lane >> (s + 2);
+    const int rk = k == 0 ? rw[0] : (k == 1 ? rw[1] : (k == 2 ? rw[2] : rw[3]));
+    const int dx_lo = rect_byte(rk, 0), nxk = rect_byte(rk, 1) - dx_lo + 1;
+    const int dz_lo = rect_byte(rk, 2), wz = rect_byte(rk, 3) - dz_lo + 1;
+    const uint32_t *mylist = es.list[k];
     const unsigned char *rows8 = reinterpret_cast<const unsigned char *>(es.rows);
+    const int n_dxpass = (nxmax + 7) >> 3;               // 2 only when some rotation has 9..11 dx values
+    const int n_zpass = CLIP ? (21 + 10) / 11 : 1;       // dz chunks of 11 (up to 21 values when CLIP)
     int best = 0;  // WANT_KEY: count << 12 | 4095 - key
 
-    for (int pass0 = 0; pass0 < T; pass0 += 32) {
-        const int item = pass0 + p;
-        const bool valid = item < T;
-        int k = 0;
-#pragma unroll
-        for (int q = 1; q < 4; q++) if (item >= base[q]) k = q;
-        int rk = rw[0], nchk = nch[0], basek = base[0];
-#pragma unroll
-        for (int q = 1; q < 4; q++) if (q == k) { rk = rw[q]; nchk = nch[q]; basek = base[q]; }
-        const int local = item - basek;
-        const int ch = CLIP ? local % nchk : 0;
-        const int dx = rect_byte(rk, 0) + (CLIP ? local / nchk : local);
-        const int dzlo = rect_byte(rk, 2) + 11 * ch;
-        int W = rect_byte(rk, 3) - dzlo + 1;
+    for (int pass = 0; pass < n_dxpass * n_zpass; pass++) {
+        const int dxi = dxi0 + 8 * (CLIP ? pass / n_zpass : pass);
+        const int ch = CLIP ? pass % n_zpass : 0;
+        const int dx = dx_lo + dxi;
+        const int dzlo = dz_lo + 11 * ch;
+        int W = wz - 11 * ch;
         if (W > 11) W = 11;
+        const bool valid = k < n_rot && dxi < nxk && W > 0;
         const int cz = 10 + dzlo;  // CLIP: shift = cz - z_k
-        const uint32_t *mylist = es.list[k];
-
-        int cnt[11];
-#pragma unroll
-        for (int j = 0; j < 11; j++) cnt[j] = 0;
+        // running totals: fifteen-bit fields, field j of wide[j % 3] at bit 15 * (j / 3)
+        unsigned long long wide0 = 0ull, wide1 = 0ull, wide2 = 0ull;
+        const unsigned long long M = 0x1Full | (0x1Full << 15) | (0x1Full << 30) | (0x1Full << 45);
 
         for (int c0 = 0; c0 < nblk; c0 += LIST_CHUNK) {
             const int cn = min(LIST_CHUNK, nblk - c0);
-            const int cnp = (cn + 4 * G - 1) & ~(4 * G - 1);  // padded with entries that add nothing
-            // expand: lane b computes the four rotated entries of block b
-            {
-                uint32_t e0 = DUMMY_ENTRY, e1 = DUMMY_ENTRY, e2 = DUMMY_ENTRY, e3 = DUMMY_ENTRY;
-                if (lane < cn) {
-                    const uint32_t e = tlist[c0 + lane];
-                    const int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
-                    const int rb = (code * ROWS_PER_CLASS + y * 11) * 2;
-                    if (CLIP) {  // rowoff2 | z_k << 12 | x_k << 16
-                        e0 = (uint32_t)(rb + 2 * x) | (z << 12) | (x << 16);
-                        e1 = (uint32_t)(rb + 2 * z) | ((10 - x) << 12) | (z << 16);
-                        e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 - z) << 12) | ((10 - x) << 16);
-                        e3 = (uint32_t)(rb + 2 * (10 - z)) | (x << 12) | ((10 - z) << 16);
-                    } else {  // rowoff2 | shift << 16 with shift = 10 + dz_lo(k) - z_k
-                        e0 = (uint32_t)(rb + 2 * x) | ((10 + rect_byte(rw[0], 2) - z) << 16);
-                        e1 = (uint32_t)(rb + 2 * z) | ((10 + rect_byte(rw[1], 2) - (10 - x)) << 16);
-                        e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 + rect_byte(rw[2], 2) - (10 - z)) << 16);
-                        e3 = (uint32_t)(rb + 2 * (10 - z)) | ((10 + rect_byte(rw[3], 2) - x) << 16);
-                    }
+            // expand: lane b computes the four rotated entries of block b; blocks of empty planes are dropped
+            uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            bool keep = false;
+            if (lane < cn) {
+                const uint32_t e = tlist[c0 + lane];
+                const int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
+                keep = (es.planes[code] >> y) & 1u;
+                const int rb = (code * ROWS_PER_CLASS + y * 11) * 2;
+                if (CLIP) {  // rowoff2 | z_k << 12 | x_k << 16
+                    e0 = (uint32_t)(rb + 2 * x) | (z << 12) | (x << 16);
+                    e1 = (uint32_t)(rb + 2 * z) | ((10 - x) << 12) | (z << 16);
+                    e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 - z) << 12) | ((10 - x) << 16);
+                    e3 = (uint32_t)(rb + 2 * (10 - z)) | (x << 12) | ((10 - z) << 16);
+                } else {  // rowoff2 | shift << 16 with shift = 10 + dz_lo(k) - z_k
+                    e0 = (uint32_t)(rb + 2 * x) | ((10 + rect_byte(rw[0], 2) - z) << 16);
+                    e1 = (uint32_t)(rb + 2 * z) | ((10 + rect_byte(rw[1], 2) - (10 - x)) << 16);
+                    e2 = (uint32_t)(rb + 2 * (10 - x)) | ((10 + rect_byte(rw[2], 2) - (10 - z)) << 16);
+                    e3 = (uint32_t)(rb + 2 * (10 - z)) | ((10 + rect_byte(rw[3], 2) - x) << 16);
                 }
-                es.list[0][lane] = e0; es.list[1][lane] = e1; es.list[2][lane] = e2; es.list[3][lane] = e3;
+            }
+            const unsigned km = __ballot_sync(0xffffffffu, keep);
+            const int ck = __popc(km);
+            if (ck == 0) continue;  // warp-uniform
+            const int cnp = (ck + 4 * G - 1) & ~(4 * G - 1);  // padded with entries that add nothing
+            es.list[0][lane] = DUMMY_ENTRY; es.list[1][lane] = DUMMY_ENTRY;
+            es.list[2][lane] = DUMMY_ENTRY; es.list[3][lane] = DUMMY_ENTRY;
+            __syncwarp();
+            if (keep) {
+                const int pos = __popc(km & ((1u << lane) - 1u));
+                es.list[0][pos] = e0; es.list[1][pos] = e1; es.list[2][pos] = e2; es.list[3][pos] = e3;
             }
             __syncwarp();
             if (valid) {
@@ -194,29 +199,33 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
                             v = sh >= 0 ? (sh > 31 ? 0u : R >> sh) : (sh < -31 ? 0u : R << (-sh));
                             v &= 0x7FFu;
                         } else {
-                            const uint32_t e2 = e - 2u * (uint32_t)dx;  // row offset never borrows
-                            const uint32_t R = *reinterpret_cast<const unsigned short *>(rows8 + (e2 & 0xFFFFu));
-                            v = R >> (e2 >> 16);
+                            const uint32_t ed = e - 2u * (uint32_t)dx;  // row offset never borrows
+                            const uint32_t R = *reinterpret_cast<const unsigned short *>(rows8 + (ed & 0xFFFFu));
+                            v = R >> (ed >> 16);
                         }
                         acc += tbl[v];
                     }
                 }
-#pragma unroll
-                for (int j = 0; j < 11; j++) cnt[j] += (int)((acc >> (5 * j)) & 31ull);
+                wide0 += acc & M;
+                wide1 += (acc >> 5) & M;
+                wide2 += (acc >> 10) & M;
             }
             __syncwarp();
         }
         // combine the block slices of the G lane groups
-        for (int s = ppad; s < 32; s <<= 1) {
-#pragma unroll
-            for (int j = 0; j < 11; j++) cnt[j] += __shfl_xor_sync(0xffffffffu, cnt[j], s);
+        for (int st = 4 << s; st < 32; st <<= 1) {
+            wide0 += __shfl_xor_sync(0xffffffffu, wide0, st);
+            wide1 += __shfl_xor_sync(0xffffffffu, wide1, st);
+            wide2 += __shfl_xor_sync(0xffffffffu, wide2, st);
         }
         if (valid) {
             const int kbase = k * 441 + (dx + 10) * 21 + (dzlo + 10);
 #pragma unroll
             for (int j = 0; j < 11; j++) {
                 if (j < W) {
-                    const int sc = WANT_KEY ? ((cnt[j] << 12) | (4095 - (kbase + j))) : cnt[j];
+                    const unsigned long long wj = (j % 3 == 0) ? wide0 : (j % 3 == 1 ? wide1 : wide2);
+                    const int c = (int)((wj >> (15 * (j / 3))) & 0x7FFFull);
+                    const int sc = WANT_KEY ? ((c << 12) | (4095 - (kbase + j))) : c;
                     best = max(best, sc);
                 }
             }

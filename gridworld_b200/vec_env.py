@@ -5,6 +5,7 @@ This is the batched form of the reference's GridWorld (reference gridworld/env.p
 render=False, vector_state=True. PyTorch only hands out the device tensors; every state update,
 observation and reward is computed by libiglu_b200.so (there is no CPU / eager fallback).
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -151,7 +152,16 @@ class IGLUVecEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _guard(self):
+        """Makes self.device current for the C-ABI call (cheap no-op when it already is)."""
+        if torch.cuda.current_device() == self.device.index:
+            return contextlib.nullcontext()
+        return torch.cuda.device(self.device)
+
     def _dev(self, x, dtype, shape):
+        if isinstance(x, torch.Tensor) and x.dtype == dtype and x.device == self.device and x.is_contiguous() \
+                and tuple(x.shape) == tuple(shape):
+            return x
         t = torch.as_tensor(x)
         if t.dtype != dtype or t.device != self.device:
             t = t.to(device=self.device, dtype=dtype)
@@ -161,7 +171,7 @@ class IGLUVecEnv:
         return t
 
     def _count(self):
-        self.gpu_launches += self._L.iglu_last_launch_count(self._ctx)
+        self.gpu_launches += 1  # every C-ABI entry point of this class launches exactly one kernel
 
     # ------------------------------------------------------------------ tasks
     def set_tasks(self, targets, starts=None, init_poses=None, env_idx=None, reset=True):
@@ -232,7 +242,7 @@ class IGLUVecEnv:
         self._check_task()
         n = self.num_envs
         L, st, ob = self._L, C.byref(self._st), C.byref(self._ob)
-        with torch.cuda.device(self.device):
+        with self._guard():
             if self._kind == _lib.WALKING_DISCRETE:
                 a = self._dev(actions, torch.int32, (n,))
                 _lib.check(L.iglu_step_walking(self._ctx, st, a.data_ptr(), ob, self._stream()))
@@ -267,7 +277,7 @@ class IGLUVecEnv:
         for t, dt in ((actions_host, torch.int32), (reward_host, torch.float64), (done_host, torch.uint8)):
             if t.device.type != 'cpu' or t.dtype != dt or not t.is_contiguous() or t.numel() != self.num_envs:
                 raise ValueError('step_host needs contiguous CPU tensors of dtype int32 / float64 / uint8, [n]')
-        with torch.cuda.device(self.device):
+        with self._guard():
             _lib.check(self._L.iglu_step_walking_host(self._ctx, C.byref(self._st), actions_host.data_ptr(),
                                                       self._actions_dev.data_ptr(), C.byref(self._ob),
                                                       reward_host.data_ptr(), done_host.data_ptr(),
