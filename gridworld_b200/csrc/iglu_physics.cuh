@@ -81,12 +81,17 @@ __device__ __forceinline__ double strafe_degrees(double s0, double s1) {
 }
 
 // `key in self.world`: the 37x37 floor at y = -2 (world.py:60-71) plus the placed blocks mirrored
-// in grid[y+1, x+5, z+5] (env.py:136-142).  Branch-free: one predicated byte load.
-__device__ __forceinline__ bool world_has(const int8_t *__restrict__ g, int x, int y, int z) {
+// in grid[y+1, x+5, z+5] (env.py:136-142).  Split in two so that a batch of lookups issues all its
+// loads before any result is consumed: world_addr() gives an always-valid byte offset (0 when the
+// key is outside the zone), world_has() combines the loaded byte with the bounds / floor tests.
+__device__ __forceinline__ int world_addr(int x, int y, int z) {
     const bool in_zone = (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
-    const int c = in_zone ? (int)g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)] : 0;
+    return in_zone ? (y + 1) * 121 + (x + 5) * 11 + (z + 5) : 0;
+}
+__device__ __forceinline__ bool world_has(int cell_value, int x, int y, int z) {
+    const bool in_zone = (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
     const bool floor_hit = y == -2 && abs(x) <= 18 && abs(z) <= 18;
-    return floor_hit || c != 0;
+    return floor_hit || (in_zone && cell_value != 0);
 }
 
 // `self.world[key]` for a key known to be present: WHITE (-1) / GREY (0) floor or the block colour.
@@ -104,7 +109,21 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
                                         double &agent_dy) {
     const double pad = 0.25;
     const int nx = (int)rint(px), ny = (int)rint(py), nz = (int)rint(pz);
-    // gather the 12 neighbour cells (6 faces x 2 heights) first: independent loads
+    // gather the 12 neighbour cells (6 faces x 2 heights) first: independent unconditional loads
+    int cv[12];
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
+        const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int ox = nx, oy = ny - h, oz = nz;
+            if (axis == 0) ox += sgn;
+            else if (axis == 1) oy += sgn;
+            else oz += sgn;
+            cv[2 * f + h] = g[world_addr(ox, oy, oz)];
+        }
+    }
     unsigned solid = 0;
 #pragma unroll
     for (int f = 0; f < 6; f++) {
@@ -116,7 +135,7 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
             if (axis == 0) ox += sgn;
             else if (axis == 1) oy += sgn;
             else oz += sgn;
-            solid |= (unsigned)world_has(g, ox, oy, oz) << (2 * f + h);
+            solid |= (unsigned)world_has(cv[2 * f + h], ox, oy, oz) << (2 * f + h);
         }
     }
 #pragma unroll
@@ -197,14 +216,16 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         int kx = 0, ky = 0, kz = 0, qx = 0, qy = 0, qz = 0;
         bool has_prev = false, hit = false;
         for (int i0 = 0; i0 < 40 && !hit; i0 += 8) {
-            int bx[8], by[8], bz[8];
-            unsigned solid = 0;
+            int bx[8], by[8], bz[8], cv[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 bx[j] = (int)rint(px); by[j] = (int)rint(py); bz[j] = (int)rint(pz);
-                solid |= (unsigned)world_has(g, bx[j], by[j], bz[j]) << j;
+                cv[j] = g[world_addr(bx[j], by[j], bz[j])];
                 px = px + sx; py = py + syy; pz = pz + sz;
             }
+            unsigned solid = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) solid |= (unsigned)world_has(cv[j], bx[j], by[j], bz[j]) << j;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 if (!hit) {

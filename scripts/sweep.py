@@ -67,6 +67,10 @@ def reward_only(n, support, rho, reps=5):
 
 
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'one':  # one: <reward_mode> <inplace 0/1> <envs> [steps]
+        K = int(sys.argv[5]) if len(sys.argv) > 5 else 30
+        print(json.dumps(walking(int(sys.argv[4]), 'compact', 0.2, sys.argv[2], bool(int(sys.argv[3])), K=K)))
+        sys.exit(0)
     which = sys.argv[1:] or ['walking', 'flying', 'reward']
     if 'walking' in which:
         for rm in ('every_step', 'on_change'):
