@@ -81,17 +81,27 @@ __device__ __forceinline__ double strafe_degrees(double s0, double s1) {
 }
 
 // `key in self.world`: the 37x37 floor at y = -2 (world.py:60-71) plus the placed blocks mirrored
-// in grid[y+1, x+5, z+5] (env.py:136-142).  Split in two so that a batch of lookups issues all its
-// loads before any result is consumed: world_addr() gives an always-valid byte offset (0 when the
-// key is outside the zone), world_has() combines the loaded byte with the bounds / floor tests.
-__device__ __forceinline__ int world_addr(int x, int y, int z) {
-    const bool in_zone = (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
-    return in_zone ? (y + 1) * 121 + (x + 5) * 11 + (z + 5) : 0;
+// in grid[y+1, x+5, z+5] (env.py:136-142).  A lookup is split in two so that a batch issues all its
+// loads before any result is consumed: in_zone()/cell_of() say whether a byte has to be fetched at
+// all (a scattered 1-byte load costs a full L1 wavefront per lane, so keys outside the zone, floor
+// keys and keys equal to the previous sample are predicated off), world_has() combines the byte
+// with the bounds / floor tests.
+__device__ __forceinline__ bool in_zone(int x, int y, int z) {
+    return (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
+}
+__device__ __forceinline__ int cell_of(int x, int y, int z) { return (y + 1) * 121 + (x + 5) * 11 + (z + 5); }
+
+// Predicated signed-byte load (0 when pred is false; no memory access then). Inline PTX so that the
+// compiler neither turns the predicate into a branch nor waits on one load before issuing the next.
+__device__ __forceinline__ int ld_s8_if(const int8_t *p, bool pred) {
+    int v;
+    asm volatile("{\n .reg .pred q;\n setp.ne.b32 q, %2, 0;\n mov.b32 %0, 0;\n @q ld.global.s8 %0, [%1];\n}"
+                 : "=r"(v) : "l"(p), "r"((int)pred) : "memory");
+    return v;
 }
 __device__ __forceinline__ bool world_has(int cell_value, int x, int y, int z) {
-    const bool in_zone = (unsigned)(x + 5) <= 10u && (unsigned)(z + 5) <= 10u && (unsigned)(y + 1) <= 8u;
     const bool floor_hit = y == -2 && abs(x) <= 18 && abs(z) <= 18;
-    return floor_hit || (in_zone && cell_value != 0);
+    return floor_hit || cell_value != 0;  // cell_value is 0 for keys outside the zone
 }
 
 // `self.world[key]` for a key known to be present: WHITE (-1) / GREY (0) floor or the block colour.
@@ -109,19 +119,26 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
                                         double &agent_dy) {
     const double pad = 0.25;
     const int nx = (int)rint(px), ny = (int)rint(py), nz = (int)rint(pz);
-    // gather the 12 neighbour cells (6 faces x 2 heights) first: independent unconditional loads
+    // A face can only act when the overlap along its axis is >= pad, and the two faces of one axis
+    // exclude each other (after +axis pushes the position back the -axis overlap is -pad), so which
+    // faces need their two neighbour cells is known from the incoming position: fetch only those,
+    // all loads issued before any is used.
+    const double ex = px - (double)nx, ey = py - (double)ny, ez = pz - (double)nz;
     int cv[12];
 #pragma unroll
     for (int f = 0; f < 6; f++) {
         const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
         const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
+        const double e = (axis == 0) ? ex : (axis == 1 ? ey : ez);
+        const bool face_on = e * (double)sgn >= pad;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             int ox = nx, oy = ny - h, oz = nz;
             if (axis == 0) ox += sgn;
             else if (axis == 1) oy += sgn;
             else oz += sgn;
-            cv[2 * f + h] = g[world_addr(ox, oy, oz)];
+            const bool need = face_on && in_zone(ox, oy, oz);
+            cv[2 * f + h] = ld_s8_if(g + (need ? cell_of(ox, oy, oz) : 0), need);
         }
     }
     unsigned solid = 0;
@@ -217,10 +234,17 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         bool has_prev = false, hit = false;
         for (int i0 = 0; i0 < 40 && !hit; i0 += 8) {
             int bx[8], by[8], bz[8], cv[8];
+            int lx = qx, ly = qy, lz = qz;  // key of the sample before this batch (valid when has_prev)
+            bool lvalid = has_prev;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
                 bx[j] = (int)rint(px); by[j] = (int)rint(py); bz[j] = (int)rint(pz);
-                cv[j] = g[world_addr(bx[j], by[j], bz[j])];
+                // a sample whose key equals the previous sample's key is never looked up (world.py:95)
+                const bool fresh = !lvalid || bx[j] != lx || by[j] != ly || bz[j] != lz;
+                const bool need = fresh && in_zone(bx[j], by[j], bz[j]);
+                cv[j] = ld_s8_if(g + (need ? cell_of(bx[j], by[j], bz[j]) : 0), need);
+                lx = bx[j]; ly = by[j]; lz = bz[j];
+                lvalid = true;
                 px = px + sx; py = py + syy; pz = pz + sz;
             }
             unsigned solid = 0;
