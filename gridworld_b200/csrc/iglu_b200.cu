@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     const bool grid_obs = p.cfg.write_grid_obs && p.obs.grid != nullptr;
     const bool early = grid_obs || every_step;  // the set of envs phase B touches is known before phase A
+    const bool alternate = (p.cfg.reserved & 1) == 0;  // reserved bit 0 = 1 disables the phase alternation
     const int cap = p.cfg.tlist_cap;
     uint32_t seq_issue = 0, seq_cons = 0;  // ring sequence numbers (warp-uniform, live across groups)
 
@@ -197,15 +198,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
             }
             seq_issue++;
         };
-        unsigned pend = 0, todo = 0;
-        if (early) {
-            todo = pend = __ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0));
-            for (int f = 0; f < NB && pend; f++) {
-                issue(__ffs(pend) - 1);
-                pend &= pend - 1;
-            }
-        }
-
         Action act;
         act.s0 = act.s1 = act.jump = act.cam0 = act.cam1 = 0.0;
         act.hotbar = 0; act.remove = act.add = false;
@@ -249,68 +241,97 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
 
         const int dsize_old = dsize;
         int edit_cell = -1, edit_val = 0;
-        if (valid) {
-            step_no += 1;  // env.py:276
-            world_step(p.st.grid + i * GSTRIDE, p.st.init + i * GSTRIDE, has_start, a, act, flying,
-                       p.cfg.select_and_place != 0, dsize, edit_cell, edit_val);
-            p.st.pose[0 * n + i] = a.x; p.st.pose[1 * n + i] = a.y; p.st.pose[2 * n + i] = a.z;
-            p.st.pose[3 * n + i] = a.yaw; p.st.pose[4 * n + i] = a.pitch; p.st.pose[5 * n + i] = a.dy;
-            // env.py:283-289 (float32 casts round to nearest even)
-            if (p.obs.agent_pos) {
-                float *ap = p.obs.agent_pos + 5 * i;
-                ap[0] = (float)a.x; ap[1] = (float)a.y; ap[2] = (float)a.z;
-                ap[3] = (float)a.pitch; ap[4] = (float)a.yaw;
+        auto run_physics = [&]() {
+            if (valid) {
+                step_no += 1;  // env.py:276
+                world_step(p.st.grid + i * GSTRIDE, p.st.init + i * GSTRIDE, has_start, a, act, flying,
+                           p.cfg.select_and_place != 0, dsize, edit_cell, edit_val);
+                p.st.pose[0 * n + i] = a.x; p.st.pose[1 * n + i] = a.y; p.st.pose[2 * n + i] = a.z;
+                p.st.pose[3 * n + i] = a.yaw; p.st.pose[4 * n + i] = a.pitch; p.st.pose[5 * n + i] = a.dy;
+                // env.py:283-289 (float32 casts round to nearest even)
+                if (p.obs.agent_pos) {
+                    float *ap = p.obs.agent_pos + 5 * i;
+                    ap[0] = (float)a.x; ap[1] = (float)a.y; ap[2] = (float)a.z;
+                    ap[3] = (float)a.pitch; ap[4] = (float)a.yaw;
+                }
+                if (p.obs.inventory) {
+                    float *iv = p.obs.inventory + 6 * i;
+                    iv[0] = (float)lo16(a.inv01); iv[1] = (float)hi16(a.inv01); iv[2] = (float)lo16(a.inv23);
+                    iv[3] = (float)hi16(a.inv23); iv[4] = (float)lo16(a.inv45); iv[5] = (float)hi16(a.inv45);
+                }
+                if (p.obs.compass) p.obs.compass[i] = (float)(a.yaw - 180.0);
             }
-            if (p.obs.inventory) {
-                float *iv = p.obs.inventory + 6 * i;
-                iv[0] = (float)lo16(a.inv01); iv[1] = (float)hi16(a.inv01); iv[2] = (float)lo16(a.inv23);
-                iv[3] = (float)hi16(a.inv23); iv[4] = (float)lo16(a.inv45); iv[5] = (float)hi16(a.inv45);
-            }
-            if (p.obs.compass) p.obs.compass[i] = (float)(a.yaw - 180.0);
-        }
-        __syncwarp();
+            __syncwarp();
+        };
 
-        // ------------------------------------------------------------- phase B
-        const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
-        const bool want_eval = valid && nblk > 0 && (every_step || changed);
-        const unsigned em = __ballot_sync(0xffffffffu, want_eval);
+        // ring consumer: one env at a time -- wait for its slot, optionally apply this step's edit to the
+        // staged grid, widen it into obs['grid'], evaluate maximal_intersection, refill the slot.
+        unsigned pend = 0, todo = 0;
         const unsigned hm = __ballot_sync(0xffffffffu, has_start);
-        if (!early) {
-            todo = pend = em;
+        int mi_eval = 0;
+        auto ring_start = [&](unsigned mask) {
+            todo = pend = mask;
             for (int f = 0; f < NB && pend; f++) {
                 issue(__ffs(pend) - 1);
                 pend &= pend - 1;
             }
-        }
-        int mi_eval = 0;
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int64_t ej = grp * 32 + j;
-            const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
-            Slot &sl = ws.slot[seq_cons % NB];
-            if (ev && hs) load_grid_smem(ws.init, p.st.init + ej * GSTRIDE, lane);
-            mbar_wait(&ws.bar[seq_cons % NB], (seq_cons / NB) & 1u);
-            // The copy may have raced with this step's edit of the same env: apply it to the staged grid.
-            const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
-            const int evl = __shfl_sync(0xffffffffu, edit_val, j);
-            if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
-            __syncwarp();
-            if (grid_obs) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
-            if (ev) {
-                build_rows(ws.es, sl.grid, ws.init, hs, lane);
-                const int nb = __shfl_sync(0xffffffffu, nblk, j);
-                const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
-                const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
-                const int r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
-                if (lane == j) mi_eval = r;
+        };
+        auto ring_drain = [&](bool obs_on, unsigned em, bool patch, bool keep) {
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t ej = grp * 32 + j;
+                const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
+                Slot &sl = ws.slot[seq_cons % NB];
+                if (ev && hs) load_grid_smem(ws.init, p.st.init + ej * GSTRIDE, lane);
+                mbar_wait(&ws.bar[seq_cons % NB], (seq_cons / NB) & 1u);
+                if (patch) {  // the copy may have raced with this step's edit of the same env
+                    const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
+                    const int evl = __shfl_sync(0xffffffffu, edit_val, j);
+                    if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
+                }
+                __syncwarp();
+                if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
+                if (ev) {
+                    build_rows(ws.es, sl.grid, ws.init, hs, lane);
+                    const int nb = __shfl_sync(0xffffffffu, nblk, j);
+                    const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
+                    const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
+                    const int r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
+                    if (keep && lane == j) mi_eval = r;
+                }
+                __syncwarp();  // every lane is done with the slot before it is refilled
+                seq_cons++;
+                if (pend) {
+                    issue(__ffs(pend) - 1);
+                    pend &= pend - 1;
+                }
             }
-            __syncwarp();  // every lane is done with the slot before it is refilled
-            seq_cons++;
-            if (pend) {
-                issue(__ffs(pend) - 1);
-                pend &= pend - 1;
-            }
+        };
+
+        // Half of the warps stream the observations first and run the physics afterwards, the other half
+        // the other way round, so that on every SM the latency-bound fp64 phase of one half overlaps the
+        // HBM-bound phase of the other. Observation-first warps stage the PRE-step grid: the (at most one)
+        // cell this step edits is patched into obs['grid'] by its own lane afterwards and only envs whose
+        // block count changed are evaluated again -- for all others the pre-step grid IS the post-step grid.
+        const bool b_first = early && alternate && (wid & 1);
+        if (b_first) {
+            const unsigned pre_eval = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
+            const unsigned obs_mask = grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u;
+            ring_start(obs_mask | pre_eval);
+            ring_drain(grid_obs, pre_eval, false, false);
+            run_physics();
+            if (grid_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
+            const unsigned fix = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != dsize_old);
+            ring_start(fix);
+            ring_drain(false, fix, true, true);
+        } else {
+            if (early) ring_start(__ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0)));
+            run_physics();
+            const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
+            const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
+            if (!early) ring_start(em);
+            ring_drain(grid_obs, em, true, true);
         }
 
         // ------------------------------------------------------------- phase C

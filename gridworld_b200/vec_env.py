@@ -66,7 +66,8 @@ class IGLUVecEnv:
       num_envs, device, auto_reset (an env that returned done is reset at the start of the next
       step call and then stepped -- per env this is exactly `reset(); step(a)` on the reference),
       reward_mode ('on_change' = the reference's gate, 'every_step' = evaluate maximal_intersection
-      on every step; outputs are identical), grid_obs (materialise the int32 obs['grid'] each step).
+      on every step; outputs are identical), grid_obs (materialise the int32 obs['grid'] each step),
+      alternate_phases (scheduling only: half of the warps write observations before the physics).
 
     step() returns device tensors that alias persistent buffers: a policy reads them in place.
     """
@@ -74,7 +75,7 @@ class IGLUVecEnv:
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
-                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX):
+                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=True):
         if render:
             raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
         if reward_mode not in ('on_change', 'every_step'):
@@ -135,7 +136,7 @@ class IGLUVecEnv:
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
                           _lib.REWARD_EVERY_STEP if reward_mode == 'every_step' else _lib.REWARD_ON_CHANGE,
-                          int(self.grid_obs), int(tlist_cap), 0,
+                          int(self.grid_obs), int(tlist_cap), 0 if alternate_phases else 1,
                           float(right_placement_scale), float(wrong_placement_scale))
         self._ctx = C.c_void_p()
         with torch.cuda.device(dev):

@@ -72,7 +72,8 @@ typedef struct iglu_config {
     int32_t write_grid_obs;     /* 1: materialise obs['grid'] int32[n,9,11,11] every step (env.py:288) */
     int32_t tlist_cap;          /* uint16 slots per row of iglu_state.tlist: multiple of 8, >= 72,
                                    <= IGLU_TLIST_ROW_MAX; holds IGLU_TLIST_HDR + max target blocks */
-    int32_t reserved;
+    int32_t reserved;           /* bit 0: 1 disables the observation-first / physics-first warp alternation
+                                   (scheduling only, results identical) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
 } iglu_config;
