@@ -315,23 +315,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         // cell this step edits is patched into obs['grid'] by its own lane afterwards and only envs whose
         // block count changed are evaluated again -- for all others the pre-step grid IS the post-step grid.
         const bool b_first = early && alternate && (wid & 1);
-        if (b_first) {
-            const unsigned pre_eval = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
-            const unsigned obs_mask = grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u;
-            ring_start(obs_mask | pre_eval);
-            ring_drain(grid_obs, pre_eval, false, false);
-            run_physics();
-            if (grid_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
-            const unsigned fix = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != dsize_old);
-            ring_start(fix);
-            ring_drain(false, fix, true, true);
-        } else {
-            if (early) ring_start(__ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0)));
-            run_physics();
+#pragma unroll 1
+        for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once in the binary
+            if (stage == 1) {
+                run_physics();
+                if (b_first && grid_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
+                continue;
+            }
             const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
-            const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
-            if (!early) ring_start(em);
-            ring_drain(grid_obs, em, true, true);
+            unsigned mask, em;
+            bool start, drain = true, obs_on, patch, keep;
+            if (stage == 0) {
+                if (b_first) {  // pre-step grids: observations + (every_step) evaluations whose result is unused
+                    em = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
+                    mask = em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u);
+                    start = true; obs_on = grid_obs; patch = false; keep = false;
+                } else {        // only start the prefetch; consumed after the physics
+                    em = 0u;
+                    mask = __ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0));
+                    start = early; drain = false; obs_on = false; patch = false; keep = false;
+                }
+            } else {
+                if (b_first) {  // re-evaluate the envs whose block count changed
+                    em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && changed);
+                    start = true; obs_on = false; patch = true; keep = true;
+                } else {
+                    em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
+                    start = !early; obs_on = grid_obs; patch = true; keep = true;
+                }
+            }
+            if (start) ring_start(mask);
+            if (drain) ring_drain(obs_on, em, patch, keep);
         }
 
         // ------------------------------------------------------------- phase C

@@ -185,12 +185,10 @@ __device__ __forceinline__ void update_sub(const int8_t *__restrict__ g, Agent &
         a.dy = a.dy > -50.0 ? a.dy : -50.0;
     }
     dy += a.dy * dt;
-    double cx = a.x + dx, cy = a.y + dy, cz = a.z + dz;
-    if (-7.0 <= cx && cx <= 7.0 && -7.0 <= cz && cz <= 7.0 && -3.0 <= cy && cy < 10.0) {
-        collide(g, cx, cy, cz, a.dy);
-        a.x = cx; a.y = cy; a.z = cz;
-    } else if (!flying) {
-        double ux = a.x, uy = a.y + dy, uz = a.z;
+    const double cx = a.x + dx, cy = a.y + dy, cz = a.z + dz;
+    const bool inside = -7.0 <= cx && cx <= 7.0 && -7.0 <= cz && cz <= 7.0 && -3.0 <= cy && cy < 10.0;
+    if (inside || !flying) {  // world.py:258-261: collide(cand) or, when walking, collide((x, y + dy, z))
+        double ux = inside ? cx : a.x, uy = inside ? cy : a.y + dy, uz = inside ? cz : a.z;
         collide(g, ux, uy, uz, a.dy);
         a.x = ux; a.y = uy; a.z = uz;
     }
