@@ -23,9 +23,10 @@
 
 namespace iglu {
 
-constexpr int WARPS_PER_CTA = 8;
+constexpr int WARPS_PER_CTA = 16;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int NB = 4;        // TMA ring depth per warp
+constexpr int CTAS_PER_SM = 2;   // 32 warps / SM: 64 registers per thread, ~6 KB of shared memory per warp
+constexpr int NB = 2;        // TMA ring depth per warp
 constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
 constexpr int TL_PRE = 64;   // target blocks prefetched with the header (longer lists are read from global)
 
@@ -36,7 +37,6 @@ struct __align__(16) Slot {
 
 struct __align__(16) WarpScratch {
     Slot slot[NB];
-    uint32_t init[GSTRIDE / 4];        // starting grid (only for envs that have one)
     EvalScratch es;
     unsigned long long bar[NB];        // mbarriers of the ring
 };
@@ -54,6 +54,7 @@ struct StepParams {
     const int32_t *inventory;  // flying [n]
     const int32_t *placement;  // flying [n]
     const int32_t *buttons;    // walking dict [n][8]
+    int group;                 // envs per warp: 32, or 16 when there are too few envs to fill the SMs
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
@@ -82,13 +83,6 @@ __device__ __forceinline__ int pack16(int a, int b) { return (a & 0xFFFF) | (b <
 __device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xFFFF); }
 __device__ __forceinline__ int hi16(int w) { return (int)(int16_t)((unsigned)w >> 16); }
 
-// Cooperative 16-byte copy of one env's padded grid (69 x int4) global -> shared (generic proxy).
-__device__ __forceinline__ void load_grid_smem(uint32_t *dst, const int8_t *src, int lane) {
-    const int4 *s = reinterpret_cast<const int4 *>(src);
-    int4 *d = reinterpret_cast<int4 *>(dst);
-    for (int q = lane; q < GSTRIDE / 16; q += 32) d[q] = s[q];
-}
-
 // Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element
 // e0 of the obs array (4-byte aligned only); the body is written as 16-byte streaming stores.
 __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, int64_t e0, const uint32_t *sg,
@@ -113,7 +107,7 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
     WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + TABLE_BYTES);
@@ -128,7 +122,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
     __syncthreads();
 
     const int64_t n = p.st.n;
-    const int64_t ngroups = (n + 31) / 32;
+    const int GS = p.group;
+    const int64_t ngroups = (n + GS - 1) / GS;
     const bool flying = KIND == IGLU_FLYING;
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     const bool grid_obs = p.cfg.write_grid_obs && p.obs.grid != nullptr;
@@ -137,10 +132,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
     const int cap = p.cfg.tlist_cap;
     uint32_t seq_issue = 0, seq_cons = 0;  // ring sequence numbers (warp-uniform, live across groups)
 
-    for (int64_t grp = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; grp < ngroups;
+    // groups are dealt warp-major (warp w of every CTA before warp w + 1 of any) so that a partial last
+    // wave spreads evenly over the SMs
+    for (int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x; grp < ngroups;
          grp += (int64_t)gridDim.x * WARPS_PER_CTA) {
-        const int64_t i = grp * 32 + lane;
-        const bool valid = i < n;
+        const int64_t i = grp * GS + lane;
+        const bool valid = lane < GS && i < n;
         const int64_t ii = valid ? i : n - 1;  // clamp: invalid lanes read a real env, write nothing
 
         // ------------------------------------------------------------- phase A
@@ -166,7 +163,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
             while (rm) {
                 const int j = __ffs(rm) - 1;
                 rm &= rm - 1;
-                const int64_t ej = grp * 32 + j;
+                const int64_t ej = grp * GS + j;
                 const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
                 int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
                 const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
@@ -188,7 +185,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
         auto issue = [&](int j) {
             const int nbj = __shfl_sync(0xffffffffu, nblk, j);
             if (lane == 0) {
-                const int64_t ej = grp * 32 + j;
+                const int64_t ej = grp * GS + j;
                 Slot &sl = ws.slot[seq_issue % NB];
                 unsigned long long *bar = &ws.bar[seq_issue % NB];
                 const uint32_t tbytes = (uint32_t)((2 * (TL_HDR + min(nbj, TL_PRE)) + 15) & ~15);
@@ -280,10 +277,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int64_t ej = grp * 32 + j;
+                const int64_t ej = grp * GS + j;
                 const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
                 Slot &sl = ws.slot[seq_cons % NB];
-                if (ev && hs) load_grid_smem(ws.init, p.st.init + ej * GSTRIDE, lane);
                 mbar_wait(&ws.bar[seq_cons % NB], (seq_cons / NB) & 1u);
                 if (patch) {  // the copy may have raced with this step's edit of the same env
                     const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
@@ -293,7 +289,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_step(const StepParams p) {
                 __syncwarp();
                 if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
                 if (ev) {
-                    build_rows(ws.es, sl.grid, ws.init, hs, lane);
+                    build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
                     const int nb = __shfl_sync(0xffffffffu, nblk, j);
                     const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
                     const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
@@ -486,7 +482,7 @@ struct __align__(16) PairScratch {
 };
 
 template <bool CLIP, bool WANT_KEY>
-__global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_t *__restrict__ grids,
+__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
                                                                      const int8_t *__restrict__ fulls,
                                                                      int invariant, int32_t *__restrict__ out,
@@ -534,7 +530,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 2) k_max_intersection(const int8_
             n_rot = 4;
         }
         __syncwarp();
-        build_rows(ps.es, ps.grid, ps.grid, false, lane);
+        build_rows(ps.es, ps.grid, nullptr, false, lane);
         int key = -1;
         const int best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);
         if (lane == 0) {
@@ -649,16 +645,16 @@ extern "C" int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *o
     return check(cudaPeekAtLastError());
 }
 
-static unsigned step_grid(const iglu_ctx *ctx, int64_t n) {
-    const int64_t groups = (n + 31) / 32;
-    const int64_t ctas = (groups + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int64_t resident = (int64_t)ctx->num_sms * 2;  // __launch_bounds__(256, 2): persistent CTAs
-    return (unsigned)(ctas < resident ? ctas : resident);
-}
-
+// Persistent launch: CTAS_PER_SM CTAs on every SM. When 32-env groups would leave warp slots idle (fewer
+// groups than resident warps) the groups are halved so that twice as many warps share the per-env work.
 template <int KIND>
-static int launch_step(iglu_ctx *ctx, const StepParams &p, void *stream) {
-    k_step<KIND><<<step_grid(ctx, p.st.n), CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
+static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
+    const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
+    const int64_t warp_slots = resident_ctas * WARPS_PER_CTA;
+    p.group = ((p.st.n + 31) / 32 < warp_slots) ? 16 : 32;
+    const int64_t groups = (p.st.n + p.group - 1) / p.group;
+    const unsigned grid = (unsigned)(groups < resident_ctas ? groups : resident_ctas);
+    k_step<KIND><<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
     ctx->last_launches = 1;
     return check(cudaPeekAtLastError());
 }
@@ -732,7 +728,7 @@ extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets,
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IGLU_ERR_CUDA;
     const size_t smem = TABLE_BYTES + WARPS_PER_CTA * sizeof(PairScratch);
     const int64_t ctas = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int64_t resident = (int64_t)sms * 2;
+    const int64_t resident = (int64_t)sms * CTAS_PER_SM;
     const unsigned grid = (unsigned)(ctas < resident ? ctas : resident);
     cudaStream_t s = (cudaStream_t)stream;
     const bool clip = fulls && invariant;

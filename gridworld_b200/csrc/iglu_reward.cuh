@@ -25,12 +25,16 @@
 namespace iglu {
 
 constexpr int ROWS_PER_CLASS = 99;               // 9 y-levels x 11 x-rows
-constexpr int NROWS = 16 * ROWS_PER_CLASS;       // 4-bit class codes
-constexpr int ROWS_WORDS = NROWS / 2;            // uint16 rows packed in uint32 words (792)
+constexpr int NCLASS = 13;                       // class 0 = never-set dummy rows, 1..6 colours, 7..12 = values -6..-1
+constexpr int NROWS = NCLASS * ROWS_PER_CLASS;   // 1287 uint16 rows
+constexpr int ROWS_WORDS = (NROWS + 1 + 7) / 8 * 4;  // uint16 rows packed in uint32 words, padded to 16 bytes (648)
 constexpr int LIST_CHUNK = 28;                   // target blocks per pass (<= 31 adds per 5-bit field)
 constexpr int LIST_CAP = 32;                     // chunk padded up to a multiple of 4*G <= 32
 constexpr int SPREAD_N = 2048;
 constexpr uint32_t DUMMY_ENTRY = 2 * 50;         // row 50 of class 0 (never set), shift 0 -> adds nothing
+
+// class index of a 4-bit code (value & 15): 1..6 -> 1..6, 10..15 (values -6..-1) -> 7..12
+__device__ __forceinline__ int class_of(int code) { return code < 8 ? code : code - 3; }
 
 // Per-warp scratch for one evaluation.
 struct __align__(16) EvalScratch {
@@ -49,9 +53,10 @@ __device__ __forceinline__ void build_spread_table(unsigned long long *tbl, int 
     }
 }
 
-// Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows. Both are 16-byte aligned
-// shared-memory copies of GSTRIDE bytes whose pad bytes (cells >= 1089) are zero.
-__device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid, const uint32_t *init,
+// Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows. `grid` is a 16-byte aligned
+// shared-memory copy of GSTRIDE bytes, `init` the env's starting grid in GLOBAL memory (same layout); pad
+// bytes (cells >= 1089) are zero in both.
+__device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                            bool has_init, int lane) {
     int4 *rz = reinterpret_cast<int4 *>(es.rows);
     for (int q = lane; q < ROWS_WORDS / 4; q += 32) rz[q] = make_int4(0, 0, 0, 0);
@@ -62,7 +67,7 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
     for (int q = lane; q < GSTRIDE / 16; q += 32) {
         const int4 gv = g4[q];
         int4 iv = make_int4(0, 0, 0, 0);
-        if (has_init) iv = i4[q];
+        if (has_init) iv = __ldg(i4 + q);
         if ((gv.x | gv.y | gv.z | gv.w | iv.x | iv.y | iv.z | iv.w) == 0) continue;
         const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
         const uint32_t iw[4] = {(uint32_t)iv.x, (uint32_t)iv.y, (uint32_t)iv.z, (uint32_t)iv.w};
@@ -75,7 +80,7 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
                 const int cell = 16 * q + 4 * w + j;
                 if (d != 0 && cell < CELLS) {
                     const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
-                    const int row = (d & 15) * ROWS_PER_CLASS + y * 11 + x;
+                    const int row = class_of(d & 15) * ROWS_PER_CLASS + y * 11 + x;
                     atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
                     atomicOr(&es.planes[d & 15], 1u << y);
                 }
@@ -158,7 +163,7 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
                 const uint32_t e = tlist[c0 + lane];
                 const int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
                 keep = (es.planes[code] >> y) & 1u;
-                const int rb = (code * ROWS_PER_CLASS + y * 11) * 2;
+                const int rb = (class_of(code) * ROWS_PER_CLASS + y * 11) * 2;
                 if (CLIP) {  // rowoff2 | z_k << 12 | x_k << 16
                     e0 = (uint32_t)(rb + 2 * x) | (z << 12) | (x << 16);
                     e1 = (uint32_t)(rb + 2 * z) | ((10 - x) << 12) | (z << 16);
