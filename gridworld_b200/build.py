@@ -36,8 +36,24 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(name, defines, verbose=False):
+    """Tuning aid: builds csrc/libiglu_b200_<name>.so with extra -D defines (select it with the
+    IGLU_B200_SO environment variable)."""
+    so = os.path.join(CSRC, f'libiglu_b200_{name}.so')
+    cmd = [_nvcc()] + NVCC_FLAGS + [f'-D{d}' for d in defines] + ['-o', so] + [os.path.join(CSRC, f) for f in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f'nvcc failed building {so}')
+    return so
+
+
 def build_library(force=False, verbose=False):
     """Compile the CUDA library if it is missing or stale; returns the path of the .so."""
+    override = os.environ.get('IGLU_B200_SO')
+    if override:
+        return override
     if not force and not needs_build():
         return SO
     cmd = [_nvcc()] + NVCC_FLAGS + ['-o', SO] + [os.path.join(CSRC, f) for f in SOURCES]

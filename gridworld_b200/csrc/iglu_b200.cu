@@ -23,10 +23,16 @@
 
 namespace iglu {
 
-constexpr int WARPS_PER_CTA = 16;
+#ifndef IGLU_WARPS_PER_CTA
+#define IGLU_WARPS_PER_CTA 12
+#endif
+#ifndef IGLU_RING
+#define IGLU_RING 3
+#endif
+constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int CTAS_PER_SM = 2;   // 32 warps / SM: 64 registers per thread, ~6 KB of shared memory per warp
-constexpr int NB = 2;        // TMA ring depth per warp
+constexpr int CTAS_PER_SM = 2;   // 24 warps / SM with 12-warp CTAs: <= 85 registers per thread, ~7 KB smem per warp
+constexpr int NB = IGLU_RING;    // TMA ring depth per warp
 constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
 constexpr int TL_PRE = 64;   // target blocks prefetched with the header (longer lists are read from global)
 
@@ -404,7 +410,7 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
         if (d != 0) {
             const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
             const int pos = nout + __popc(m & ((1u << lane) - 1u));
-            if (pos < room) tl[TL_HDR + pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((d & 15) << 12));
+            if (pos < room) tl[TL_HDR + pos] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(d) << 12));
             xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
         }
         nout += __popc(m);
@@ -515,7 +521,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
                 const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
                 if (tv != 0) {
                     const int pos = nout + __popc(m & ((1u << lane) - 1u));
-                    ps.list[pos] = (uint16_t)(y | (x << 4) | (z << 8) | ((tv & 15) << 12));
+                    ps.list[pos] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
                 }
                 if (bv != 0) { xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z); }
             }
@@ -651,7 +657,7 @@ template <int KIND>
 static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
     const int64_t warp_slots = resident_ctas * WARPS_PER_CTA;
-    p.group = ((p.st.n + 31) / 32 < warp_slots) ? 16 : 32;
+    p.group = (2 * ((p.st.n + 31) / 32) <= warp_slots) ? 16 : 32;
     const int64_t groups = (p.st.n + p.group - 1) / p.group;
     const unsigned grid = (unsigned)(groups < resident_ctas ? groups : resident_ctas);
     k_step<KIND><<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);

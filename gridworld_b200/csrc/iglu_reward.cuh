@@ -33,8 +33,11 @@ constexpr int LIST_CAP = 32;                     // chunk padded up to a multipl
 constexpr int SPREAD_N = 2048;
 constexpr uint32_t DUMMY_ENTRY = 2 * 50;         // row 50 of class 0 (never set), shift 0 -> adds nothing
 
-// class index of a 4-bit code (value & 15): 1..6 -> 1..6, 10..15 (values -6..-1) -> 7..12
-__device__ __forceinline__ int class_of(int code) { return code < 8 ? code : code - 3; }
+// Grid / target values are differences of colour ids, i.e. -6..6 (env.py:230, 290). code_of() maps a value
+// to a 4-bit code (value & 15; 8 = "not a valid value", never matches), class_of() a code to its row class:
+// 1..6 -> 1..6, 10..15 (values -6..-1) -> 7..12, anything else -> 0 (the never-set dummy class).
+__device__ __forceinline__ int code_of(int v) { return (v >= -6 && v <= 6) ? (v & 15) : 8; }
+__device__ __forceinline__ int class_of(int code) { return code < 7 ? code : (code >= 10 ? code - 3 : 0); }
 
 // Per-warp scratch for one evaluation.
 struct __align__(16) EvalScratch {
@@ -78,7 +81,7 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
             for (int j = 0; j < 4; j++) {
                 const int d = (int)(int8_t)(gw[w] >> (8 * j)) - (int)(int8_t)(iw[w] >> (8 * j));
                 const int cell = 16 * q + 4 * w + j;
-                if (d != 0 && cell < CELLS) {
+                if (d != 0 && d >= -6 && d <= 6 && cell < CELLS) {
                     const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
                     const int row = class_of(d & 15) * ROWS_PER_CLASS + y * 11 + x;
                     atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
