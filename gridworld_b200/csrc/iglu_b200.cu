@@ -24,14 +24,14 @@
 namespace iglu {
 
 #ifndef IGLU_WARPS_PER_CTA
-#define IGLU_WARPS_PER_CTA 12
+#define IGLU_WARPS_PER_CTA 8
 #endif
 #ifndef IGLU_RING
-#define IGLU_RING 3
+#define IGLU_RING 4
 #endif
 constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
-constexpr int CTAS_PER_SM = 2;   // 24 warps / SM with 12-warp CTAs: <= 85 registers per thread, ~7 KB smem per warp
+constexpr int CTAS_PER_SM = 2;   // 16 warps / SM: measured faster than 20 / 24 / 32 warps with fewer registers (profiles/)
 constexpr int NB = IGLU_RING;    // TMA ring depth per warp
 constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
 constexpr int TL_PRE = 64;   // target blocks prefetched with the header (longer lists are read from global)
@@ -97,16 +97,27 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
     int32_t *og = obs_grid + e0;
     const int h = (int)((4 - (e0 & 3)) & 3);  // elements before the first 16-byte boundary
     if (lane < h) og[lane] = (int32_t)sg8[lane];
-    const int nbody = (CELLS - h) >> 2;
+    const int nbody = (CELLS - h) >> 2;  // 271 or 272 sixteen-byte chunks
     int4 *o4 = reinterpret_cast<int4 *>(og + h);
-    for (int m = lane; m < nbody; m += 32) {
-        const uint32_t w = __funnelshift_r(sg[m], sg[m + 1], 8 * h);  // bytes h + 4m .. h + 4m + 3
+    // fully unrolled, all shared-memory loads first: one LDS latency per env instead of one per chunk
+    uint32_t lo[9], hi[9];
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        const int m = lane + 32 * it;
+        const bool on = it < 8 || m < nbody;
+        lo[it] = on ? sg[m] : 0u;
+        hi[it] = on ? sg[m + 1] : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        const int m = lane + 32 * it;
+        const uint32_t w = __funnelshift_r(lo[it], hi[it], 8 * h);  // bytes h + 4m .. h + 4m + 3
         int4 v;
         v.x = (int)(int8_t)(w);  // sign-extend each byte
         v.y = (int)(int8_t)(w >> 8);
         v.z = (int)(int8_t)(w >> 16);
         v.w = (int)(int8_t)(w >> 24);
-        __stcs(o4 + m, v);
+        if (it < 8 || m < nbody) __stcs(o4 + m, v);
     }
     const int t0 = h + 4 * nbody;
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];

@@ -62,7 +62,11 @@ __device__ __forceinline__ void build_spread_table(unsigned long long *tbl, int 
 __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                            bool has_init, int lane) {
     int4 *rz = reinterpret_cast<int4 *>(es.rows);
-    for (int q = lane; q < ROWS_WORDS / 4; q += 32) rz[q] = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int it = 0; it < (ROWS_WORDS / 4 + 31) / 32; it++) {
+        const int q = lane + 32 * it;
+        if (q < ROWS_WORDS / 4) rz[q] = make_int4(0, 0, 0, 0);
+    }
     if (lane < 16) es.planes[lane] = 0u;
     __syncwarp();
     const int4 *g4 = reinterpret_cast<const int4 *>(grid);
@@ -183,9 +187,11 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
             const int ck = __popc(km);
             if (ck == 0) continue;  // warp-uniform
             const int cnp = (ck + 4 * G - 1) & ~(4 * G - 1);  // padded with entries that add nothing
-            es.list[0][lane] = DUMMY_ENTRY; es.list[1][lane] = DUMMY_ENTRY;
-            es.list[2][lane] = DUMMY_ENTRY; es.list[3][lane] = DUMMY_ENTRY;
-            __syncwarp();
+            // kept blocks are compacted to slots [0, ck); slots [ck, cnp) get entries that add nothing
+            if (lane >= ck && lane < cnp) {
+                es.list[0][lane] = DUMMY_ENTRY; es.list[1][lane] = DUMMY_ENTRY;
+                es.list[2][lane] = DUMMY_ENTRY; es.list[3][lane] = DUMMY_ENTRY;
+            }
             if (keep) {
                 const int pos = __popc(km & ((1u << lane) - 1u));
                 es.list[0][pos] = e0; es.list[1][pos] = e1; es.list[2][pos] = e2; es.list[3][pos] = e3;
