@@ -494,9 +494,90 @@ __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, cons
 // Task(target, full_grid, invariant).maximal_intersection(grid) per pair (BASELINE config 4).
 struct __align__(16) PairScratch {
     uint32_t grid[GSTRIDE / 4];
+    uint32_t tgt[GSTRIDE / 4];
     uint16_t list[IGLU_TLIST_MAX];
     EvalScratch es;
 };
+
+// Copies the 1089 cells at `src` (any alignment) into a 16-byte aligned shared-memory buffer of GSTRIDE
+// bytes (pad zeroed) with coalesced 4-byte global loads + funnel shifts. `last_word` is the aligned word
+// holding the last byte of the whole source array; nothing beyond it is read.
+__device__ __forceinline__ void load_cells_smem(uint32_t *dst, const int8_t *src, const uint32_t *last_word, int lane) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
+    const int sh = (int)(a & 3) * 8;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    uint32_t lo[9], hi[9];
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        const int i = lane + 32 * it;
+        lo[it] = (i <= 272 && w + i <= last_word) ? __ldg(w + i) : 0u;
+        hi[it] = (i <= 272 && w + i + 1 <= last_word) ? __ldg(w + i + 1) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < 9; it++) {
+        const int i = lane + 32 * it;
+        uint32_t v = __funnelshift_r(lo[it], hi[it], sh);
+        if (i == 272) v &= 0xFFu;       // cells 1088 | pad
+        if (i > 272) v = 0u;
+        if (i < GSTRIDE / 4) dst[i] = v;
+    }
+}
+
+// Bounding box (x_min, x_max, z_min, z_max) of the non-zero cells of a staged grid; empty = (10, 0, 10, 0).
+__device__ __forceinline__ void bbox_smem(const uint32_t *g, int lane, int &xmin, int &xmax, int &zmin, int &zmax) {
+    xmin = 10; xmax = 0; zmin = 10; zmax = 0;
+    for (int i = lane; i < (CELLS + 3) / 4; i += 32) {
+        const uint32_t v = g[i];
+        if (v == 0u) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if ((v >> (8 * j)) & 0xFFu) {
+                const int c = 4 * i + j, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+                xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
+            }
+        }
+    }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
+}
+
+// Ordered (ascending cell index) list of the non-zero cells of a staged target grid. Lane L owns the 36
+// cells [36 L, 36 L + 36): count, exclusive scan over lanes, emit. Returns the number of blocks.
+__device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list, int lane) {
+    uint32_t wv[9];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const int i = 9 * lane + q;
+        wv[q] = i < GSTRIDE / 4 ? t[i] : 0u;
+        const uint32_t v = wv[q];
+        const uint32_t nz = (v | ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;  // 0x80 per non-zero byte
+        cnt += __popc(nz);
+    }
+    int pos = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pos, d);
+        if (lane >= d) pos += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, pos, 31);
+    pos -= cnt;
+    if (cnt) {
+#pragma unroll
+        for (int q = 0; q < 9; q++) {
+            if (wv[q] == 0u) continue;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int tv = (int)(int8_t)(wv[q] >> (8 * j));
+                if (tv != 0) {
+                    const int c = 36 * lane + 4 * q + j, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+                    list[pos++] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
+                }
+            }
+        }
+    }
+    return total;
+}
 
 template <bool CLIP, bool WANT_KEY>
 __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(const int8_t *__restrict__ grids,
@@ -511,38 +592,28 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
     PairScratch &ps = scratch[wid];
     build_spread_table(tbl, threadIdx.x, CTA_THREADS);
     __syncthreads();
-    int8_t *sg = reinterpret_cast<int8_t *>(ps.grid);
+    const int64_t total_bytes = count * CELLS;
+    auto last_word_of = [&](const int8_t *base) {
+        return reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(base) + total_bytes - 1) & ~(uintptr_t)3);
+    };
+    const uint32_t *glast = last_word_of(grids), *tlast = last_word_of(targets);
+    const uint32_t *flast = fulls ? last_word_of(fulls) : nullptr;
     for (int64_t pr = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; pr < count;
          pr += (int64_t)gridDim.x * WARPS_PER_CTA) {
-        const int8_t *g = grids + pr * CELLS, *t = targets + pr * CELLS;
-        const int8_t *f = fulls ? fulls + pr * CELLS : nullptr;
-        int nout = 0, xmin = 10, xmax = 0, zmin = 10, zmax = 0;
-        for (int c0 = 0; c0 < GSTRIDE; c0 += 32) {
-            const int c = c0 + lane;
-            int tv = 0, bv = 0;
-            if (c < CELLS) {
-                tv = t[c];
-                bv = f ? (int)f[c] : tv;
-                sg[c] = g[c];
-            } else if (c < GSTRIDE) {
-                sg[c] = 0;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, tv != 0);
-            if (c < CELLS) {
-                const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-                if (tv != 0) {
-                    const int pos = nout + __popc(m & ((1u << lane) - 1u));
-                    ps.list[pos] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
-                }
-                if (bv != 0) { xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z); }
-            }
-            nout += __popc(m);
-        }
-        xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-        zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
+        load_cells_smem(ps.grid, grids + pr * CELLS, glast, lane);
+        load_cells_smem(ps.tgt, targets + pr * CELLS, tlast, lane);
+        __syncwarp();
+        const int nout = compact_target(ps.tgt, ps.list, lane);
         int4 rc = make_int4(0, 0, 0, 0);  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
         if (invariant) {
+            int xmin, xmax, zmin, zmax;
+            if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid
+                __syncwarp();
+                load_cells_smem(ps.tgt, fulls + pr * CELLS, flast, lane);
+                __syncwarp();
+            }
+            bbox_smem(ps.tgt, lane, xmin, xmax, zmin, zmax);
             rc = rects_from_bbox(xmin, xmax, zmin, zmax);
             n_rot = 4;
         }
