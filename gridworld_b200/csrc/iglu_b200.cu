@@ -526,34 +526,24 @@ __device__ __forceinline__ void load_cells_smem(uint32_t *dst, const int8_t *src
 // Bounding box (x_min, x_max, z_min, z_max) of the non-zero cells of a staged grid; empty = (10, 0, 10, 0).
 __device__ __forceinline__ void bbox_smem(const uint32_t *g, int lane, int &xmin, int &xmax, int &zmin, int &zmax) {
     xmin = 10; xmax = 0; zmin = 10; zmax = 0;
-    for (int i = lane; i < (CELLS + 3) / 4; i += 32) {
-        const uint32_t v = g[i];
-        if (v == 0u) continue;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if ((v >> (8 * j)) & 0xFFu) {
-                const int c = 4 * i + j, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-                xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
-            }
-        }
+    unsigned long long m = cell_mask36(g, nullptr, lane);
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int c = 36 * lane + b, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+        xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
     }
     xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
     zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
 }
 
-// Ordered (ascending cell index) list of the non-zero cells of a staged target grid. Lane L owns the 36
-// cells [36 L, 36 L + 36): count, exclusive scan over lanes, emit. Returns the number of blocks.
-__device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list, int lane) {
-    uint32_t wv[9];
-    int cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 9; q++) {
-        const int i = 9 * lane + q;
-        wv[q] = i < GSTRIDE / 4 ? t[i] : 0u;
-        const uint32_t v = wv[q];
-        const uint32_t nz = (v | ((v & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;  // 0x80 per non-zero byte
-        cnt += __popc(nz);
-    }
+// Ordered (ascending cell index) list of the non-zero cells of a staged target grid + their bounding box.
+// Lane L owns the 36 cells [36 L, 36 L + 36): count, exclusive scan over lanes, emit. Returns the count.
+__device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list, int lane, int &xmin, int &xmax,
+                                              int &zmin, int &zmax) {
+    xmin = 10; xmax = 0; zmin = 10; zmax = 0;
+    unsigned long long m = cell_mask36(t, nullptr, lane);
+    const int cnt = __popcll(m);
     int pos = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -562,20 +552,16 @@ __device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list,
     }
     const int total = __shfl_sync(0xffffffffu, pos, 31);
     pos -= cnt;
-    if (cnt) {
-#pragma unroll
-        for (int q = 0; q < 9; q++) {
-            if (wv[q] == 0u) continue;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int tv = (int)(int8_t)(wv[q] >> (8 * j));
-                if (tv != 0) {
-                    const int c = 36 * lane + 4 * q + j, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-                    list[pos++] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
-                }
-            }
-        }
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        const int tv = cell_value36(t, lane, b);
+        const int c = 36 * lane + b, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+        list[pos++] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
+        xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
     }
+    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
+    zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
     return total;
 }
 
@@ -603,17 +589,17 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
         load_cells_smem(ps.grid, grids + pr * CELLS, glast, lane);
         load_cells_smem(ps.tgt, targets + pr * CELLS, tlast, lane);
         __syncwarp();
-        const int nout = compact_target(ps.tgt, ps.list, lane);
+        int xmin, xmax, zmin, zmax;
+        const int nout = compact_target(ps.tgt, ps.list, lane, xmin, xmax, zmin, zmax);
         int4 rc = make_int4(0, 0, 0, 0);  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
         if (invariant) {
-            int xmin, xmax, zmin, zmax;
             if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid
                 __syncwarp();
                 load_cells_smem(ps.tgt, fulls + pr * CELLS, flast, lane);
                 __syncwarp();
+                bbox_smem(ps.tgt, lane, xmin, xmax, zmin, zmax);
             }
-            bbox_smem(ps.tgt, lane, xmin, xmax, zmin, zmax);
             rc = rects_from_bbox(xmin, xmax, zmin, zmax);
             n_rot = 4;
         }

@@ -56,9 +56,35 @@ __device__ __forceinline__ void build_spread_table(unsigned long long *tbl, int 
     }
 }
 
-// Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows. `grid` is a 16-byte aligned
-// shared-memory copy of GSTRIDE bytes, `init` the env's starting grid in GLOBAL memory (same layout); pad
-// bytes (cells >= 1089) are zero in both.
+// Lane L owns the 36 cells [36 L, 36 L + 36) of a staged grid (nine 32-bit words; lane stride 9 words is
+// conflict-free). Returns a 36-bit mask with bit b set when cell 36 L + b differs from `sub` (or from 0
+// when sub == nullptr). `g` is shared memory, `sub` may be shared or global. Grids are sparse, so all
+// per-cell work is done by looping over the set bits instead of visiting every byte.
+__device__ __forceinline__ unsigned long long cell_mask36(const uint32_t *g, const uint32_t *sub, int lane) {
+    unsigned long long m = 0ull;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const int i = 9 * lane + q;
+        uint32_t x = 0u;
+        if (i < GSTRIDE / 4) {
+            x = g[i];
+            if (sub) x ^= sub[i];
+        }
+        const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;  // 1 per non-zero byte
+        const uint32_t nib = (nz * 0x01020408u) >> 24;                                    // gather into 4 bits
+        m |= (unsigned long long)(nib & 0xFu) << (4 * q);
+    }
+    return m;
+}
+
+// value of cell `b` (0..35) of lane `lane`'s segment
+__device__ __forceinline__ int cell_value36(const uint32_t *g, int lane, int b) {
+    return (int)(int8_t)(g[9 * lane + (b >> 2)] >> (8 * (b & 3)));
+}
+
+// Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows / es.planes. `grid` is a
+// 16-byte aligned shared-memory copy of GSTRIDE bytes, `init` the env's starting grid in GLOBAL memory
+// (same layout); pad bytes (cells >= 1089) are zero in both.
 __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                            bool has_init, int lane) {
     int4 *rz = reinterpret_cast<int4 *>(es.rows);
@@ -68,30 +94,20 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
         if (q < ROWS_WORDS / 4) rz[q] = make_int4(0, 0, 0, 0);
     }
     if (lane < 16) es.planes[lane] = 0u;
+    const uint32_t *iw = has_init ? reinterpret_cast<const uint32_t *>(init) : nullptr;
+    unsigned long long m = cell_mask36(grid, iw, lane);
     __syncwarp();
-    const int4 *g4 = reinterpret_cast<const int4 *>(grid);
-    const int4 *i4 = reinterpret_cast<const int4 *>(init);
-    for (int q = lane; q < GSTRIDE / 16; q += 32) {
-        const int4 gv = g4[q];
-        int4 iv = make_int4(0, 0, 0, 0);
-        if (has_init) iv = __ldg(i4 + q);
-        if ((gv.x | gv.y | gv.z | gv.w | iv.x | iv.y | iv.z | iv.w) == 0) continue;
-        const uint32_t gw[4] = {(uint32_t)gv.x, (uint32_t)gv.y, (uint32_t)gv.z, (uint32_t)gv.w};
-        const uint32_t iw[4] = {(uint32_t)iv.x, (uint32_t)iv.y, (uint32_t)iv.z, (uint32_t)iv.w};
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-            if ((gw[w] | iw[w]) == 0u) continue;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int d = (int)(int8_t)(gw[w] >> (8 * j)) - (int)(int8_t)(iw[w] >> (8 * j));
-                const int cell = 16 * q + 4 * w + j;
-                if (d != 0 && d >= -6 && d <= 6 && cell < CELLS) {
-                    const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
-                    const int row = class_of(d & 15) * ROWS_PER_CLASS + y * 11 + x;
-                    atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
-                    atomicOr(&es.planes[d & 15], 1u << y);
-                }
-            }
+    while (m) {
+        const int b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+        int d = cell_value36(grid, lane, b);
+        if (has_init) d -= cell_value36(iw, lane, b);
+        const int cell = 36 * lane + b;
+        if (d >= -6 && d <= 6) {  // other values are not colour differences and match nothing
+            const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
+            const int row = class_of(d & 15) * ROWS_PER_CLASS + y * 11 + x;
+            atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
+            atomicOr(&es.planes[d & 15], 1u << y);
         }
     }
     __syncwarp();
