@@ -191,18 +191,14 @@ def run_reference_arm(args):
 
 def run_b200_arm(args):
     import torch
-    import torch.distributed as dist
+    from gridworld_b200 import dist as D
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    rank, world, local = D.rank_info()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device; the product path has no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+    D.init('nccl', dev)
 
     import gridworld_b200 as gw
     n = args.envs
@@ -216,10 +212,7 @@ def run_b200_arm(args):
     K, W = args.steps, args.warmup
 
     def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+        D.barrier(dev)
 
     for t in range(W):
         env.step(actions[t % P])
@@ -237,10 +230,7 @@ def run_b200_arm(args):
     total_ms = ev[0].elapsed_time(ev[K])
     step_ms = np.array([ev[t].elapsed_time(ev[t + 1]) for t in range(K)])
     launches = env.gpu_launches - launches0
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+    total_ms_max = D.max_over_ranks(total_ms, dev)
     value = n * world * K / (total_ms_max * 1e-3)
 
     # ---- e2e through the host-buffer C-ABI call (pinned host actions in, reward/done out) ----
@@ -256,10 +246,25 @@ def run_b200_arm(args):
         env.step_host(acts_host[t % P], r_host, d_host)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n * world * Ke / float(te.item())
+    e2e_value = n * world * Ke / D.max_over_ranks(e2e_s, dev)
+
+    # ---- second half of BASELINE.json's metric: max-intersection evals/sec (stateless sweep, config 4) ----
+    mi_evals = None
+    if not args.no_mi:
+        npairs = 1_000_000
+        Tp = synth_targets(npairs, DENSITY, 'compact', 1237).to(dev)
+        Gp = synth_targets(npairs, DENSITY, 'compact', 1238).to(dev)
+        Gp[:npairs // 2] = torch.rot90(Tp[:npairs // 2], k=1, dims=(2, 3))  # half are rotated copies
+        gw.max_intersection(Gp, Tp)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        for _ in range(5):
+            gw.max_intersection(Gp, Tp)
+        m1.record()
+        barrier()
+        mi_evals = world * npairs * 5 / (D.max_over_ranks(m0.elapsed_time(m1), dev) * 1e-3)
+        del Tp, Gp
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -282,6 +287,9 @@ def run_b200_arm(args):
                     'd2h_bytes_per_step': 9 * n, 'steps': Ke,
                     'api': 'IGLUVecEnv.step_host -> iglu_step_walking_host (pinned host buffers)'},
             'gpu_launches': int(launches),
+            'max_intersection': {'evals_per_sec': mi_evals, 'pairs_per_gpu': 1_000_000,
+                                 'inputs': 'config 4: compact targets rho=0.20; half of the grids independent, half '
+                                           'a rotated copy of the target; int8 [n,9,11,11] resident in HBM'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': recorded_traffic(),
                          'kernel': 'iglu::k_step<0>', 'kernel_ms': kernel_ms,
@@ -296,9 +304,7 @@ def run_b200_arm(args):
                                     'sample': f'8192 envs x {steps_cpu} steps of the workload, {dt:.1f} s wall, '
                                               'oracle/iglu_oracle.c (C port of the reference step), reward on change'}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.shutdown()
 
 
 def main():
@@ -312,6 +318,7 @@ def main():
     ap.add_argument('--reward-mode', default='every_step', choices=['every_step', 'on_change'])
     ap.add_argument('--inplace', action='store_true', help='do not materialise the int32 grid obs')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-mi', action='store_true', help='skip the max-intersection evals/sec leg')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

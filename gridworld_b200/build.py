@@ -36,6 +36,23 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+MB_SO = os.path.join(CSRC, 'libiglu_microbench.so')
+
+
+def build_microbench(force=False):
+    """Integer-pipe peak microbenchmark (measurement aid used by scripts/reward_roofline.py)."""
+    src = os.path.join(CSRC, 'iglu_microbench.cu')
+    if not force and os.path.exists(MB_SO) and os.path.getmtime(MB_SO) >= os.path.getmtime(src):
+        return MB_SO
+    cmd = [_nvcc(), '-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--shared',
+           '-Xcompiler', '-fPIC', '-o', MB_SO, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        print(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed building libiglu_microbench.so')
+    return MB_SO
+
+
 def build_variant(name, defines, verbose=False):
     """Tuning aid: builds csrc/libiglu_b200_<name>.so with extra -D defines (select it with the
     IGLU_B200_SO environment variable)."""

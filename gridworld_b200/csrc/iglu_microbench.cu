@@ -1,0 +1,71 @@
+// iglu_microbench.cu -- integer-pipe peak microbenchmark (measurement aid, not part of the step path).
+//
+// SURVEY 8(d) asks that the reward kernel's roofline denominator (POPC / LOP3 / IADD throughput) be
+// MEASURED on the box rather than taken from a table. Each kernel runs 8 independent dependency chains
+// per thread so that the pipe, not the latency, is the limit; results are warp-instructions per clock
+// per SM and G thread-ops/s for the whole chip.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int ITERS = 4096;
+constexpr int CHAINS = 8;
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, uint32_t seed) {
+    uint32_t a[CHAINS];
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) a[c] = seed + threadIdx.x * 2654435761u + c * 40503u;
+    const uint32_t k1 = seed | 1u, k2 = ~seed;
+    for (int i = 0; i < ITERS; i++) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; c++) {
+            if (OP == 0) a[c] = __popc(a[c]) + k1;               // POPC (+ IADD to keep the chain alive)
+            else if (OP == 1) a[c] = (a[c] & k1) ^ k2;           // one LOP3
+            else if (OP == 2) a[c] = a[c] + k1 + k2;             // one IADD3
+            else a[c] = a[c] * k1 + k2;                          // one IMAD
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) r ^= a[c];
+    if (r == 0x12345u) out[0] = r;  // never true in practice; keeps the result live
+}
+
+template <int OP>
+double run(int sms, cudaStream_t s, uint32_t *scratch) {
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    k_int_peak<OP><<<blocks, threads, 0, s>>>(scratch, 12345u);
+    cudaEventRecord(e0, s);
+    k_int_peak<OP><<<blocks, threads, 0, s>>>(scratch, 54321u);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double thread_ops = (double)blocks * threads * ITERS * CHAINS;
+    return thread_ops / (ms * 1e-3);  // thread-level ops per second (chain op; POPC chain = POPC + IADD)
+}
+
+}  // namespace
+
+// out[0..3] = thread-ops/s of the POPC(+IADD), LOP3, IADD3 and IMAD chains; returns 0 on success.
+extern "C" int iglu_mb_int_peak(double *out, void *stream) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -2;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -2;
+    uint32_t *scratch = nullptr;
+    if (cudaMalloc(&scratch, 64) != cudaSuccess) return -2;
+    cudaStream_t s = (cudaStream_t)stream;
+    out[0] = run<0>(sms, s, scratch);
+    out[1] = run<1>(sms, s, scratch);
+    out[2] = run<2>(sms, s, scratch);
+    out[3] = run<3>(sms, s, scratch);
+    cudaFree(scratch);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}

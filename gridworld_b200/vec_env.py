@@ -75,7 +75,7 @@ class IGLUVecEnv:
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
-                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=True):
+                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None):
         if render:
             raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
         if reward_mode not in ('on_change', 'every_step'):
@@ -97,6 +97,8 @@ class IGLUVecEnv:
         self.auto_reset = bool(auto_reset)
         self.reward_mode = reward_mode
         self.grid_obs = bool(grid_obs) and self.vector_state
+        if alternate_phases is None:  # measured: helps when few envs are evaluated per step (profiles/)
+            alternate_phases = reward_mode != 'every_step'
         if action_space == 'flying':
             kind = _lib.FLYING
         else:

@@ -21,9 +21,9 @@ if [[ $what == *sweep* ]]; then
 fi
 if [[ $what == *ncu* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
-      --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/ncu_launches.log 2>&1
+      --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 5 --no-cpu --no-mi > gpurun_out/ncu_launches.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_step -s 10 -c 2 \
-      -f -o gpurun_out/prof_step python bench.py --steps 10 --warmup 5 --no-cpu > gpurun_out/ncu_full.log 2>&1
+      -f -o gpurun_out/prof_step python bench.py --steps 10 --warmup 5 --no-cpu --no-mi > gpurun_out/ncu_full.log 2>&1
   tail -3 gpurun_out/ncu_full.log
   ls -la gpurun_out
 fi

@@ -49,6 +49,42 @@ def flying(n, K=200):
     return {'kind': 'flying+target_in_obs', 'envs': n, 'ms_per_step': ms, 'env_steps_per_sec': n / ms * 1e3}
 
 
+def p_eval_mean(T, limit=2000):
+    """SURVEY 8(d) algorithmic work per evaluation: P_eval = sum_k S_k * NR_k popcount-ANDs, with S_k the
+    admissible shifts of rotation k and NR_k the non-empty (class, y, x) rows of the rotated target."""
+    T = T[:limit].cpu().numpy()
+    tot = 0.0
+    for t in T:
+        nz = np.argwhere(t != 0)
+        if len(nz) == 0:
+            continue
+        xmin, xmax, zmin, zmax = nz[:, 1].min(), nz[:, 1].max(), nz[:, 2].min(), nz[:, 2].max()
+        s_even = (xmin - (xmax - 10) + 1) * (zmin - (zmax - 10) + 1)  # same count for all four rotations
+        cls = t[nz[:, 0], nz[:, 1], nz[:, 2]]
+        nr_x = len({(c, y, x) for c, (y, x, z) in zip(cls, nz)})   # rotations 0 and 2: rows along x
+        nr_z = len({(c, y, z) for c, (y, x, z) in zip(cls, nz)})   # rotations 1 and 3: rows along z
+        tot += s_even * (2 * nr_x + 2 * nr_z)
+    return tot / len(T)
+
+
+_INT_PEAK = None
+
+
+def int_peak():
+    """thread-ops/s of the POPC(+IADD), LOP3, IADD3, IMAD chains measured by csrc/iglu_microbench.cu."""
+    global _INT_PEAK
+    if _INT_PEAK is None:
+        import ctypes as C
+        from gridworld_b200 import build as B
+        lib = C.CDLL(B.build_microbench())
+        out = (C.c_double * 4)()
+        lib.iglu_mb_int_peak.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+        torch.cuda.synchronize()
+        assert lib.iglu_mb_int_peak(out, None) == 0
+        _INT_PEAK = dict(zip(('popc', 'lop3', 'iadd3', 'imad'), list(out)))
+    return _INT_PEAK
+
+
 def reward_only(n, support, rho, reps=5):
     T = synth_targets(n, rho, support, 1237).cuda()
     Gd = synth_targets(n, rho, support, 1238).cuda()
@@ -63,8 +99,13 @@ def reward_only(n, support, rho, reps=5):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    pe = p_eval_mean(T)
+    pk = int_peak()
+    evals = n / ms * 1e3
     return {'kind': 'max_intersection', 'pairs': n, 'support': support, 'rho': rho, 'ms': ms,
-            'evals_per_sec': n / ms * 1e3}
+            'evals_per_sec': evals, 'p_eval_mean': pe, 'popcount_ands_per_sec': evals * pe,
+            'popc_peak_thread_ops_per_sec': pk['popc'], 'frac_of_popc_peak': evals * pe / pk['popc'],
+            'hbm_bytes_per_eval': 2 * 1089 + 4, 'hbm_gbs': evals * (2 * 1089 + 4) / 1e9, 'int_peaks': pk}
 
 
 if __name__ == '__main__':
