@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
     const int64_t ngroups = (n + GS - 1) / GS;
     const bool flying = KIND == IGLU_FLYING;
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
-    const bool grid_obs = p.cfg.write_grid_obs && p.obs.grid != nullptr;
+    const bool grid_obs = p.cfg.write_grid_obs == 1 && p.obs.grid != nullptr;  // rewrite obs['grid'] every step
+    const bool inc_obs = p.cfg.write_grid_obs == 2 && p.obs.grid != nullptr;   // keep it up to date cell by cell
     const bool early = grid_obs || every_step;  // the set of envs phase B touches is known before phase A
     const bool alternate = (p.cfg.reserved & 1) == 0;  // reserved bit 0 = 1 disables the phase alternation
     const int cap = p.cfg.tlist_cap;
@@ -185,6 +186,10 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
                 int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
                 const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
                 for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
+                if (inc_obs) {  // incremental observation: a reset rewrites the whole row
+                    const int8_t *si = p.st.init + ej * GSTRIDE;
+                    for (int c = lane; c < CELLS; c += 32) p.obs.grid[ej * CELLS + c] = hs ? (int32_t)si[c] : 0;
+                }
             }
             // the TMA reads below go through the async proxy: order them after these generic-proxy writes
             __threadfence();
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
         for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once in the binary
             if (stage == 1) {
                 run_physics();
-                if (b_first && grid_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
+                if (((b_first && grid_obs) || inc_obs) && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
                 continue;
             }
             const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
         __syncwarp();
         int xmin, xmax, zmin, zmax;
         const int nout = compact_target(ps.tgt, ps.list, lane, xmin, xmax, zmin, zmax);
-        int4 rc = make_int4(0, 0, 0, 0);  // task.py:59-60 admissible = [[(0, 0)]]
+        int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
         if (invariant) {
             if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid

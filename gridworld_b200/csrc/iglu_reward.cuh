@@ -113,20 +113,28 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
     __syncwarp();
 }
 
-// Rectangles of the four rotations from the rotation-0 bounding box of the non-zero cells
-// (x_min..x_max, z_min..z_max; empty = (10, 0, 10, 0) which yields all 441 shifts, task.py:67-72).
-// Packed as 16 int8 in an int4: per rotation dx_lo, dx_hi, dz_lo, dz_hi.
+// Admissible-shift rectangles of the four rotations from the rotation-0 bounding box of the non-zero
+// cells (x_min..x_max, z_min..z_max; empty = (10, 0, 10, 0) which yields all 441 shifts, task.py:67-72).
+// Packed as one 32-bit word per rotation: byte 0 = dx_lo (int8), byte 1 = number of dx values (bits 0-4),
+// byte 2 = dz_lo (int8), byte 3 = number of dz values; bits 13-14 of word 0 hold the lane-mapping shift
+// s = ceil(log2(min(8, max dx count))) so that the evaluation does not have to derive it per env.
 __device__ __forceinline__ int4 rects_from_bbox(int xmin, int xmax, int zmin, int zmax) {
-    int r[4];
+    int r[4], nxmax = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        r[k] = ((xmax - 10) & 0xFF) | ((xmin & 0xFF) << 8) | (((zmax - 10) & 0xFF) << 16) | ((zmin & 0xFF) << 24);
+        const int nx = xmin - (xmax - 10) + 1, nz = zmin - (zmax - 10) + 1;
+        r[k] = ((xmax - 10) & 0xFF) | ((nx & 0x1F) << 8) | (((zmax - 10) & 0xFF) << 16) | ((nz & 0xFF) << 24);
+        nxmax = max(nxmax, nx);
         // rotate the box: x' = z, z' = 10 - x  (task.py:52-53)
-        const int nxmin = zmin, nxmax = zmax, nzmin = 10 - xmax, nzmax = 10 - xmin;
-        xmin = nxmin; xmax = nxmax; zmin = nzmin; zmax = nzmax;
+        const int nxmin = zmin, nxmax2 = zmax, nzmin = 10 - xmax, nzmax = 10 - xmin;
+        xmin = nxmin; xmax = nxmax2; zmin = nzmin; zmax = nzmax;
     }
+    const int s = nxmax <= 1 ? 0 : (nxmax <= 2 ? 1 : (nxmax <= 4 ? 2 : 3));
+    r[0] |= s << 13;
     return make_int4(r[0], r[1], r[2], r[3]);
 }
+// rectangle (0, 0) x (0, 0) of rotation 0 only (invariant=False, task.py:59-60)
+__device__ __forceinline__ int4 rects_identity() { return make_int4(0x01000100, 0, 0, 0); }
 
 __device__ __forceinline__ int rect_byte(int w, int i) { return (int)(int8_t)((unsigned)w >> (8 * i)); }
 
@@ -146,18 +154,18 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
     if (WANT_KEY) *key_out = -1;
     if (nblk == 0) return 0;
     const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
-    // ---- work items: lane -> (rotation k, dx index, block-slice g); s = ceil(log2(max dx count)) ----
-    int nxmax = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) nxmax = max(nxmax, rect_byte(rw[k], 1) - rect_byte(rw[k], 0) + 1);
-    const int s = nxmax <= 1 ? 0 : (nxmax <= 2 ? 1 : (nxmax <= 4 ? 2 : 3));
+    // ---- work items: lane -> (rotation k, dx index, block-slice g) ----
+    const int s = (rc.x >> 13) & 3;
     const int G = 8 >> s;                      // lane groups sharing the blocks of one work item
     const int dxi0 = lane & ((1 << s) - 1);
     const int k = (lane >> s) & 3;
     const int g = lane >> (s + 2);
     const int rk = k == 0 ? rw[0] : (k == 1 ? rw[1] : (k == 2 ? rw[2] : rw[3]));
-    const int dx_lo = rect_byte(rk, 0), nxk = rect_byte(rk, 1) - dx_lo + 1;
-    const int dz_lo = rect_byte(rk, 2), wz = rect_byte(rk, 3) - dz_lo + 1;
+    const int dx_lo = rect_byte(rk, 0), nxk = (rk >> 8) & 0x1F;
+    const int dz_lo = rect_byte(rk, 2), wz = (rk >> 24) & 0xFF;
+    int nxmax = 8;
+    if (CLIP) nxmax = max(max((rw[0] >> 8) & 0x1F, (rw[1] >> 8) & 0x1F), max((rw[2] >> 8) & 0x1F, (rw[3] >> 8) & 0x1F));
+    else if (s == 3) nxmax = max((rw[0] >> 8) & 0x1F, (rw[1] >> 8) & 0x1F);  // rotations 2, 3 repeat 0, 1
     const uint32_t *mylist = es.list[k];
     const unsigned char *rows8 = reinterpret_cast<const unsigned char *>(es.rows);
     const int n_dxpass = (nxmax + 7) >> 3;               // 2 only when some rotation has 9..11 dx values

@@ -69,7 +69,9 @@ typedef struct iglu_config {
     int32_t auto_reset;         /* 1: an env whose previous step returned done is reset (env.py:206-261)
                                    at the start of the next step call, then stepped */
     int32_t reward_mode;        /* iglu_reward_mode */
-    int32_t write_grid_obs;     /* 1: materialise obs['grid'] int32[n,9,11,11] every step (env.py:288) */
+    int32_t write_grid_obs;     /* obs['grid'] int32[n,9,11,11] (env.py:288): 0 = not produced, 1 = rewritten in full
+                                   every step, 2 = kept up to date incrementally (the cell a step edits + whole
+                                   rows on reset); the buffer contents are identical for 1 and 2 */
     int32_t tlist_cap;          /* uint16 slots per row of iglu_state.tlist: multiple of 8, >= 72,
                                    <= IGLU_TLIST_ROW_MAX; holds IGLU_TLIST_HDR + max target blocks */
     int32_t reserved;           /* bit 0: 1 disables the observation-first / physics-first warp alternation

@@ -28,7 +28,8 @@ def time_steps(env, step_fn, K=300, W=20):
 
 
 def walking(n, support, rho, reward_mode, inplace, K=300):
-    env = gw.make_vec(n, action_space='walking', max_steps=250, reward_mode=reward_mode, grid_obs=not inplace,
+    env = gw.make_vec(n, action_space='walking', max_steps=250, reward_mode=reward_mode,
+                      grid_obs='incremental' if inplace == 2 else (not inplace),
                       alternate_phases=not os.environ.get('IGLU_NO_ALT'))
     env.set_tasks(synth_targets(n, rho, support, 1235).cuda())
     acts = torch.randint(0, 18, (64, n), device='cuda', dtype=torch.int32)
@@ -111,7 +112,7 @@ def reward_only(n, support, rho, reps=5):
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'one':  # one: <reward_mode> <inplace 0/1> <envs> [steps]
         K = int(sys.argv[5]) if len(sys.argv) > 5 else 30
-        print(json.dumps(walking(int(sys.argv[4]), 'compact', 0.2, sys.argv[2], bool(int(sys.argv[3])), K=K)))
+        print(json.dumps(walking(int(sys.argv[4]), 'compact', 0.2, sys.argv[2], int(sys.argv[3]), K=K)))
         sys.exit(0)
     which = sys.argv[1:] or ['walking', 'flying', 'reward']
     if 'walking' in which:

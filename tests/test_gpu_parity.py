@@ -247,14 +247,17 @@ def _tasks(rng, n):
     return T, S, poses
 
 
-@pytest.mark.parametrize('reward_mode,alternate', [('on_change', True), ('every_step', True), ('every_step', False)])
-def test_walking_batch_vs_oracle(reward_mode, alternate):
+@pytest.mark.parametrize('reward_mode,alternate,grid_obs', [('on_change', True, True), ('every_step', True, True),
+                                                            ('every_step', False, True),
+                                                            ('on_change', False, 'incremental'),
+                                                            ('every_step', True, 'incremental')])
+def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs):
     import gridworld_b200 as gw
     n, steps = 2048, 400
     rng = np.random.RandomState(3)
     T, S, poses = _tasks(rng, n)
     env = gw.make_vec(n, action_space='walking', max_steps=100, auto_reset=True, reward_mode=reward_mode,
-                      alternate_phases=alternate)
+                      alternate_phases=alternate, grid_obs=grid_obs)
     env.set_tasks(T, S, poses)
     orc = O.OracleBatch(n, 'walking', max_steps=100, threads=8)
     orc.set_tasks(T, S, poses)
