@@ -41,14 +41,7 @@ struct __align__(16) Slot {
     uint16_t trow[TL_HDR + TL_PRE];    // rectangle header + first target blocks
 };
 
-struct __align__(16) WarpScratch {
-    Slot slot[NB];
-    EvalScratch es;
-    unsigned long long bar[NB];        // mbarriers of the ring
-};
-
 constexpr size_t TABLE_BYTES = SPREAD_N * sizeof(unsigned long long);
-constexpr size_t SMEM_BYTES = TABLE_BYTES + WARPS_PER_CTA * sizeof(WarpScratch);
 
 struct StepParams {
     iglu_state st;
@@ -123,20 +116,44 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepParams p) {
+// PHASES selects what one launch does (same source, three instantiations):
+//   3  fused:        phase A (physics) + B (observation / reward) + C (bookkeeping) -- one launch per step
+//   1  physics only: phase A; leaves wrong_placement in istate w7 for the second launch
+//   2  observe only: phases B + C on the state left by a PHASES = 1 launch. It needs no fp64 physics
+//      registers, so it runs at 64 registers / 32 warps per SM with small (<= 32 env) chunks per warp,
+//      which is what the latency-bound per-env chain of phase B wants.
+template <int PHASES> struct StepCfg {
+    static constexpr int WPC = PHASES == 2 ? 16 : (PHASES == 1 ? 4 : WARPS_PER_CTA);
+    static constexpr int NBUF = PHASES == 2 ? 2 : NB;
+};
+template <int NBUF> struct __align__(16) WarpScratchT {
+    Slot slot[NBUF];
+    EvalScratch es;
+    unsigned long long bar[NBUF];      // mbarriers of the ring
+};
+template <int PHASES> constexpr size_t step_smem_bytes() {
+    return PHASES == 1 ? 0 : TABLE_BYTES + StepCfg<PHASES>::WPC * sizeof(WarpScratchT<StepCfg<PHASES>::NBUF>);
+}
+
+template <int KIND, int PHASES>
+__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : CTAS_PER_SM) k_step(const StepParams p) {
+    constexpr int WPC = StepCfg<PHASES>::WPC;
+    constexpr int NBUF = StepCfg<PHASES>::NBUF;
+    constexpr bool HAS_A = PHASES != 2, HAS_B = PHASES != 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
-    WarpScratch *scratch = reinterpret_cast<WarpScratch *>(smem_raw + TABLE_BYTES);
+    WarpScratchT<NBUF> *scratch = reinterpret_cast<WarpScratchT<NBUF> *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    WarpScratch &ws = scratch[wid];
-    build_spread_table(tbl, threadIdx.x, CTA_THREADS);
-    if (lane == 0) {
+    WarpScratchT<NBUF> &ws = scratch[HAS_B ? wid : 0];
+    if (HAS_B) {
+        build_spread_table(tbl, threadIdx.x, WPC * 32);
+        if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < NB; s++) mbar_init(&ws.bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int s = 0; s < NBUF; s++) mbar_init(&ws.bar[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     const int64_t n = p.st.n;
     const int GS = p.group;
@@ -152,55 +169,59 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
 
     // groups are dealt warp-major (warp w of every CTA before warp w + 1 of any) so that a partial last
     // wave spreads evenly over the SMs
-    for (int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x; grp < ngroups;
-         grp += (int64_t)gridDim.x * WARPS_PER_CTA) {
+    for (int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x; grp < ngroups; grp += (int64_t)gridDim.x * WPC) {
         const int64_t i = grp * GS + lane;
         const bool valid = lane < GS && i < n;
         const int64_t ii = valid ? i : n - 1;  // clamp: invalid lanes read a real env, write nothing
 
         // ------------------------------------------------------------- phase A
-        int w[7], tm[6];
+        int w[8], tm[6];
 #pragma unroll
-        for (int c = 0; c < 7; c++) w[c] = p.st.istate[c * n + ii];
+        for (int c = 0; c < 8; c++) w[c] = p.st.istate[c * n + ii];
 #pragma unroll
         for (int c = 0; c < 6; c++) tm[c] = p.st.tmeta[c * n + ii];
         const int nblk = tm[0], target_size = tm[1];
         const bool has_start = tm[5] != 0;
         Agent a;
-        a.x = p.st.pose[0 * n + ii]; a.y = p.st.pose[1 * n + ii]; a.z = p.st.pose[2 * n + ii];
-        a.yaw = p.st.pose[3 * n + ii]; a.pitch = p.st.pose[4 * n + ii]; a.dy = p.st.pose[5 * n + ii];
+        if (HAS_A) {
+            a.x = p.st.pose[0 * n + ii]; a.y = p.st.pose[1 * n + ii]; a.z = p.st.pose[2 * n + ii];
+            a.yaw = p.st.pose[3 * n + ii]; a.pitch = p.st.pose[4 * n + ii]; a.dy = p.st.pose[5 * n + ii];
+        }
         a.inv01 = w[0]; a.inv23 = w[1]; a.inv45 = w[2];
         a.active = w[3] & 0xFF; a.tis = (w[3] >> 8) & 0xFF; a.err = (w[3] >> 24) & 0xFF;
         const bool done_prev = ((w[3] >> 16) & 0xFF) != 0;
         int step_no = w[4], dsize = w[5], max_int = w[6];
 
         // auto-reset (env.py:206-261): grid <- starting grid, cooperatively, 16 bytes per lane
-        const bool do_reset = valid && p.cfg.auto_reset && done_prev;
-        unsigned rm = __ballot_sync(0xffffffffu, do_reset);
-        if (rm) {
-            while (rm) {
-                const int j = __ffs(rm) - 1;
-                rm &= rm - 1;
-                const int64_t ej = grp * GS + j;
-                const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
-                int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
-                const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
-                for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
-                if (inc_obs) {  // incremental observation: a reset rewrites the whole row
-                    const int8_t *si = p.st.init + ej * GSTRIDE;
-                    for (int c = lane; c < CELLS; c += 32) p.obs.grid[ej * CELLS + c] = hs ? (int32_t)si[c] : 0;
+        const bool do_reset = HAS_A && valid && p.cfg.auto_reset && done_prev;
+        if (HAS_A) {
+            unsigned rm = __ballot_sync(0xffffffffu, do_reset);
+            if (rm) {
+                while (rm) {
+                    const int j = __ffs(rm) - 1;
+                    rm &= rm - 1;
+                    const int64_t ej = grp * GS + j;
+                    const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
+                    int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
+                    const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
+                    for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
+                    if (inc_obs) {  // incremental observation: a reset rewrites the whole row
+                        const int8_t *si = p.st.init + ej * GSTRIDE;
+                        for (int c = lane; c < CELLS; c += 32) p.obs.grid[ej * CELLS + c] = hs ? (int32_t)si[c] : 0;
+                    }
                 }
+                if (HAS_B) {  // the TMA reads below go through the async proxy: order them after these writes
+                    __threadfence();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                }
+                __syncwarp();
             }
-            // the TMA reads below go through the async proxy: order them after these generic-proxy writes
-            __threadfence();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __syncwarp();
-        }
-        if (do_reset) {
-            a.x = p.st.init_pose[0 * n + i]; a.y = p.st.init_pose[1 * n + i]; a.z = p.st.init_pose[2 * n + i];
-            a.yaw = p.st.init_pose[3 * n + i]; a.pitch = p.st.init_pose[4 * n + i];
-            a.inv01 = tm[2]; a.inv23 = tm[3]; a.inv45 = tm[4];
-            step_no = 0; dsize = 0; max_int = 0;  // dy / tis / active survive (reference quirk)
+            if (do_reset) {
+                a.x = p.st.init_pose[0 * n + i]; a.y = p.st.init_pose[1 * n + i]; a.z = p.st.init_pose[2 * n + i];
+                a.yaw = p.st.init_pose[3 * n + i]; a.pitch = p.st.init_pose[4 * n + i];
+                a.inv01 = tm[2]; a.inv23 = tm[3]; a.inv45 = tm[4];
+                step_no = 0; dsize = 0; max_int = 0;  // dy / tis / active survive (reference quirk)
+            }
         }
 
         // ring producer: lane 0 issues the bulk copies of env j of this group into the next slot
@@ -208,8 +229,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
             const int nbj = __shfl_sync(0xffffffffu, nblk, j);
             if (lane == 0) {
                 const int64_t ej = grp * GS + j;
-                Slot &sl = ws.slot[seq_issue % NB];
-                unsigned long long *bar = &ws.bar[seq_issue % NB];
+                Slot &sl = ws.slot[seq_issue % NBUF];
+                unsigned long long *bar = &ws.bar[seq_issue % NBUF];
                 const uint32_t tbytes = (uint32_t)((2 * (TL_HDR + min(nbj, TL_PRE)) + 15) & ~15);
                 mbar_expect_tx(bar, GSTRIDE + tbytes);
                 tma_load(sl.grid, p.st.grid + ej * GSTRIDE, GSTRIDE, bar);
@@ -217,50 +238,50 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
             }
             seq_issue++;
         };
-        Action act;
-        act.s0 = act.s1 = act.jump = act.cam0 = act.cam1 = 0.0;
-        act.hotbar = 0; act.remove = act.add = false;
-        if (KIND == IGLU_WALKING_DISCRETE) {  // world.py:360-394
-            const int ac = p.actions[ii];
-            if (ac == 1) act.s0 = -1.0;
-            else if (ac == 2) act.s0 = 1.0;
-            else if (ac == 3) act.s1 = -1.0;
-            else if (ac == 4) act.s1 = 1.0;
-            else if (ac == 5) act.jump = 1.0;
-            else if (ac >= 6 && ac <= 11) act.hotbar = ac - 5;
-            else if (ac == 12) act.cam0 = -5.0;
-            else if (ac == 13) act.cam0 = 5.0;
-            else if (ac == 14) act.cam1 = -5.0;
-            else if (ac == 15) act.cam1 = 5.0;
-            else if (ac == 16) act.remove = true;
-            else if (ac == 17) act.add = true;
-        } else if (KIND == IGLU_FLYING) {  // world.py:416-432 (float32 widened to fp64)
-            act.s0 = (double)p.movement[3 * ii + 0];
-            act.s1 = (double)p.movement[3 * ii + 1];
-            act.jump = (double)p.movement[3 * ii + 2];
-            act.cam0 = (double)p.camera[2 * ii + 0];
-            act.cam1 = (double)p.camera[2 * ii + 1];
-            act.hotbar = p.inventory[ii];
-            const int pl = p.placement[ii];
-            act.add = pl == 1;
-            act.remove = pl == 2;
-        } else {  // world.py:396-414
-            const int32_t *b = p.buttons + 8 * ii;
-            if (b[0]) act.s0 += -1.0;
-            if (b[1]) act.s0 += 1.0;
-            if (b[2]) act.s1 += -1.0;
-            if (b[3]) act.s1 += 1.0;
-            act.jump = (double)b[4];
-            act.remove = b[5] != 0;
-            act.add = b[6] != 0;
-            act.hotbar = b[7];
-            act.cam0 = (double)p.camera[2 * ii + 0];
-            act.cam1 = (double)p.camera[2 * ii + 1];
-        }
 
-        const int dsize_old = dsize;
+        int dsize_old = dsize;
         int edit_cell = -1, edit_val = 0;
         auto run_physics = [&]() {
+            Action act;
+            act.s0 = act.s1 = act.jump = act.cam0 = act.cam1 = 0.0;
+            act.hotbar = 0; act.remove = act.add = false;
+            if (KIND == IGLU_WALKING_DISCRETE) {  // world.py:360-394
+                const int ac = p.actions[ii];
+                if (ac == 1) act.s0 = -1.0;
+                else if (ac == 2) act.s0 = 1.0;
+                else if (ac == 3) act.s1 = -1.0;
+                else if (ac == 4) act.s1 = 1.0;
+                else if (ac == 5) act.jump = 1.0;
+                else if (ac >= 6 && ac <= 11) act.hotbar = ac - 5;
+                else if (ac == 12) act.cam0 = -5.0;
+                else if (ac == 13) act.cam0 = 5.0;
+                else if (ac == 14) act.cam1 = -5.0;
+                else if (ac == 15) act.cam1 = 5.0;
+                else if (ac == 16) act.remove = true;
+                else if (ac == 17) act.add = true;
+            } else if (KIND == IGLU_FLYING) {  // world.py:416-432 (float32 widened to fp64)
+                act.s0 = (double)p.movement[3 * ii + 0];
+                act.s1 = (double)p.movement[3 * ii + 1];
+                act.jump = (double)p.movement[3 * ii + 2];
+                act.cam0 = (double)p.camera[2 * ii + 0];
+                act.cam1 = (double)p.camera[2 * ii + 1];
+                act.hotbar = p.inventory[ii];
+                const int pl = p.placement[ii];
+                act.add = pl == 1;
+                act.remove = pl == 2;
+            } else {  // world.py:396-414
+                const int32_t *b = p.buttons + 8 * ii;
+                if (b[0]) act.s0 += -1.0;
+                if (b[1]) act.s0 += 1.0;
+                if (b[2]) act.s1 += -1.0;
+                if (b[3]) act.s1 += 1.0;
+                act.jump = (double)b[4];
+                act.remove = b[5] != 0;
+                act.add = b[6] != 0;
+                act.hotbar = b[7];
+                act.cam0 = (double)p.camera[2 * ii + 0];
+                act.cam1 = (double)p.camera[2 * ii + 1];
+            }
             if (valid) {
                 step_no += 1;  // env.py:276
                 world_step(p.st.grid + i * GSTRIDE, p.st.init + i * GSTRIDE, has_start, a, act, flying,
@@ -290,7 +311,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
         int mi_eval = 0;
         auto ring_start = [&](unsigned mask) {
             todo = pend = mask;
-            for (int f = 0; f < NB && pend; f++) {
+            for (int f = 0; f < NBUF && pend; f++) {
                 issue(__ffs(pend) - 1);
                 pend &= pend - 1;
             }
@@ -301,14 +322,14 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
                 todo &= todo - 1;
                 const int64_t ej = grp * GS + j;
                 const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
-                Slot &sl = ws.slot[seq_cons % NB];
-                mbar_wait(&ws.bar[seq_cons % NB], (seq_cons / NB) & 1u);
+                Slot &sl = ws.slot[seq_cons % NBUF];
+                mbar_wait(&ws.bar[seq_cons % NBUF], (seq_cons / NBUF) & 1u);
                 if (patch) {  // the copy may have raced with this step's edit of the same env
                     const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
                     const int evl = __shfl_sync(0xffffffffu, edit_val, j);
                     if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
+                    __syncwarp();
                 }
-                __syncwarp();
                 if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
                 if (ev) {
                     build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
@@ -327,63 +348,81 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_step(const StepPar
             }
         };
 
-        // Half of the warps stream the observations first and run the physics afterwards, the other half
-        // the other way round, so that on every SM the latency-bound fp64 phase of one half overlaps the
-        // HBM-bound phase of the other. Observation-first warps stage the PRE-step grid: the (at most one)
-        // cell this step edits is patched into obs['grid'] by its own lane afterwards and only envs whose
-        // block count changed are evaluated again -- for all others the pre-step grid IS the post-step grid.
-        const bool b_first = early && alternate && (wid & 1);
+        if (PHASES == 1) {
+            run_physics();
+            if (inc_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
+        } else if (PHASES == 2) {
+            // state was advanced by the physics launch: wrong_placement (task.py:111) is in w7
+            const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || w[7] != 0));
+            ring_start(em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u));
+            ring_drain(grid_obs, em, false, true);
+        } else {
+            // Half of the warps stream the observations first and run the physics afterwards, the other
+            // half the other way round (scheduling option). Observation-first warps stage the PRE-step
+            // grid: the (at most one) cell this step edits is patched into obs['grid'] by its own lane
+            // afterwards and only envs whose block count changed are evaluated again -- for all others the
+            // pre-step grid IS the post-step grid.
+            const bool b_first = early && alternate && (wid & 1);
 #pragma unroll 1
-        for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once in the binary
-            if (stage == 1) {
-                run_physics();
-                if (((b_first && grid_obs) || inc_obs) && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
-                continue;
-            }
-            const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
-            unsigned mask, em;
-            bool start, drain = true, obs_on, patch, keep;
-            if (stage == 0) {
-                if (b_first) {  // pre-step grids: observations + (every_step) evaluations whose result is unused
-                    em = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
-                    mask = em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u);
-                    start = true; obs_on = grid_obs; patch = false; keep = false;
-                } else {        // only start the prefetch; consumed after the physics
-                    em = 0u;
-                    mask = __ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0));
-                    start = early; drain = false; obs_on = false; patch = false; keep = false;
+            for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once
+                if (stage == 1) {
+                    run_physics();
+                    if (((b_first && grid_obs) || inc_obs) && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
+                    continue;
                 }
-            } else {
-                if (b_first) {  // re-evaluate the envs whose block count changed
-                    em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && changed);
-                    start = true; obs_on = false; patch = true; keep = true;
+                const bool changed = dsize != dsize_old;  // task.py:111-112 gate (wrong_placement != 0)
+                unsigned mask, em;
+                bool start, drain = true, obs_on, patch, keep;
+                if (stage == 0) {
+                    if (b_first) {  // pre-step grids: observations + (every_step) evaluations, result unused
+                        em = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
+                        mask = em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u);
+                        start = true; obs_on = grid_obs; patch = false; keep = false;
+                    } else {        // only start the prefetch; consumed after the physics
+                        em = 0u;
+                        mask = __ballot_sync(0xffffffffu, valid && (grid_obs || nblk > 0));
+                        start = early; drain = false; obs_on = false; patch = false; keep = false;
+                    }
                 } else {
-                    em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
-                    start = !early; obs_on = grid_obs; patch = true; keep = true;
+                    if (b_first) {  // re-evaluate the envs whose block count changed
+                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && changed);
+                        start = true; obs_on = false; patch = true; keep = true;
+                    } else {
+                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
+                        start = !early; obs_on = grid_obs; patch = true; keep = true;
+                    }
                 }
+                if (start) ring_start(mask);
+                if (drain) ring_drain(obs_on, em, patch, keep);
             }
-            if (start) ring_start(mask);
-            if (drain) ring_drain(obs_on, em, patch, keep);
         }
 
         // ------------------------------------------------------------- phase C
         if (valid) {
-            const int wrong = dsize_old - dsize;                  // task.py:111
-            const int mi = wrong != 0 ? mi_eval : max_int;        // task.py:112
-            bool done = mi == target_size;                        // task.py:113
-            const int right = mi - max_int;                       // task.py:115
-            done = done || (step_no == p.cfg.max_steps);          // env.py:292
-            const double reward = right == 0 ? (double)wrong * p.cfg.wrong_placement_scale
-                                             : (double)right * p.cfg.right_placement_scale;
-            p.obs.reward[i] = reward;
-            p.obs.done[i] = (uint8_t)done;
-            p.st.istate[0 * n + i] = a.inv01;
-            p.st.istate[1 * n + i] = a.inv23;
-            p.st.istate[2 * n + i] = a.inv45;
-            p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
-            p.st.istate[4 * n + i] = step_no;
-            p.st.istate[5 * n + i] = dsize;
-            p.st.istate[6 * n + i] = mi;
+            if (HAS_A) {
+                p.st.istate[0 * n + i] = a.inv01;
+                p.st.istate[1 * n + i] = a.inv23;
+                p.st.istate[2 * n + i] = a.inv45;
+                p.st.istate[4 * n + i] = step_no;
+                p.st.istate[5 * n + i] = dsize;
+            }
+            const int wrong = HAS_A ? dsize_old - dsize : w[7];                // task.py:111
+            if (PHASES == 1) {  // bookkeeping is finished by the observe launch
+                p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((a.err & 0xFF) << 24);
+                p.st.istate[6 * n + i] = max_int;
+                p.st.istate[7 * n + i] = wrong;
+            } else {
+                const int mi = wrong != 0 ? mi_eval : max_int;                 // task.py:112
+                bool done = mi == target_size;                                 // task.py:113
+                const int right = mi - max_int;                                // task.py:115
+                done = done || (step_no == p.cfg.max_steps);                   // env.py:292
+                const double reward = right == 0 ? (double)wrong * p.cfg.wrong_placement_scale
+                                                 : (double)right * p.cfg.right_placement_scale;
+                p.obs.reward[i] = reward;
+                p.obs.done[i] = (uint8_t)done;
+                p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
+                p.st.istate[6 * n + i] = mi;
+            }
         }
     }
 }
@@ -685,9 +724,13 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     int rc = check(cudaMemcpyToSymbol(g_trig, trig, sizeof(trig)));
     if (!rc) rc = check(cudaMemcpyToSymbol(g_strafe_deg, sdeg, sizeof(sdeg)));
     if (!rc) rc = check(cudaMemcpyToSymbol(g_jump_speed, &jump, sizeof(jump)));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_step<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_step<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    const int s3 = (int)step_smem_bytes<3>(), s2 = (int)step_smem_bytes<2>();
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s3));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s3));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, s3));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (rc) { delete c; return rc; }
     *out = c;
     return IGLU_OK;
@@ -724,17 +767,41 @@ extern "C" int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *o
     return check(cudaPeekAtLastError());
 }
 
-// Persistent launch: CTAS_PER_SM CTAs on every SM. When 32-env groups would leave warp slots idle (fewer
-// groups than resident warps) the groups are halved so that twice as many warps share the per-env work.
+// One step = either one fused launch (physics + observation/reward + bookkeeping) or two launches
+// (physics, then observe). The split is used whenever every env needs phase-B work (obs['grid'] rewritten
+// every step and/or maximal_intersection on every step): the observe launch has no fp64 physics in it, so
+// it fits 64 registers and runs 32 warps per SM on small chunks, which shortens the latency-bound
+// per-env chain (measured, profiles/). reserved bit 1 forces the fused launch.
 template <int KIND>
 static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = p.st.n;
+    const bool all_envs_b = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP || (p.cfg.write_grid_obs == 1 && p.obs.grid);
+    const bool split = all_envs_b && !(p.cfg.reserved & 2);
+    if (!split) {
+        const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
+        const int64_t warp_slots = resident_ctas * StepCfg<3>::WPC;
+        p.group = (2 * ((n + 31) / 32) <= warp_slots) ? 16 : 32;
+        const int64_t groups = (n + p.group - 1) / p.group;
+        const unsigned grid = (unsigned)(groups < resident_ctas ? groups : resident_ctas);
+        k_step<KIND, 3><<<grid, StepCfg<3>::WPC * 32, step_smem_bytes<3>(), s>>>(p);
+        ctx->last_launches = 1;
+        return check(cudaPeekAtLastError());
+    }
+    // launch 1: physics, one thread per env, 32-env groups, 4-warp CTAs
+    p.group = 32;
+    const int64_t groups_a = (n + 31) / 32;
+    k_step<KIND, 1><<<(unsigned)((groups_a + StepCfg<1>::WPC - 1) / StepCfg<1>::WPC), StepCfg<1>::WPC * 32, 0, s>>>(p);
+    // launch 2: observe, persistent, chunk = ceil(n / resident warps) envs per warp (<= 32)
     const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
-    const int64_t warp_slots = resident_ctas * WARPS_PER_CTA;
-    p.group = (2 * ((p.st.n + 31) / 32) <= warp_slots) ? 16 : 32;
-    const int64_t groups = (p.st.n + p.group - 1) / p.group;
-    const unsigned grid = (unsigned)(groups < resident_ctas ? groups : resident_ctas);
-    k_step<KIND><<<grid, CTA_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    ctx->last_launches = 1;
+    const int64_t warp_slots = resident_ctas * StepCfg<2>::WPC;
+    int64_t chunk = (n + warp_slots - 1) / warp_slots;
+    p.group = (int)(chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk));
+    const int64_t groups_b = (n + p.group - 1) / p.group;
+    const int64_t ctas_b = (groups_b + StepCfg<2>::WPC - 1) / StepCfg<2>::WPC;
+    k_step<KIND, 2><<<(unsigned)(ctas_b < resident_ctas ? ctas_b : resident_ctas), StepCfg<2>::WPC * 32,
+                      step_smem_bytes<2>(), s>>>(p);
+    ctx->last_launches = 2;
     return check(cudaPeekAtLastError());
 }
 

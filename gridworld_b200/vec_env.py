@@ -69,7 +69,9 @@ class IGLUVecEnv:
       on every step; outputs are identical), grid_obs (True: rewrite the int32 obs['grid'] in full every step;
       'incremental': keep the persistent obs['grid'] buffer up to date cell by cell -- same contents, ~20x
       fewer bytes; False: no int32 copy, obs['grid'] is the int8 state view),
-      alternate_phases (scheduling only: half of the warps write observations before the physics).
+      alternate_phases (scheduling only: half of the warps write observations before the physics),
+      split_launch (scheduling only: physics and observation/reward as two launches when every env needs
+      observation or reward work).
 
     step() returns device tensors that alias persistent buffers: a policy reads them in place.
     """
@@ -77,7 +79,7 @@ class IGLUVecEnv:
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
-                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None):
+                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None, split_launch=True):
         if render:
             raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
         if reward_mode not in ('on_change', 'every_step'):
@@ -143,7 +145,7 @@ class IGLUVecEnv:
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
                           _lib.REWARD_EVERY_STEP if reward_mode == 'every_step' else _lib.REWARD_ON_CHANGE,
-                          int(self.grid_obs_mode), int(tlist_cap), 0 if alternate_phases else 1,
+                          int(self.grid_obs_mode), int(tlist_cap), (0 if alternate_phases else 1) | (0 if split_launch else 2),
                           float(right_placement_scale), float(wrong_placement_scale))
         self._ctx = C.c_void_p()
         with torch.cuda.device(dev):
@@ -179,7 +181,7 @@ class IGLUVecEnv:
         return t
 
     def _count(self):
-        self.gpu_launches += 1  # every C-ABI entry point of this class launches exactly one kernel
+        self.gpu_launches += self._L.iglu_last_launch_count(self._ctx)
 
     # ------------------------------------------------------------------ tasks
     def set_tasks(self, targets, starts=None, init_poses=None, env_idx=None, reset=True):

@@ -74,8 +74,9 @@ typedef struct iglu_config {
                                    rows on reset); the buffer contents are identical for 1 and 2 */
     int32_t tlist_cap;          /* uint16 slots per row of iglu_state.tlist: multiple of 8, >= 72,
                                    <= IGLU_TLIST_ROW_MAX; holds IGLU_TLIST_HDR + max target blocks */
-    int32_t reserved;           /* bit 0: 1 disables the observation-first / physics-first warp alternation
-                                   (scheduling only, results identical) */
+    int32_t reserved;           /* scheduling switches (results identical): bit 0 = 1 disables the observation-first /
+                                   physics-first warp alternation of the fused launch; bit 1 = 1 forces the fused
+                                   launch where the library would use two launches (physics, then observe) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
 } iglu_config;
@@ -91,7 +92,7 @@ typedef struct iglu_state {
     double *init_pose; /* [5][n]  x, y, z, yaw, pitch      (initial_position / initial_rotation) */
     int32_t *istate;   /* [8][n]  w0..w2: inventory 6 x int16; w3: active | tis<<8 | done_prev<<16 | err<<24;
                                   w4: step_no; w5: nnz(grid - init) (task.prev_grid_size); w6: max_int;
-                                  w7: reserved */
+                                  w7: wrong_placement of the last physics launch (task.py:111) */
     uint16_t *tlist;   /* [n][tlist_cap]  row = 16-byte header + block list of the synthetic task.
                                   header: 16 int8, per rotation r: dx_lo, dx_hi, dz_lo, dz_hi of the admissible
                                   shifts (task.py:57-72; always a rectangle);
