@@ -569,25 +569,20 @@ __device__ __forceinline__ void load_cells_smem(uint32_t *dst, const int8_t *src
 
 // Bounding box (x_min, x_max, z_min, z_max) of the non-zero cells of a staged grid; empty = (10, 0, 10, 0).
 __device__ __forceinline__ void bbox_smem(const uint32_t *g, int lane, int &xmin, int &xmax, int &zmin, int &zmax) {
-    xmin = 10; xmax = 0; zmin = 10; zmax = 0;
-    unsigned long long m = cell_mask36(g, nullptr, lane);
-    while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int c = 36 * lane + b, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-        xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
-    }
-    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-    zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
+    int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+    for_each_nonzero_cell(g, nullptr, lane, [&](int c, int, int) {
+        const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+    });
+    xmin = __reduce_min_sync(0xffffffffu, x0); xmax = __reduce_max_sync(0xffffffffu, x1);
+    zmin = __reduce_min_sync(0xffffffffu, z0); zmax = __reduce_max_sync(0xffffffffu, z1);
 }
 
 // Ordered (ascending cell index) list of the non-zero cells of a staged target grid + their bounding box.
 // Lane L owns the 36 cells [36 L, 36 L + 36): count, exclusive scan over lanes, emit. Returns the count.
 __device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list, int lane, int &xmin, int &xmax,
                                               int &zmin, int &zmax) {
-    xmin = 10; xmax = 0; zmin = 10; zmax = 0;
-    unsigned long long m = cell_mask36(t, nullptr, lane);
-    const int cnt = __popcll(m);
+    const int cnt = count_nonzero_cells(t, lane);
     int pos = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -596,16 +591,14 @@ __device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list,
     }
     const int total = __shfl_sync(0xffffffffu, pos, 31);
     pos -= cnt;
-    while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        const int tv = cell_value36(t, lane, b);
-        const int c = 36 * lane + b, y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+    int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+    for_each_nonzero_cell(t, nullptr, lane, [&](int c, int tv, int) {
+        const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
         list[pos++] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
-        xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
-    }
-    xmin = __reduce_min_sync(0xffffffffu, xmin); xmax = __reduce_max_sync(0xffffffffu, xmax);
-    zmin = __reduce_min_sync(0xffffffffu, zmin); zmax = __reduce_max_sync(0xffffffffu, zmax);
+        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+    });
+    xmin = __reduce_min_sync(0xffffffffu, x0); xmax = __reduce_max_sync(0xffffffffu, x1);
+    zmin = __reduce_min_sync(0xffffffffu, z0); zmax = __reduce_max_sync(0xffffffffu, z1);
     return total;
 }
 
@@ -768,16 +761,15 @@ extern "C" int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *o
 }
 
 // One step = either one fused launch (physics + observation/reward + bookkeeping) or two launches
-// (physics, then observe). The split is used whenever every env needs phase-B work (obs['grid'] rewritten
-// every step and/or maximal_intersection on every step): the observe launch has no fp64 physics in it, so
-// it fits 64 registers and runs 32 warps per SM on small chunks, which shortens the latency-bound
-// per-env chain (measured, profiles/). reserved bit 1 forces the fused launch.
+// (physics, then observe). The split is used when maximal_intersection is evaluated for every env on every
+// step: the observe launch has no fp64 physics in it, so it fits 64 registers and runs 32 warps per SM on
+// small chunks, which shortens the latency-bound per-env chain. reserved bit 1 forces the fused launch.
 template <int KIND>
 static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n = p.st.n;
-    const bool all_envs_b = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP || (p.cfg.write_grid_obs == 1 && p.obs.grid);
-    const bool split = all_envs_b && !(p.cfg.reserved & 2);
+    // measured (profiles/): the split wins when every env is evaluated; the fused launch wins otherwise
+    const bool split = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP && !(p.cfg.reserved & 2);
     if (!split) {
         const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
         const int64_t warp_slots = resident_ctas * StepCfg<3>::WPC;

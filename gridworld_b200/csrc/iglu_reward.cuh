@@ -56,12 +56,14 @@ __device__ __forceinline__ void build_spread_table(unsigned long long *tbl, int 
     }
 }
 
-// Lane L owns the 36 cells [36 L, 36 L + 36) of a staged grid (nine 32-bit words; lane stride 9 words is
-// conflict-free). Returns a 36-bit mask with bit b set when cell 36 L + b differs from `sub` (or from 0
-// when sub == nullptr). `g` is shared memory, `sub` may be shared or global. Grids are sparse, so all
-// per-cell work is done by looping over the set bits instead of visiting every byte.
-__device__ __forceinline__ unsigned long long cell_mask36(const uint32_t *g, const uint32_t *sub, int lane) {
-    unsigned long long m = 0ull;
+// Sparse traversal of a staged grid. Lane L owns the 36 cells [36 L, 36 L + 36) = nine 32-bit words (lane
+// stride 9 words is bank-conflict free). Grids hold a few dozen blocks, so instead of visiting every
+// byte each lane first builds a 9-bit mask of its non-zero words (3 instructions per word) and then
+// loops over the set words / non-zero bytes only, in ascending cell order:  f(cell, value, sub_value).
+// `g` is shared memory; `sub` (may be nullptr) is subtracted cell-wise and may be shared or global.
+template <class F>
+__device__ __forceinline__ void for_each_nonzero_cell(const uint32_t *g, const uint32_t *sub, int lane, F f) {
+    unsigned wm = 0u;
 #pragma unroll
     for (int q = 0; q < 9; q++) {
         const int i = 9 * lane + q;
@@ -70,16 +72,32 @@ __device__ __forceinline__ unsigned long long cell_mask36(const uint32_t *g, con
             x = g[i];
             if (sub) x ^= sub[i];
         }
-        const uint32_t nz = ((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) >> 7;  // 1 per non-zero byte
-        const uint32_t nib = (nz * 0x01020408u) >> 24;                                    // gather into 4 bits
-        m |= (unsigned long long)(nib & 0xFu) << (4 * q);
+        if (x) wm |= 1u << q;
     }
-    return m;
+    while (wm) {
+        const int q = __ffs(wm) - 1;
+        wm &= wm - 1;
+        const int i = 9 * lane + q;
+        const uint32_t gw = g[i], sw = sub ? sub[i] : 0u;
+        uint32_t x = gw ^ sw;
+        while (x) {
+            const int j = (__ffs(x) - 1) >> 3;
+            x &= ~(0xFFu << (8 * j));
+            f(4 * i + j, (int)(int8_t)(gw >> (8 * j)), (int)(int8_t)(sw >> (8 * j)));
+        }
+    }
 }
 
-// value of cell `b` (0..35) of lane `lane`'s segment
-__device__ __forceinline__ int cell_value36(const uint32_t *g, int lane, int b) {
-    return (int)(int8_t)(g[9 * lane + (b >> 2)] >> (8 * (b & 3)));
+// number of cells of lane L's segment that differ from 0 (ascending-order emit needs it for the scan)
+__device__ __forceinline__ int count_nonzero_cells(const uint32_t *g, int lane) {
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+        const int i = 9 * lane + q;
+        const uint32_t x = i < GSTRIDE / 4 ? g[i] : 0u;
+        cnt += __popc((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u);
+    }
+    return cnt;
 }
 
 // Pack the (difference) grid `grid` (minus `init` when has_init) into es.rows / es.planes. `grid` is a
@@ -94,22 +112,17 @@ __device__ __forceinline__ void build_rows(EvalScratch &es, const uint32_t *grid
         if (q < ROWS_WORDS / 4) rz[q] = make_int4(0, 0, 0, 0);
     }
     if (lane < 16) es.planes[lane] = 0u;
-    const uint32_t *iw = has_init ? reinterpret_cast<const uint32_t *>(init) : nullptr;
-    unsigned long long m = cell_mask36(grid, iw, lane);
     __syncwarp();
-    while (m) {
-        const int b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-        int d = cell_value36(grid, lane, b);
-        if (has_init) d -= cell_value36(iw, lane, b);
-        const int cell = 36 * lane + b;
+    const uint32_t *iw = has_init ? reinterpret_cast<const uint32_t *>(init) : nullptr;
+    for_each_nonzero_cell(grid, iw, lane, [&](int cell, int gv, int sv) {
+        const int d = gv - sv;
         if (d >= -6 && d <= 6) {  // other values are not colour differences and match nothing
             const int y = cell / 121, r = cell - 121 * y, x = r / 11, z = r - 11 * x;
             const int row = class_of(d & 15) * ROWS_PER_CLASS + y * 11 + x;
             atomicOr(&es.rows[row >> 1], (1u << (10 - z)) << (16 * (row & 1)));
             atomicOr(&es.planes[d & 15], 1u << y);
         }
-    }
+    });
     __syncwarp();
 }
 
