@@ -106,10 +106,13 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         const int m = lane + 32 * it;
         const uint32_t w = __funnelshift_r(lo[it], hi[it], 8 * h);  // bytes h + 4m .. h + 4m + 3
         int4 v;
-        v.x = (int)(int8_t)(w);  // sign-extend each byte
-        v.y = (int)(int8_t)(w >> 8);
-        v.z = (int)(int8_t)(w >> 16);
-        v.w = (int)(int8_t)(w >> 24);
+        v.x = (int)__byte_perm(w, 0, 0x4440);  // zero-extend each byte (one PRMT) ...
+        v.y = (int)__byte_perm(w, 0, 0x4441);
+        v.z = (int)__byte_perm(w, 0, 0x4442);
+        v.w = (int)__byte_perm(w, 0, 0x4443);
+        if (w & 0x80808080u) {                  // ... and sign-extend in the rare word that holds a negative cell
+            v.x = (int)(int8_t)(w); v.y = (int)(int8_t)(w >> 8); v.z = (int)(int8_t)(w >> 16); v.w = (int)(int8_t)(w >> 24);
+        }
         if (it < 8 || m < nbody) __stcs(o4 + m, v);
     }
     const int t0 = h + 4 * nbody;
@@ -166,6 +169,12 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     const bool alternate = (p.cfg.reserved & 1) == 0;  // reserved bit 0 = 1 disables the phase alternation
     const int cap = p.cfg.tlist_cap;
     uint32_t seq_issue = 0, seq_cons = 0;  // ring sequence numbers (warp-uniform, live across groups)
+    uint32_t slot_addr[NBUF], bar_addr[NBUF];  // shared-window addresses of the ring (computed once)
+#pragma unroll
+    for (int s = 0; s < NBUF; s++) {
+        slot_addr[s] = HAS_B ? smem_u32(&ws.slot[s]) : 0u;
+        bar_addr[s] = HAS_B ? smem_u32(&ws.bar[s]) : 0u;
+    }
 
     // groups are dealt warp-major (warp w of every CTA before warp w + 1 of any) so that a partial last
     // wave spreads evenly over the SMs
@@ -225,16 +234,19 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
         }
 
         // ring producer: lane 0 issues the bulk copies of env j of this group into the next slot
+        const uint32_t my_tbytes = (uint32_t)((2 * (TL_HDR + min(nblk, TL_PRE)) + 15) & ~15);
         auto issue = [&](int j) {
-            const int nbj = __shfl_sync(0xffffffffu, nblk, j);
+            const uint32_t tbytes = __shfl_sync(0xffffffffu, my_tbytes, j);
             if (lane == 0) {
                 const int64_t ej = grp * GS + j;
-                Slot &sl = ws.slot[seq_issue % NBUF];
-                unsigned long long *bar = &ws.bar[seq_issue % NBUF];
-                const uint32_t tbytes = (uint32_t)((2 * (TL_HDR + min(nbj, TL_PRE)) + 15) & ~15);
-                mbar_expect_tx(bar, GSTRIDE + tbytes);
-                tma_load(sl.grid, p.st.grid + ej * GSTRIDE, GSTRIDE, bar);
-                tma_load(sl.trow, p.st.tlist + ej * cap, tbytes, bar);
+                uint32_t sa = slot_addr[0], ba = bar_addr[0];
+#pragma unroll
+                for (int s = 1; s < NBUF; s++) if ((int)(seq_issue % NBUF) == s) { sa = slot_addr[s]; ba = bar_addr[s]; }
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t)GSTRIDE + tbytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sa), "l"(p.st.grid + ej * GSTRIDE), "r"((uint32_t)GSTRIDE), "r"(ba) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sa + (uint32_t)GSTRIDE), "l"(p.st.tlist + ej * cap), "r"(tbytes), "r"(ba) : "memory");
             }
             seq_issue++;
         };
