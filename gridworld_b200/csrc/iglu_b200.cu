@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     WarpScratchT<NBUF> *scratch = reinterpret_cast<WarpScratchT<NBUF> *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpScratchT<NBUF> &ws = scratch[HAS_B ? wid : 0];
+    if (PHASES == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the observe launch get resident early
     if (HAS_B) {
         build_spread_table(tbl, threadIdx.x, WPC * 32);
         if (lane == 0) {
@@ -157,6 +158,9 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
         }
         __syncthreads();
     }
+    // Programmatic dependent launch: the prologue above overlaps the tail of the previous launch on the stream;
+    // nothing that launch wrote is read before this point. (A no-op when launched without the PDL attribute.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int64_t n = p.st.n;
     const int GS = p.group;
@@ -803,10 +807,19 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     p.group = (int)(chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk));
     const int64_t groups_b = (n + p.group - 1) / p.group;
     const int64_t ctas_b = (groups_b + StepCfg<2>::WPC - 1) / StepCfg<2>::WPC;
-    k_step<KIND, 2><<<(unsigned)(ctas_b < resident_ctas ? ctas_b : resident_ctas), StepCfg<2>::WPC * 32,
-                      step_smem_bytes<2>(), s>>>(p);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)(ctas_b < resident_ctas ? ctas_b : resident_ctas));
+    lc.blockDim = dim3(StepCfg<2>::WPC * 32);
+    lc.dynamicSmemBytes = step_smem_bytes<2>();
+    lc.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    const int rc = check(cudaLaunchKernelEx(&lc, k_step<KIND, 2>, p));
     ctx->last_launches = 2;
-    return check(cudaPeekAtLastError());
+    return rc ? rc : check(cudaPeekAtLastError());
 }
 
 extern "C" int iglu_step_walking(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions,
