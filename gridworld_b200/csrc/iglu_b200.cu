@@ -777,15 +777,17 @@ extern "C" int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *o
 }
 
 // One step = either one fused launch (physics + observation/reward + bookkeeping) or two launches
-// (physics, then observe). The split is used when maximal_intersection is evaluated for every env on every
-// step: the observe launch has no fp64 physics in it, so it fits 64 registers and runs 32 warps per SM on
-// small chunks, which shortens the latency-bound per-env chain. reserved bit 1 forces the fused launch.
+// (physics, then observe). In the split form the physics launch needs no shared memory and the observe
+// launch has no fp64 physics in it, so it fits 64 registers and runs 32 warps per SM on small chunks,
+// which shortens the latency-bound per-env chain. reserved bit 1 forces the fused launch, bit 2 the split.
 template <int KIND>
 static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n = p.st.n;
-    // measured (profiles/): the split wins when every env is evaluated; the fused launch wins otherwise
-    const bool split = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP && !(p.cfg.reserved & 2);
+    // measured (profiles/r01_launch_policy.txt): the fused launch only wins for on_change reward + fully
+    // rewritten obs['grid'] (its ring prefetch hides behind the physics); everything else is faster split
+    const bool fused_better = p.cfg.reward_mode != IGLU_REWARD_EVERY_STEP && p.cfg.write_grid_obs == 1 && p.obs.grid;
+    const bool split = ((!fused_better) && !(p.cfg.reserved & 2)) || (p.cfg.reserved & 4);
     if (!split) {
         const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
         const int64_t warp_slots = resident_ctas * StepCfg<3>::WPC;

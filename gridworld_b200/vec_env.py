@@ -145,7 +145,7 @@ class IGLUVecEnv:
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
                           _lib.REWARD_EVERY_STEP if reward_mode == 'every_step' else _lib.REWARD_ON_CHANGE,
-                          int(self.grid_obs_mode), int(tlist_cap), (0 if alternate_phases else 1) | (0 if split_launch else 2),
+                          int(self.grid_obs_mode), int(tlist_cap), (0 if alternate_phases else 1) | (0 if split_launch else 2) | (4 if split_launch == 'force' else 0),
                           float(right_placement_scale), float(wrong_placement_scale))
         self._ctx = C.c_void_p()
         with torch.cuda.device(dev):

@@ -76,7 +76,8 @@ typedef struct iglu_config {
                                    <= IGLU_TLIST_ROW_MAX; holds IGLU_TLIST_HDR + max target blocks */
     int32_t reserved;           /* scheduling switches (results identical): bit 0 = 1 disables the observation-first /
                                    physics-first warp alternation of the fused launch; bit 1 = 1 forces the fused
-                                   launch where the library would use two launches (physics, then observe) */
+                                   launch where the library would use two launches (physics, then observe);
+                                   bit 2 = 1 forces the two-launch form */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
 } iglu_config;

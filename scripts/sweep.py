@@ -31,7 +31,7 @@ def walking(n, support, rho, reward_mode, inplace, K=300):
     env = gw.make_vec(n, action_space='walking', max_steps=250, reward_mode=reward_mode,
                       grid_obs='incremental' if inplace == 2 else (not inplace),
                       alternate_phases=not os.environ.get('IGLU_NO_ALT'),
-                      split_launch=not os.environ.get('IGLU_NO_SPLIT'))
+                      split_launch='force' if os.environ.get('IGLU_FORCE_SPLIT') else (not os.environ.get('IGLU_NO_SPLIT')))
     env.set_tasks(synth_targets(n, rho, support, 1235).cuda())
     acts = torch.randint(0, 18, (64, n), device='cuda', dtype=torch.int32)
     ms = time_steps(env, lambda t: env.step(acts[t % 64]), K=K)
