@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
             if (inc_obs && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
         } else if (PHASES == 2) {
             // state was advanced by the physics launch: wrong_placement (task.py:111) is in w7
-            const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || w[7] != 0));
+            // an all-zero difference grid (dsize == 0) scores 0 without looking: no target cell can equal 0
+            const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != 0 && (every_step || w[7] != 0));
             ring_start(em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u));
             ring_drain(grid_obs, em, false, true);
         } else {
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 bool start, drain = true, obs_on, patch, keep;
                 if (stage == 0) {
                     if (b_first) {  // pre-step grids: observations + (every_step) evaluations, result unused
-                        em = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0) : 0u;
+                        em = every_step ? __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != 0) : 0u;
                         mask = em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u);
                         start = true; obs_on = grid_obs; patch = false; keep = false;
                     } else {        // only start the prefetch; consumed after the physics
@@ -401,10 +402,10 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                     }
                 } else {
                     if (b_first) {  // re-evaluate the envs whose block count changed
-                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && changed);
+                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && changed && dsize != 0);
                         start = true; obs_on = false; patch = true; keep = true;
                     } else {
-                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && (every_step || changed));
+                        em = mask = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != 0 && (every_step || changed));
                         start = !early; obs_on = grid_obs; patch = true; keep = true;
                     }
                 }
