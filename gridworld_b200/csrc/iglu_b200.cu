@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/iglu_b200.h"
@@ -27,7 +28,7 @@ namespace iglu {
 #define IGLU_WARPS_PER_CTA 8
 #endif
 #ifndef IGLU_RING
-#define IGLU_RING 4
+#define IGLU_RING 3
 #endif
 constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
@@ -82,17 +83,25 @@ __device__ __forceinline__ int pack16(int a, int b) { return (a & 0xFFFF) | (b <
 __device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xFFFF); }
 __device__ __forceinline__ int hi16(int w) { return (int)(int16_t)((unsigned)w >> 16); }
 
-// Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element
-// e0 of the obs array (4-byte aligned only); the body is written as 16-byte streaming stores.
+// Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element e0
+// of the obs array (4-byte aligned only). The 16-byte aligned body is widened into a shared-memory staging
+// buffer and written by ONE TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP.G.S): plain
+// per-lane stores of 4.4 KB per env back up the SM's memory-instruction queue once HBM is saturated and
+// stall every warp's shared-memory traffic with it (measured: observation stores and reward evaluation
+// did not overlap); the bulk-copy engine drains asynchronously instead. The <= 3 head / tail elements
+// are stored by single lanes. `stage` must not be rewritten before obs_store_wait_read().
+__device__ __forceinline__ void obs_store_wait_read(int lane) {
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+}
 __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, int64_t e0, const uint32_t *sg,
-                                               int lane) {
+                                               uint32_t *stage, int lane) {
     const int8_t *sg8 = reinterpret_cast<const int8_t *>(sg);
     int32_t *og = obs_grid + e0;
     const int h = (int)((4 - (e0 & 3)) & 3);  // elements before the first 16-byte boundary
+    const int nbody = (CELLS - h) >> 2;        // 271 or 272 sixteen-byte chunks
+    obs_store_wait_read(lane);                 // the previous env's bulk store has finished reading `stage`
     if (lane < h) og[lane] = (int32_t)sg8[lane];
-    const int nbody = (CELLS - h) >> 2;  // 271 or 272 sixteen-byte chunks
-    int4 *o4 = reinterpret_cast<int4 *>(og + h);
-    // fully unrolled, all shared-memory loads first: one LDS latency per env instead of one per chunk
     uint32_t lo[9], hi[9];
 #pragma unroll
     for (int it = 0; it < 9; it++) {
@@ -101,6 +110,7 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         lo[it] = on ? sg[m] : 0u;
         hi[it] = on ? sg[m + 1] : 0u;
     }
+    int4 *s4 = reinterpret_cast<int4 *>(stage);
 #pragma unroll
     for (int it = 0; it < 9; it++) {
         const int m = lane + 32 * it;
@@ -113,10 +123,17 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         if (w & 0x80808080u) {                  // ... and sign-extend in the rare word that holds a negative cell
             v.x = (int)(int8_t)(w); v.y = (int)(int8_t)(w >> 8); v.z = (int)(int8_t)(w >> 16); v.w = (int)(int8_t)(w >> 24);
         }
-        if (it < 8 || m < nbody) __stcs(o4 + m, v);
+        if (it < 8 || m < nbody) s4[m] = v;
     }
     const int t0 = h + 4 * nbody;
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
+    __syncwarp();
+    if (lane == 0) {
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                     ::"l"(og + h), "r"(smem_u32(stage)), "r"((uint32_t)(16 * nbody)) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
 }
 
 // PHASES selects what one launch does (same source, three instantiations):
@@ -125,13 +142,20 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
 //   2  observe only: phases B + C on the state left by a PHASES = 1 launch. It needs no fp64 physics
 //      registers, so it runs at 64 registers / 32 warps per SM with small (<= 32 env) chunks per warp,
 //      which is what the latency-bound per-env chain of phase B wants.
+#ifndef IGLU_OBS_WARPS
+#define IGLU_OBS_WARPS 8
+#endif
+#ifndef IGLU_OBS_RING
+#define IGLU_OBS_RING 3
+#endif
 template <int PHASES> struct StepCfg {
-    static constexpr int WPC = PHASES == 2 ? 16 : (PHASES == 1 ? 4 : WARPS_PER_CTA);
-    static constexpr int NBUF = PHASES == 2 ? 2 : NB;
+    static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
+    static constexpr int NBUF = PHASES == 2 ? IGLU_OBS_RING : NB;
 };
 template <int NBUF> struct __align__(16) WarpScratchT {
     Slot slot[NBUF];
     EvalScratch es;
+    uint32_t stage[1092];              // one env's obs['grid'] row widened to int32, source of the TMA bulk store
     unsigned long long bar[NBUF];      // mbarriers of the ring
 };
 template <int PHASES> constexpr size_t step_smem_bytes() {
@@ -183,7 +207,8 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     // groups are dealt warp-major (warp w of every CTA before warp w + 1 of any) so that a partial last
     // wave spreads evenly over the SMs
     for (int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x; grp < ngroups; grp += (int64_t)gridDim.x * WPC) {
-        const int64_t i = grp * GS + lane;
+        auto env_of = [&](int j) -> int64_t { return grp * GS + j; };
+        const int64_t i = env_of(lane);
         const bool valid = lane < GS && i < n;
         const int64_t ii = valid ? i : n - 1;  // clamp: invalid lanes read a real env, write nothing
 
@@ -213,7 +238,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 while (rm) {
                     const int j = __ffs(rm) - 1;
                     rm &= rm - 1;
-                    const int64_t ej = grp * GS + j;
+                    const int64_t ej = env_of(j);
                     const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
                     int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
                     const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
@@ -239,18 +264,20 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 
         // ring producer: lane 0 issues the bulk copies of env j of this group into the next slot
         const uint32_t my_tbytes = (uint32_t)((2 * (TL_HDR + min(nblk, TL_PRE)) + 15) & ~15);
+        unsigned need_tlist = 0xffffffffu;  // envs whose target list is needed (the ones that get evaluated)
         auto issue = [&](int j) {
-            const uint32_t tbytes = __shfl_sync(0xffffffffu, my_tbytes, j);
+            const uint32_t tbytes = ((need_tlist >> j) & 1u) ? __shfl_sync(0xffffffffu, my_tbytes, j) : 0u;
             if (lane == 0) {
-                const int64_t ej = grp * GS + j;
+                const int64_t ej = env_of(j);
                 uint32_t sa = slot_addr[0], ba = bar_addr[0];
 #pragma unroll
                 for (int s = 1; s < NBUF; s++) if ((int)(seq_issue % NBUF) == s) { sa = slot_addr[s]; ba = bar_addr[s]; }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t)GSTRIDE + tbytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(sa), "l"(p.st.grid + ej * GSTRIDE), "r"((uint32_t)GSTRIDE), "r"(ba) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(sa + (uint32_t)GSTRIDE), "l"(p.st.tlist + ej * cap), "r"(tbytes), "r"(ba) : "memory");
+                if (tbytes)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(sa + (uint32_t)GSTRIDE), "l"(p.st.tlist + ej * cap), "r"(tbytes), "r"(ba) : "memory");
             }
             seq_issue++;
         };
@@ -336,7 +363,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
             while (todo) {
                 const int j = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int64_t ej = grp * GS + j;
+                const int64_t ej = env_of(j);
                 const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
                 Slot &sl = ws.slot[seq_cons % NBUF];
                 mbar_wait(&ws.bar[seq_cons % NBUF], (seq_cons / NBUF) & 1u);
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                     if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
                     __syncwarp();
                 }
-                if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
+                if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, ws.stage, lane);
                 if (ev) {
                     build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
                     const int nb = __shfl_sync(0xffffffffu, nblk, j);
@@ -371,6 +398,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
             // state was advanced by the physics launch: wrong_placement (task.py:111) is in w7
             // an all-zero difference grid (dsize == 0) scores 0 without looking: no target cell can equal 0
             const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != 0 && (every_step || w[7] != 0));
+            need_tlist = em;
             ring_start(em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u));
             ring_drain(grid_obs, em, false, true);
         } else {
@@ -383,6 +411,10 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 #pragma unroll 1
             for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once
                 if (stage == 1) {
+                    if (b_first && grid_obs) {  // the lane-local patch below must land after the row's bulk store
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        __syncwarp();
+                    }
                     run_physics();
                     if (((b_first && grid_obs) || inc_obs) && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
                     continue;
@@ -413,6 +445,8 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 if (drain) ring_drain(obs_on, em, patch, keep);
             }
         }
+
+        if (HAS_B && grid_obs && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
         // ------------------------------------------------------------- phase C
         if (valid) {
