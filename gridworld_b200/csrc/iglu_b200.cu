@@ -28,7 +28,7 @@ namespace iglu {
 #define IGLU_WARPS_PER_CTA 8
 #endif
 #ifndef IGLU_RING
-#define IGLU_RING 3
+#define IGLU_RING 4
 #endif
 constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
 constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
@@ -83,25 +83,19 @@ __device__ __forceinline__ int pack16(int a, int b) { return (a & 0xFFFF) | (b <
 __device__ __forceinline__ int lo16(int w) { return (int)(int16_t)(w & 0xFFFF); }
 __device__ __forceinline__ int hi16(int w) { return (int)(int16_t)((unsigned)w >> 16); }
 
-// Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element e0
-// of the obs array (4-byte aligned only). The 16-byte aligned body is widened into a shared-memory staging
-// buffer and written by ONE TMA bulk store (cp.async.bulk.global.shared::cta, SASS UBLKCP.G.S): plain
-// per-lane stores of 4.4 KB per env back up the SM's memory-instruction queue once HBM is saturated and
-// stall every warp's shared-memory traffic with it (measured: observation stores and reward evaluation
-// did not overlap); the bulk-copy engine drains asynchronously instead. The <= 3 head / tail elements
-// are stored by single lanes. `stage` must not be rewritten before obs_store_wait_read().
-__device__ __forceinline__ void obs_store_wait_read(int lane) {
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    __syncwarp();
-}
+// Widen one env's int8 grid (shared memory) into its int32 observation row. The row starts at element
+// e0 of the obs array (4-byte aligned only); the body is written as 16-byte streaming stores, fully
+// unrolled with all shared-memory loads first. (A variant that staged the widened row in shared memory and
+// wrote it with one TMA bulk store -- cp.async.bulk.global.shared::cta -- was measured and was not faster:
+// profiles/r01_launch_policy.txt.)
 __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, int64_t e0, const uint32_t *sg,
-                                               uint32_t *stage, int lane) {
+                                               int lane) {
     const int8_t *sg8 = reinterpret_cast<const int8_t *>(sg);
     int32_t *og = obs_grid + e0;
     const int h = (int)((4 - (e0 & 3)) & 3);  // elements before the first 16-byte boundary
-    const int nbody = (CELLS - h) >> 2;        // 271 or 272 sixteen-byte chunks
-    obs_store_wait_read(lane);                 // the previous env's bulk store has finished reading `stage`
     if (lane < h) og[lane] = (int32_t)sg8[lane];
+    const int nbody = (CELLS - h) >> 2;        // 271 or 272 sixteen-byte chunks
+    int4 *o4 = reinterpret_cast<int4 *>(og + h);
     uint32_t lo[9], hi[9];
 #pragma unroll
     for (int it = 0; it < 9; it++) {
@@ -110,7 +104,6 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         lo[it] = on ? sg[m] : 0u;
         hi[it] = on ? sg[m + 1] : 0u;
     }
-    int4 *s4 = reinterpret_cast<int4 *>(stage);
 #pragma unroll
     for (int it = 0; it < 9; it++) {
         const int m = lane + 32 * it;
@@ -123,17 +116,10 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         if (w & 0x80808080u) {                  // ... and sign-extend in the rare word that holds a negative cell
             v.x = (int)(int8_t)(w); v.y = (int)(int8_t)(w >> 8); v.z = (int)(int8_t)(w >> 16); v.w = (int)(int8_t)(w >> 24);
         }
-        if (it < 8 || m < nbody) s4[m] = v;
+        if (it < 8 || m < nbody) __stcs(o4 + m, v);
     }
     const int t0 = h + 4 * nbody;
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
-    __syncwarp();
-    if (lane == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                     ::"l"(og + h), "r"(smem_u32(stage)), "r"((uint32_t)(16 * nbody)) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
 }
 
 // PHASES selects what one launch does (same source, three instantiations):
@@ -143,10 +129,10 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
 //      registers, so it runs at 64 registers / 32 warps per SM with small (<= 32 env) chunks per warp,
 //      which is what the latency-bound per-env chain of phase B wants.
 #ifndef IGLU_OBS_WARPS
-#define IGLU_OBS_WARPS 8
+#define IGLU_OBS_WARPS 16
 #endif
 #ifndef IGLU_OBS_RING
-#define IGLU_OBS_RING 3
+#define IGLU_OBS_RING 2
 #endif
 template <int PHASES> struct StepCfg {
     static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
@@ -155,7 +141,6 @@ template <int PHASES> struct StepCfg {
 template <int NBUF> struct __align__(16) WarpScratchT {
     Slot slot[NBUF];
     EvalScratch es;
-    uint32_t stage[1092];              // one env's obs['grid'] row widened to int32, source of the TMA bulk store
     unsigned long long bar[NBUF];      // mbarriers of the ring
 };
 template <int PHASES> constexpr size_t step_smem_bytes() {
@@ -373,7 +358,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                     if (ec >= 0 && lane == 0) reinterpret_cast<int8_t *>(sl.grid)[ec] = (int8_t)evl;
                     __syncwarp();
                 }
-                if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, ws.stage, lane);
+                if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
                 if (ev) {
                     build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
                     const int nb = __shfl_sync(0xffffffffu, nblk, j);
@@ -411,10 +396,6 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 #pragma unroll 1
             for (int stage = 0; stage < 3; stage++) {  // a loop so that physics / ring code exist once
                 if (stage == 1) {
-                    if (b_first && grid_obs) {  // the lane-local patch below must land after the row's bulk store
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                        __syncwarp();
-                    }
                     run_physics();
                     if (((b_first && grid_obs) || inc_obs) && edit_cell >= 0) p.obs.grid[i * CELLS + edit_cell] = edit_val;
                     continue;
@@ -445,8 +426,6 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 if (drain) ring_drain(obs_on, em, patch, keep);
             }
         }
-
-        if (HAS_B && grid_obs && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 
         // ------------------------------------------------------------- phase C
         if (valid) {
