@@ -116,7 +116,15 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         if (w & 0x80808080u) {                  // ... and sign-extend in the rare word that holds a negative cell
             v.x = (int)(int8_t)(w); v.y = (int)(int8_t)(w >> 8); v.z = (int)(int8_t)(w >> 16); v.w = (int)(int8_t)(w >> 24);
         }
+#if defined(IGLU_OBS_ST_DEFAULT)
+        if (it < 8 || m < nbody) o4[m] = v;
+#elif defined(IGLU_OBS_ST_WT)
+        if (it < 8 || m < nbody) __stwt(o4 + m, v);
+#elif defined(IGLU_OBS_ST_CG)
+        if (it < 8 || m < nbody) __stcg(o4 + m, v);
+#else
         if (it < 8 || m < nbody) __stcs(o4 + m, v);
+#endif
     }
     const int t0 = h + 4 * nbody;
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
