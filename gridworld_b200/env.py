@@ -252,6 +252,19 @@ class Wrapper:
         return self.env.render()
 
 
+class Actions(Wrapper):
+    """reference gridworld/wrappers.py:11-32: Discrete(17) action space without 'place' (hotbar places)."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        from .spaces import Discrete
+        self.action_map = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+        self.action_space = Discrete(len(self.action_map))
+
+    def step(self, action):
+        return self.env.step(self.action_map[action])
+
+
 class SizeReward(Wrapper):
     """reference env.py:316-331. NB: in the reference GridWorld.step never updates .max_int /
     .wrong_placement, so this wrapper yields max_int-at-reset on the first step and 0 afterwards

@@ -100,6 +100,20 @@ class Task:
         _, arg = self._gpu(grid, True)
         return tuple(int(v) for v in arg[0].tolist())
 
+    def get_intersection(self, grid, dx, dz, rot):
+        """task.py:138-145: intersection of `grid` with rotation `rot` of the target shifted by (dx, dz).
+        Evaluated on the GPU as a single-shift (invariant=False) maximal_intersection of the rotated target
+        moved by (-dx, -dz); target cells that the shift pushes outside the zone are clipped as in the
+        reference's slicing."""
+        from .vec_env import max_intersection
+        tk = np.rot90(np.asarray(self.target_grid), k=-rot, axes=(1, 2))
+        moved = np.zeros_like(tk)
+        xs, xd = (slice(max(dx, 0), 11 + min(dx, 0)), slice(max(-dx, 0), 11 + min(-dx, 0)))
+        zs, zd = (slice(max(dz, 0), 11 + min(dz, 0)), slice(max(-dz, 0), 11 + min(-dz, 0)))
+        moved[:, xd, zd] = tk[:, xs, zs]
+        g = np.asarray(grid).astype(np.int8)[None]
+        return int(max_intersection(g, moved.astype(np.int8)[None], invariant=False)[0].item())
+
     def step_intersection(self, grid):
         """task.py:103-119"""
         grid = np.asarray(grid)
@@ -248,3 +262,84 @@ class RandomTasks(Tasks):
                     color = np.random.choice(self.num_colors) + 1
                 target_grid[height, block_x + ddx, block_z + ddz] = color
         return Task('', target_grid)
+
+
+class Subtasks(Tasks):
+    """Staged task where subtasks are separate segments (reference gridworld/tasks/task.py:208-308);
+    host-side task producer with the reference's interface and numpy global-RNG call order."""
+
+    def __init__(self, dialog, structure_seq, invariant=False, progressive=True):
+        self.dialog = dialog
+        self.invariant = invariant
+        self.progressive = progressive
+        self.structure_seq = structure_seq
+        self.next = None
+        self.full = False
+        self.task_start = 0
+        self.task_goal = 0
+        self.full_structure = self.to_dense(self.structure_seq[-1])
+        self.current = self.reset()
+
+    def __getattr__(self, name):
+        if name == 'current':
+            return None
+        return getattr(self.current, name)
+
+    def reset(self):
+        if self.next is None:
+            if len(self.structure_seq) == 1:
+                turn = -1
+            else:
+                turn = np.random.choice(len(self.structure_seq)) - 1
+            turn_goal = turn + 1
+        else:
+            turn = self.next
+            turn_goal = self.next + 1
+        self.task_start = turn
+        self.task_goal = turn_goal
+        self.current = self.create_task(self.task_start, self.task_goal)
+        return self.current
+
+    def __len__(self):
+        return len(self.structure_seq)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self.create_task(i - 1, i)
+
+    def __repr__(self):
+        return (f"Subtasks(total_steps={len(self.structure_seq)}, "
+                f"current_task_start={self.task_start}, current_task_end={self.task_goal})")
+
+    def create_task(self, turn_start, turn_goal):
+        dialog = ''
+        for turn in self.dialog[:turn_goal + 1]:
+            if isinstance(turn, list):
+                turn = '\n'.join(turn)
+            dialog += '\n' + turn if len(dialog) > 0 else turn
+        initial_blocks = [] if turn_start == -1 else self.structure_seq[turn_start]
+        tid = min(turn_goal, len(self.structure_seq) - 1) if not self.full else -1
+        target_grid = self.structure_seq[tid]
+        task = Task(dialog, target_grid=self.to_dense(target_grid), starting_grid=self.to_sparse(initial_blocks),
+                    full_grid=self.full_structure, last_instruction='\n'.join(self.dialog[tid]))
+        task.reset()
+        return task
+
+    def step_intersection(self, grid):
+        right_placement, wrong_placement, done = self.current.step_intersection(grid)
+        if done and len(self.structure_seq) > self.task_goal and self.progressive:
+            self.task_goal += 1
+            self.current = self.create_task(self.task_start, self.task_goal)
+            self.current.prev_grid_size = 0
+            _, _, done = self.current.step_intersection(grid)
+        return right_placement, wrong_placement, done
+
+    def set_task(self, task_id):
+        self.task_id = task_id
+        self.current = self.create_task(task_id - 1, task_id)
+        return self.current
+
+    def set_task_obj(self, task):
+        self.task_id = None
+        self.current = task
+        return self.current

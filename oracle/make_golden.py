@@ -18,6 +18,7 @@ Files written (all small, committed):
                      reward/done/grid)
   traces_flying.npz  flying Dict traces (float32 actions, widened to fp64 for the reference)
   traces_dict.npz    walking Dict (discretize=False) traces
+  misc.npz           Task.get_intersection and Subtasks (reset / progressive step_intersection) known answers
 """
 import os
 import pickle
@@ -465,12 +466,60 @@ def gen_dict(gym, Task):
     np.savez_compressed(os.path.join(OUT, 'traces_dict.npz'), **out)
 
 
+def gen_misc(Task, Tasks):
+    """get_intersection / Subtasks (reference tasks/task.py:138-145, 208-308) known answers."""
+    from gridworld.tasks.task import Subtasks
+    rng = np.random.RandomState(21)
+    out = {}
+    # get_intersection on admissible and non-admissible (clipping) shifts
+    T = synth_target(rng, 0.2, 'compact')
+    task = Task('', T.astype(np.int32))
+    G = related_grid(rng, task, T)
+    q = [(dx, dz, r) for r in range(4) for dx in (-4, -1, 0, 2, 5) for dz in (-3, 0, 1, 6)]
+    out['gi_target'], out['gi_grid'] = T, G
+    out['gi_query'] = np.array(q, np.int32)
+    out['gi_value'] = np.array([task.get_intersection(G.astype(np.int32), dx, dz, r) for dx, dz, r in q], np.int32)
+    # Subtasks: three stages, progressive goals
+    seq = [[(0, -1, 0, 1), (1, -1, 0, 1)],
+           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2)],
+           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2), (1, 1, 0, 3), (-2, -1, 3, 4)]]
+    dialog = ['<A> build a base', '<A> put a green one on top', ['<A> finish it', '<B> ok']]
+    np.random.seed(5)
+    st = Subtasks(dialog, seq, invariant=False, progressive=True)
+    rec = []
+    for ep in range(6):
+        cur = st.reset()
+        rec.append((st.task_start, st.task_goal, np.asarray(cur.target_grid).astype(np.int8),
+                    np.asarray(Tasks.to_dense(cur.starting_grid)).astype(np.int8), cur.max_int, cur.target_size,
+                    cur.chat))
+    out['st_start'] = np.array([r[0] for r in rec], np.int32)
+    out['st_goal'] = np.array([r[1] for r in rec], np.int32)
+    out['st_target'] = np.array([r[2] for r in rec])
+    out['st_init'] = np.array([r[3] for r in rec])
+    out['st_max_int'] = np.array([r[4] for r in rec], np.int32)
+    out['st_target_size'] = np.array([r[5] for r in rec], np.int32)
+    out['st_chat'] = np.array([r[6] for r in rec])
+    # progressive step_intersection: feed the grids of the successive stages
+    np.random.seed(7)
+    st = Subtasks(dialog, seq, invariant=False, progressive=True)
+    st.next = -1  # start from the empty world
+    st.reset()
+    steps = []
+    for blocks in seq:
+        g = np.asarray(Tasks.to_dense(blocks)).astype(np.int32)
+        r, w, d = st.step_intersection(g)
+        steps.append((r, w, int(d), st.task_goal))
+    out['st_steps'] = np.array(steps, np.int32)
+    np.savez_compressed(os.path.join(OUT, 'misc.npz'), **out)
+    print('misc.npz', out['gi_value'][:8], out['st_start'], out['st_goal'], out['st_steps'].tolist())
+
+
 def main():
     load_reference.load()
     import gym
     from gridworld.tasks import Task, Tasks
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict']
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc']
     if 'goals' in which:
         gen_goals(Task, Tasks)
     if 'pairs' in which:
@@ -481,6 +530,8 @@ def main():
         gen_flying(gym, Task)
     if 'dict' in which:
         gen_dict(gym, Task)
+    if 'misc' in which:
+        gen_misc(Task, Tasks)
 
 
 if __name__ == '__main__':

@@ -404,3 +404,38 @@ def test_dropin_gym_surface():
     obs, r, done, _ = fenv.step({'movement': np.array([1, 0, 0], np.float32), 'camera': np.zeros(2, np.float32),
                                  'inventory': 0, 'placement': 0})
     assert abs(fenv.agent.position[2] - 0.75) < 1e-12  # strafe[0] > 0 moves +z at 15 units/s
+
+
+def test_get_intersection_and_subtasks_golden():
+    """'next' rows: Task.get_intersection and the staged Subtasks producer against the reference's outputs."""
+    import gridworld_b200 as gw
+    z = G.load('misc.npz')
+    task = gw.Task('', z['gi_target'].astype(np.int32))
+    got = [task.get_intersection(z['gi_grid'], int(dx), int(dz), int(r)) for dx, dz, r in z['gi_query']]
+    assert got == z['gi_value'].tolist()
+    seq = [[(0, -1, 0, 1), (1, -1, 0, 1)],
+           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2)],
+           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2), (1, 1, 0, 3), (-2, -1, 3, 4)]]
+    dialog = ['<A> build a base', '<A> put a green one on top', ['<A> finish it', '<B> ok']]
+    np.random.seed(5)
+    st = gw.Subtasks(dialog, seq, invariant=False, progressive=True)
+    for ep in range(6):
+        cur = st.reset()
+        assert (st.task_start, st.task_goal) == (z['st_start'][ep], z['st_goal'][ep])
+        assert np.array_equal(np.asarray(cur.target_grid), z['st_target'][ep])
+        assert np.array_equal(np.asarray(gw.Tasks.to_dense(cur.starting_grid)), z['st_init'][ep])
+        assert cur.max_int == z['st_max_int'][ep] and cur.target_size == z['st_target_size'][ep]
+        assert cur.chat == str(z['st_chat'][ep])
+    np.random.seed(7)
+    st = gw.Subtasks(dialog, seq, invariant=False, progressive=True)
+    st.next = -1
+    st.reset()
+    for k, blocks in enumerate(seq):
+        r, w, d = st.step_intersection(np.asarray(gw.Tasks.to_dense(blocks)))
+        assert [r, w, int(d), st.task_goal] == z['st_steps'][k].tolist()
+    # Actions wrapper (wrappers.py:11-32): 17 actions, 'place' removed
+    env = gw.Actions(gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False))
+    assert env.action_space.n == 17
+    env.set_task(gw.Task('', gw.Tasks.to_dense([(0, -1, -2, 1)]), starting_grid=[]))
+    obs, r, done, _ = env.step(16)
+    assert r == 0 and not done
