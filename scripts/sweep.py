@@ -110,6 +110,19 @@ def reward_only(n, support, rho, reps=5):
             'hbm_bytes_per_eval': 2 * 1089 + 4, 'hbm_gbs': evals * (2 * 1089 + 4) / 1e9, 'int_peaks': pk}
 
 
+def goals_tiled(n, reward_mode, K=200):
+    """The 156 real goal structures of skills/goals.pkl (tests/golden/goals.npz) tiled over n envs."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    T = torch.as_tensor(np.load(os.path.join(root, 'tests', 'golden', 'goals.npz'))['targets'])
+    T = T[torch.arange(n) % T.shape[0]].cuda()
+    env = gw.make_vec(n, action_space='walking', max_steps=250, reward_mode=reward_mode)
+    env.set_tasks(T)
+    acts = torch.randint(0, 18, (64, n), device='cuda', dtype=torch.int32)
+    ms = time_steps(env, lambda t: env.step(acts[t % 64]), K=K)
+    return {'kind': 'walking, goals.pkl targets tiled', 'envs': n, 'reward_mode': reward_mode, 'ms_per_step': ms,
+            'env_steps_per_sec': n / ms * 1e3}
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'one':  # one: <reward_mode> <inplace 0/1> <envs> [steps]
         K = int(sys.argv[5]) if len(sys.argv) > 5 else 30
@@ -123,6 +136,9 @@ if __name__ == '__main__':
         print(json.dumps(walking(65536, 'full', 0.2, 'every_step', False)), flush=True)
         print(json.dumps(walking(1048576, 'compact', 0.2, 'on_change', True, K=50)), flush=True)
         print(json.dumps(walking(1048576, 'compact', 0.2, 'every_step', False, K=30)), flush=True)
+    if 'goals' in which:
+        for rm in ('every_step', 'on_change'):
+            print(json.dumps(goals_tiled(65536, rm)), flush=True)
     if 'flying' in which:
         print(json.dumps(flying(262144)), flush=True)
     if 'reward' in which:
