@@ -37,9 +37,16 @@ class Obs(C.Structure):
                 ('done', C.c_void_p)]
 
 
+class TaskPool(C.Structure):
+    _fields_ = [('m', C.c_int64), ('target', C.c_void_p), ('init', C.c_void_p), ('tlist', C.c_void_p),
+                ('tmeta', C.c_void_p), ('cursor', C.c_void_p), ('next_task', C.c_void_p),
+                ('seed', C.c_uint64), ('env_offset', C.c_int64)]
+
+
 EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_destroy', 'iglu_set_tasks',
            'iglu_reset', 'iglu_step_walking', 'iglu_step_flying', 'iglu_step_walking_dict',
-           'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count')
+           'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
+           'iglu_task_pool_prepare', 'iglu_task_pool_attach')
 
 _lib = None
 
@@ -72,6 +79,8 @@ def load():
     L.iglu_step_walking_host.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp, vp, vp]
     L.iglu_max_intersection.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp]
     L.iglu_last_launch_count.argtypes = [vp]
+    L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]
+    L.iglu_task_pool_attach.argtypes = [vp, C.POINTER(TaskPool)]
     if L.iglu_abi_version() != 1:
         raise RuntimeError('libiglu_b200.so ABI version mismatch')
     _lib = L

@@ -54,6 +54,7 @@ struct StepParams {
     const int32_t *inventory;  // flying [n]
     const int32_t *placement;  // flying [n]
     const int32_t *buttons;    // walking dict [n][8]
+    iglu_task_pool pool;       // device-resident task generator (m == 0: none)
     int group;                 // envs per warp: 32, or 16 when there are too few envs to fill the SMs
 };
 
@@ -130,6 +131,55 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
 }
 
+// ---- device-resident task generator (include/iglu_b200.h iglu_task_pool) ---------------------------
+// Uniform draw of a pool index for the k-th episode of (global) env `env`: splitmix64 finaliser of a
+// per-(env, episode) counter, mapped to [0, m) by multiply-shift. Stateless, so shards reproduce it.
+__device__ __forceinline__ int pool_draw(uint64_t seed, int64_t env, uint32_t episode, int64_t m) {
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(env + 1) + 0xD1B54A32D192ED03ull * (uint64_t)episode;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (int)(((x >> 32) * (uint64_t)m) >> 32);
+}
+
+// Per-env part of a draw (one thread): choose the index, advance the cursor, copy the tmeta column.
+// Returns the pool index.
+__device__ __noinline__ int pool_next(const iglu_task_pool &pool, int32_t *__restrict__ tmeta, int64_t n, int64_t i) {
+    const int64_t m = pool.m;
+    const int ep = pool.cursor[n + i];
+    int j = -1;
+    if (pool.next_task) {
+        const int nt = pool.next_task[i];
+        if (nt >= 0 && nt < m) { j = nt; pool.next_task[i] = -1; }
+    }
+    if (j < 0) j = pool_draw(pool.seed, pool.env_offset + i, (uint32_t)ep, m);
+    pool.cursor[i] = j;
+    pool.cursor[n + i] = ep + 1;
+#pragma unroll
+    for (int c = 0; c < 6; c++) tmeta[c * n + i] = pool.tmeta[c * m + j];
+    tmeta[6 * n + i] = 1;
+    return j;
+}
+
+// Warp-cooperative part: pool row j -> the env's own target / init / tlist rows (+ obs['target_grid']).
+__device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int j, int nblk, int8_t *__restrict__ target,
+                                        int8_t *__restrict__ init, uint16_t *__restrict__ tlist,
+                                        int32_t *__restrict__ target_obs, int lane) {
+    const int4 *st = reinterpret_cast<const int4 *>(pool.target + (int64_t)j * GSTRIDE);
+    const int4 *si = reinterpret_cast<const int4 *>(pool.init + (int64_t)j * GSTRIDE);
+    const int4 *sl = reinterpret_cast<const int4 *>(pool.tlist + (int64_t)j * cap);
+    for (int q = lane; q < GSTRIDE / 16; q += 32) {
+        reinterpret_cast<int4 *>(target)[q] = st[q];
+        reinterpret_cast<int4 *>(init)[q] = si[q];
+    }
+    const int nl = (2 * (TL_HDR + nblk) + 15) >> 4;
+    for (int q = lane; q < nl; q += 32) reinterpret_cast<int4 *>(tlist)[q] = sl[q];
+    if (target_obs) {
+        const int8_t *t8 = pool.target + (int64_t)j * GSTRIDE;
+        for (int c = lane; c < CELLS; c += 32) target_obs[c] = (int32_t)t8[c];
+    }
+}
+
 // PHASES selects what one launch does (same source, three instantiations):
 //   3  fused:        phase A (physics) + B (observation / reward) + C (bookkeeping) -- one launch per step
 //   1  physics only: phase A; leaves wrong_placement in istate w7 for the second launch
@@ -156,7 +206,7 @@ template <int PHASES> constexpr size_t step_smem_bytes() {
 }
 
 template <int KIND, int PHASES>
-__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : CTAS_PER_SM) k_step(const StepParams p) {
+__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : CTAS_PER_SM) k_step(const __grid_constant__ StepParams p) {
     constexpr int WPC = StepCfg<PHASES>::WPC;
     constexpr int NBUF = StepCfg<PHASES>::NBUF;
     constexpr bool HAS_A = PHASES != 2, HAS_B = PHASES != 1;
@@ -211,8 +261,6 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
         for (int c = 0; c < 8; c++) w[c] = p.st.istate[c * n + ii];
 #pragma unroll
         for (int c = 0; c < 6; c++) tm[c] = p.st.tmeta[c * n + ii];
-        const int nblk = tm[0], target_size = tm[1];
-        const bool has_start = tm[5] != 0;
         Agent a;
         if (HAS_A) {
             a.x = p.st.pose[0 * n + ii]; a.y = p.st.pose[1 * n + ii]; a.z = p.st.pose[2 * n + ii];
@@ -225,6 +273,14 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 
         // auto-reset (env.py:206-261): grid <- starting grid, cooperatively, 16 bytes per lane
         const bool do_reset = HAS_A && valid && p.cfg.auto_reset && done_prev;
+        int pool_j = -1;  // task generator: the reset first draws the env's next task (env.py:213-216)
+        if (HAS_A && p.pool.m > 0 && do_reset) {
+            pool_j = pool_next(p.pool, p.st.tmeta, n, i);
+#pragma unroll
+            for (int c = 0; c < 6; c++) tm[c] = p.pool.tmeta[c * p.pool.m + pool_j];
+        }
+        const int nblk = tm[0], target_size = tm[1];
+        const bool has_start = tm[5] != 0;
         if (HAS_A) {
             unsigned rm = __ballot_sync(0xffffffffu, do_reset);
             if (rm) {
@@ -233,13 +289,19 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                     rm &= rm - 1;
                     const int64_t ej = env_of(j);
                     const bool hs = __shfl_sync(0xffffffffu, (int)has_start, j) != 0;
-                    int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
-                    const int4 *src = reinterpret_cast<const int4 *>(p.st.init + ej * GSTRIDE);
-                    for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
-                    if (inc_obs) {  // incremental observation: a reset rewrites the whole row
-                        const int8_t *si = p.st.init + ej * GSTRIDE;
-                        for (int c = lane; c < CELLS; c += 32) p.obs.grid[ej * CELLS + c] = hs ? (int32_t)si[c] : 0;
+                    const int pj = __shfl_sync(0xffffffffu, pool_j, j);
+                    const int8_t *si = p.st.init + ej * GSTRIDE;
+                    if (pj >= 0) {
+                        pool_fetch(p.pool, cap, pj, __shfl_sync(0xffffffffu, nblk, j), p.st.target + ej * GSTRIDE,
+                                   p.st.init + ej * GSTRIDE, p.st.tlist + ej * cap,
+                                   p.obs.target_grid ? p.obs.target_grid + ej * CELLS : nullptr, lane);
+                        si = p.pool.init + (int64_t)pj * GSTRIDE;
                     }
+                    int4 *dst = reinterpret_cast<int4 *>(p.st.grid + ej * GSTRIDE);
+                    const int4 *src = reinterpret_cast<const int4 *>(si);
+                    for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = hs ? src[q] : make_int4(0, 0, 0, 0);
+                    if (inc_obs)  // incremental observation: a reset rewrites the whole row
+                        for (int c = lane; c < CELLS; c += 32) p.obs.grid[ej * CELLS + c] = hs ? (int32_t)si[c] : 0;
                 }
                 if (HAS_B) {  // the TMA reads below go through the async proxy: order them after these writes
                     __threadfence();
@@ -520,20 +582,28 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
         st.tmeta[5 * n + e] = any_start;
         st.tmeta[6 * n + e] = 1;
         st.tmeta[7 * n + e] = 0;
-#pragma unroll
-        for (int k = 0; k < 5; k++) st.init_pose[k * n + e] = init_pose ? init_pose[row * 5 + k] : 0.0;
+        if (st.init_pose)
+            for (int k = 0; k < 5; k++) st.init_pose[k * n + e] = init_pose ? init_pose[row * 5 + k] : 0.0;
     }
 }
 
 // ------------------------------------------------------------------ reset
 // GridWorld.reset (env.py:206-261). One warp per env.
 __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, const uint8_t *__restrict__ mask,
-                                               int hard) {
+                                               int hard, const __grid_constant__ iglu_task_pool pool, int cap) {
     const int lane = threadIdx.x & 31;
     const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n = st.n;
     if (e >= n) return;
     if (mask && !mask[e]) return;
+    if (pool.m > 0) {  // task generator: draw the next task first (env.py:213-216)
+        int j = 0;
+        if (lane == 0) j = pool_next(pool, st.tmeta, n, e);
+        j = __shfl_sync(0xffffffffu, j, 0);
+        pool_fetch(pool, cap, j, pool.tmeta[j], st.target + e * GSTRIDE, st.init + e * GSTRIDE,
+                   st.tlist + e * cap, obs.target_grid ? obs.target_grid + e * CELLS : nullptr, lane);
+        __syncwarp();
+    }
     const int4 *src = reinterpret_cast<const int4 *>(st.init + e * GSTRIDE);
     int4 *dst = reinterpret_cast<int4 *>(st.grid + e * GSTRIDE);
     for (int q = lane; q < GSTRIDE / 16; q += 32) dst[q] = src[q];
@@ -704,6 +774,7 @@ struct iglu_ctx {
     int device;
     int num_sms;
     int last_launches;
+    iglu_task_pool pool;  // copy of the attached generator (m == 0: none)
 };
 
 static int check(cudaError_t e) { return e == cudaSuccess ? IGLU_OK : IGLU_ERR_CUDA; }
@@ -731,6 +802,7 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     iglu_ctx *c = new iglu_ctx();
     c->cfg = *cfg;
     c->last_launches = 0;
+    memset(&c->pool, 0, sizeof(c->pool));
     if (cudaGetDevice(&c->device) != cudaSuccess) { delete c; return IGLU_ERR_CUDA; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { delete c; return IGLU_ERR_CUDA; }
@@ -788,12 +860,44 @@ extern "C" int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_ob
     return check(cudaPeekAtLastError());
 }
 
+static bool pool_ok(const iglu_task_pool *pool) {
+    return pool && pool->m > 0 && pool->m < (int64_t)1 << 31 && pool->target && pool->init && pool->tlist &&
+           pool->tmeta && pool->cursor;
+}
+
+extern "C" int iglu_task_pool_prepare(iglu_ctx *ctx, const iglu_task_pool *pool, const int8_t *target,
+                                      const int8_t *start, void *stream) {
+    if (!ctx || !pool_ok(pool) || !target) return IGLU_ERR_INVALID_ARG;
+    // the pool arrays have the layout of a state with n = m: Task.__init__ per row with the same kernel
+    iglu_state st;
+    iglu_obs obs;
+    memset(&st, 0, sizeof(st));
+    memset(&obs, 0, sizeof(obs));
+    st.n = pool->m;
+    st.target = pool->target; st.init = pool->init; st.tlist = pool->tlist; st.tmeta = pool->tmeta;
+    const int threads = 256;
+    const int64_t blocks = (pool->m * 32 + threads - 1) / threads;
+    k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(st, obs, ctx->cfg, target, start, nullptr,
+                                                                         nullptr, pool->m);
+    ctx->last_launches = 1;
+    return check(cudaPeekAtLastError());
+}
+
+extern "C" int iglu_task_pool_attach(iglu_ctx *ctx, const iglu_task_pool *pool) {
+    if (!ctx) return IGLU_ERR_INVALID_ARG;
+    if (!pool) { memset(&ctx->pool, 0, sizeof(ctx->pool)); return IGLU_OK; }
+    if (!pool_ok(pool)) return IGLU_ERR_INVALID_ARG;
+    ctx->pool = *pool;
+    return IGLU_OK;
+}
+
 extern "C" int iglu_reset(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const uint8_t *mask,
                           int hard, void *stream) {
     if (!ctx || !state_ok(st, obs)) return IGLU_ERR_INVALID_ARG;
     const int threads = 256;
     const int64_t blocks = (st->n * 32 + threads - 1) / threads;
-    k_reset<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*st, *obs, mask, hard);
+    k_reset<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*st, *obs, mask, hard, ctx->pool,
+                                                                     ctx->cfg.tlist_cap);
     ctx->last_launches = 1;
     return check(cudaPeekAtLastError());
 }
@@ -852,7 +956,7 @@ extern "C" int iglu_step_walking(iglu_ctx *ctx, const iglu_state *st, const int3
     if (ctx->cfg.action_space != IGLU_WALKING_DISCRETE) return IGLU_ERR_INVALID_ARG;
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.actions = actions;
+    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.pool = ctx->pool; p.actions = actions;
     return launch_step<IGLU_WALKING_DISCRETE>(ctx, p, stream);
 }
 
@@ -863,7 +967,7 @@ extern "C" int iglu_step_flying(iglu_ctx *ctx, const iglu_state *st, const float
     if (ctx->cfg.action_space != IGLU_FLYING) return IGLU_ERR_INVALID_ARG;
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg;
+    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.pool = ctx->pool;
     p.movement = movement; p.camera = camera; p.inventory = inventory; p.placement = placement;
     return launch_step<IGLU_FLYING>(ctx, p, stream);
 }
@@ -874,7 +978,7 @@ extern "C" int iglu_step_walking_dict(iglu_ctx *ctx, const iglu_state *st, const
     if (ctx->cfg.action_space != IGLU_WALKING_DICT) return IGLU_ERR_INVALID_ARG;
     StepParams p;
     memset(&p, 0, sizeof(p));
-    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.buttons = buttons; p.camera = camera;
+    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.pool = ctx->pool; p.buttons = buttons; p.camera = camera;
     return launch_step<IGLU_WALKING_DICT>(ctx, p, stream);
 }
 

@@ -113,6 +113,7 @@ class IGLUVecEnv:
         self._kind = kind
         self._L = _lib.load()
         self._tasks_set = False
+        self._pool = None
 
         dev = self.device
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -216,6 +217,62 @@ class IGLUVecEnv:
                 mask[idx.long()] = 1
             return self.reset(mask)
         return None
+
+    def set_task_pool(self, targets, starts=None, seed=0, env_offset=0, next_task=None, reset=True):
+        """Batched env.set_task_generator (reference env.py:166-172) with a device-resident generator.
+
+        The generator is a finite pool of tasks drawn uniformly at every reset, i.e. what
+        RandomTasks(max_cache=m).reset (task_set.py:120-127) or any Tasks-like object enumerated into
+        arrays does -- but the draw, the Task.__init__ products and the copy into the env happen on the
+        device inside reset / the auto-reset of step, so the host is not on the reset path.
+
+        targets : int8 [m, 9, 11, 11]; starts : int8 [m, 9, 11, 11] or None
+        seed, env_offset : the counter-based draw is a function of (seed, env_offset + env, episode number)
+                           (include/iglu_b200.h), so shards of one job reproduce the single-device sequence
+        next_task : optional int32 [num_envs] device tensor; an entry 0 <= j < m is used instead of the draw
+                    at that env's next reset and then set to -1 (e.g. to replay a reference generator's choices)
+        Pass targets=None to detach the generator.
+        """
+        if targets is None:
+            with self._guard():
+                _lib.check(self._L.iglu_task_pool_attach(self._ctx, None))
+            self._pool = None
+            return None
+        t = torch.as_tensor(targets)
+        m = t.shape[0]
+        t = self._dev(t, torch.int8, (m, _lib.CELLS))
+        s = None if starts is None else self._dev(starts, torch.int8, (m, _lib.CELLS))
+        dev = self.device
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        bufs = dict(target=z(m, _lib.GRID_STRIDE, dtype=torch.int8), init=z(m, _lib.GRID_STRIDE, dtype=torch.int8),
+                    tlist=z(m, self._tlist.shape[1], dtype=torch.int16), tmeta=z(8, m, dtype=torch.int32),
+                    cursor=z(2, self.num_envs, dtype=torch.int32))
+        bufs['cursor'][0] = -1
+        if next_task is not None:
+            if not (isinstance(next_task, torch.Tensor) and next_task.dtype == torch.int32 and next_task.device == dev
+                    and next_task.is_contiguous() and tuple(next_task.shape) == (self.num_envs,)):
+                raise ValueError('next_task must be a contiguous int32 device tensor of shape [num_envs]')
+            bufs['next_task'] = next_task
+        pool = _lib.TaskPool(m, bufs['target'].data_ptr(), bufs['init'].data_ptr(), bufs['tlist'].data_ptr(),
+                             bufs['tmeta'].data_ptr(), bufs['cursor'].data_ptr(),
+                             None if next_task is None else next_task.data_ptr(), int(seed) & (2 ** 64 - 1),
+                             int(env_offset))
+        with self._guard():
+            _lib.check(self._L.iglu_task_pool_prepare(self._ctx, C.byref(pool), t.data_ptr(),
+                                                      None if s is None else s.data_ptr(), self._stream()))
+            self._count()
+            _lib.check(self._L.iglu_task_pool_attach(self._ctx, C.byref(pool)))
+        self._pool = bufs  # the ctx retains these device pointers: keep the tensors alive
+        self._tasks_set = True
+        return self.reset() if reset else None
+
+    @property
+    def task_ids(self):
+        """int32 [num_envs]: pool index of each env's current task (-1 before its first draw); the host
+        side of obs['dialog'] (task.chat) is looked up with it."""
+        if getattr(self, '_pool', None) is None:
+            raise ValueError('no task pool attached')
+        return self._pool['cursor'][0]
 
     def _check_task(self):
         if not self._tasks_set:
@@ -372,11 +429,19 @@ class IGLUVecEnv:
 
     def state_dict(self):
         keys = ('_grid', '_init', '_target', '_pose', '_init_pose', '_istate', '_tlist', '_tmeta')
-        return {k[1:]: getattr(self, k).clone() for k in keys}
+        sd = {k[1:]: getattr(self, k).clone() for k in keys}
+        if self._pool is not None:  # the generator's per-env position (the pool itself is set_task_pool's input)
+            sd['pool_cursor'] = self._pool['cursor'].clone()
+        return sd
 
     def load_state_dict(self, sd):
         for k, v in sd.items():
-            getattr(self, '_' + k).copy_(v)
+            if k == 'pool_cursor':
+                if self._pool is None:
+                    raise ValueError('state has a task-pool cursor: call set_task_pool(..., reset=False) first')
+                self._pool['cursor'].copy_(v)
+            else:
+                getattr(self, '_' + k).copy_(v)
         self._tasks_set = True
 
 

@@ -95,8 +95,10 @@ typedef struct iglu_state {
                                   w4: step_no; w5: nnz(grid - init) (task.prev_grid_size); w6: max_int;
                                   w7: wrong_placement of the last physics launch (task.py:111) */
     uint16_t *tlist;   /* [n][tlist_cap]  row = 16-byte header + block list of the synthetic task.
-                                  header: 16 int8, per rotation r: dx_lo, dx_hi, dz_lo, dz_hi of the admissible
-                                  shifts (task.py:57-72; always a rectangle);
+                                  header: 16 bytes, per rotation r: dx_lo (int8), number of dx values (bits 0-4),
+                                  dz_lo (int8), number of dz values -- the admissible shifts (task.py:57-72;
+                                  always a rectangle); bits 5-6 of byte 1 of rotation 0 hold the
+                                  evaluation's lane-mapping shift (written by the library, opaque to callers);
                                   then the non-zero cells of (target - init), rotation 0, ascending cell index:
                                   y | x<<4 | z<<8 | (value & 15)<<12 */
     int32_t *tmeta;    /* [8][n]  w0: number of tlist entries; w1: target_size (task.py:35);
@@ -136,6 +138,42 @@ void iglu_ctx_destroy(iglu_ctx *ctx);
 int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, const int8_t *target,
                    const int8_t *start, const double *init_pose, const int32_t *env_idx, int64_t count,
                    void *stream);
+
+/* Device-resident task generator (reference: GridWorld.set_task_generator env.py:166-172 and the
+ * `self._task = self._task_generator.reset()` of GridWorld.reset env.py:213-216; the generator modelled is a
+ * finite set of tasks drawn uniformly, i.e. RandomTasks(max_cache=m).reset task_set.py:120-127 or any
+ * Tasks-like object whose tasks were enumerated into the pool). While a pool is attached, every reset of an
+ * env -- iglu_reset and the auto-reset inside the step calls -- first draws a pool index j and copies
+ * pool row j into the env's own target/init/tlist/tmeta rows (+ obs.target_grid), then resets as usual,
+ * with no host involvement. The draw of env e for its k-th episode (k = cursor[1][e], then incremented) is
+ *     x = seed + 0x9E3779B97F4A7C15 * (env_offset + e + 1) + 0xD1B54A32D192ED03 * k     (mod 2^64)
+ *     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9; x ^= x >> 27; x *= 0x94D049BB133111EB; x ^= x >> 31
+ *     j = ((x >> 32) * m) >> 32
+ * (the reference draws from numpy's global Mersenne Twister, which is neither per-env nor reproducible
+ * across shards; env_offset makes sharded runs reproduce the single-device sequence). If next_task is not
+ * NULL and 0 <= next_task[e] < m, that index is used instead and next_task[e] is set to -1 (consumed):
+ * a caller can impose the exact sequence a reference generator produced. */
+typedef struct iglu_task_pool {
+    int64_t m;          /* tasks in the pool (0 = no pool) */
+    int8_t *target;     /* [m][IGLU_GRID_STRIDE] */
+    int8_t *init;       /* [m][IGLU_GRID_STRIDE]  dense starting grids */
+    uint16_t *tlist;    /* [m][tlist_cap]         same row format as iglu_state.tlist */
+    int32_t *tmeta;     /* [8][m]                 same words as iglu_state.tmeta */
+    int32_t *cursor;    /* [2][n] per env: pool index of the current task (-1 before the first draw),
+                                  number of draws so far */
+    int32_t *next_task; /* [n] or NULL */
+    uint64_t seed;
+    int64_t env_offset; /* global index of env 0 of this shard */
+} iglu_task_pool;
+
+/* Task.__init__ of the synthetic task (env.py:227-232, task.py:9-72) for every pool entry:
+ * target, start device int8 [m][1089] dense (start may be NULL) -> pool->target/init/tlist/tmeta. */
+int iglu_task_pool_prepare(iglu_ctx *ctx, const iglu_task_pool *pool, const int8_t *target, const int8_t *start,
+                           void *stream);
+
+/* Attach (pool != NULL, m > 0) or detach (NULL) the generator. The ctx keeps a COPY of the struct, i.e. it
+ * retains the device pointers until detached or destroyed; the caller keeps the buffers alive. */
+int iglu_task_pool_attach(iglu_ctx *ctx, const iglu_task_pool *pool);
 
 /* GridWorld.reset (env.py:206-261) for the envs with mask[i] != 0 (mask NULL = all): grid <- start,
  * pose <- initial pose, inventory, step_no, task bookkeeping; writes the reset observation

@@ -74,6 +74,14 @@ typedef struct {
     int flying, select_and_place, max_steps;
     double right_scale, wrong_scale;
     orc_env *e;
+    /* task generator (env.py:166-172, 213-216): a finite pool drawn at every reset */
+    int64_t pool_m;
+    int8_t *pool_target, *pool_start; /* [m][CELLS] (pool_start may be NULL) */
+    uint64_t pool_seed;
+    int64_t pool_off;
+    int32_t *next_task; /* [n] imposed index for the next reset, -1 = draw */
+    int32_t *task_id;   /* [n] current pool index */
+    int32_t *episode;   /* [n] draws so far */
 } orc_batch;
 
 static double JUMP_SPEED; /* utils.py:21 sqrt(2*GRAVITY*MAX_JUMP_HEIGHT) */
@@ -442,6 +450,42 @@ static void env_reset(orc_env *e) {
     /* NOT reset (reference quirk): dy, time_int_steps, active_block, strafe */
 }
 
+/* env.set_task (env.py:155-165): store target / starting grid, build the synthetic task (env.py:227-232). */
+static void env_assign_task(orc_env *e, const int8_t *target, const int8_t *start) {
+    int32_t diff[CELLS];
+    for (int k = 0; k < CELLS; k++) {
+        e->target[k] = target[k];
+        e->init[k] = start ? start[k] : 0;
+        diff[k] = e->target[k] - e->init[k]; /* always invariant, no full_grid */
+    }
+    orc_task_init(&e->syn, diff, NULL, 1);
+}
+
+/* The batched build's generator draw (include/iglu_b200.h iglu_task_pool). The reference draws with
+ * np.random.choice from numpy's global stream (task_set.py:120-127), which has no batched meaning; the
+ * draw is therefore part of the new interface and is restated here from its published formula only. */
+static int64_t pool_draw(uint64_t seed, int64_t env, uint32_t episode, int64_t m) {
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(env + 1) + 0xD1B54A32D192ED03ull * (uint64_t)episode;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (int64_t)(((x >> 32) * (uint64_t)m) >> 32);
+}
+
+/* GridWorld.reset with a task generator: `self._task = self._task_generator.reset()` first (env.py:213-216) */
+static void batch_reset_env(orc_batch *b, int64_t i) {
+    orc_env *e = &b->e[i];
+    if (b->pool_m > 0) {
+        int64_t j = -1;
+        if (b->next_task[i] >= 0 && b->next_task[i] < b->pool_m) { j = b->next_task[i]; b->next_task[i] = -1; }
+        if (j < 0) j = pool_draw(b->pool_seed, b->pool_off + i, (uint32_t)b->episode[i], b->pool_m);
+        b->task_id[i] = (int32_t)j;
+        b->episode[i] += 1;
+        env_assign_task(e, b->pool_target + j * CELLS, b->pool_start ? b->pool_start + j * CELLS : NULL);
+    }
+    env_reset(e);
+}
+
 /* env.py:268-303 GridWorld.step for one env with an already parsed action */
 static void env_step(const orc_batch *b, orc_env *e, orc_action *a, double *reward, uint8_t *done) {
     e->step_no += 1;
@@ -506,6 +550,8 @@ orc_batch *orc_create(int n, int flying, int select_and_place, int max_steps, do
 
 void orc_destroy(orc_batch *b) {
     if (!b) return;
+    free(b->pool_target); free(b->pool_start);
+    free(b->next_task); free(b->task_id); free(b->episode);
     free(b->e);
     free(b);
 }
@@ -515,20 +561,39 @@ void orc_destroy(orc_batch *b) {
  * pose = (x, y, z, yaw, pitch) or NULL for the default (0,0,0,0,0). */
 void orc_set_task(orc_batch *b, int i, const int8_t *target, const int8_t *start, const double *pose) {
     orc_env *e = &b->e[i];
-    int32_t diff[CELLS];
-    for (int k = 0; k < CELLS; k++) {
-        e->target[k] = target[k];
-        e->init[k] = start ? start[k] : 0;
-        diff[k] = e->target[k] - e->init[k]; /* env.py:227-231 (always invariant, no full_grid) */
-    }
-    orc_task_init(&e->syn, diff, NULL, 1);
+    env_assign_task(e, target, start);
     for (int k = 0; k < 5; k++) e->init_pose[k] = pose ? pose[k] : 0.0;
     env_reset(e);
 }
 
+/* env.set_task_generator (env.py:166-172) with a pool of m tasks; does not reset. */
+void orc_set_pool(orc_batch *b, const int8_t *targets, const int8_t *starts, int64_t m, uint64_t seed,
+                  int64_t env_offset) {
+    free(b->pool_target); free(b->pool_start);
+    b->pool_target = (int8_t *)malloc((size_t)m * CELLS);
+    memcpy(b->pool_target, targets, (size_t)m * CELLS);
+    b->pool_start = NULL;
+    if (starts) {
+        b->pool_start = (int8_t *)malloc((size_t)m * CELLS);
+        memcpy(b->pool_start, starts, (size_t)m * CELLS);
+    }
+    b->pool_m = m; b->pool_seed = seed; b->pool_off = env_offset;
+    if (!b->next_task) {
+        b->next_task = (int32_t *)malloc(sizeof(int32_t) * (size_t)b->n);
+        b->task_id = (int32_t *)malloc(sizeof(int32_t) * (size_t)b->n);
+        b->episode = (int32_t *)calloc((size_t)b->n, sizeof(int32_t));
+    }
+    for (int i = 0; i < b->n; i++) { b->next_task[i] = -1; b->task_id[i] = -1; b->episode[i] = 0; }
+}
+int32_t *orc_pool_next_task(orc_batch *b) { return b->next_task; }
+int32_t *orc_pool_task_id(orc_batch *b) { return b->task_id; }
+void orc_get_target(const orc_batch *b, int32_t *target) {
+    for (int i = 0; i < b->n; i++) memcpy(target + (size_t)i * CELLS, b->e[i].target, sizeof(int32_t) * CELLS);
+}
+
 void orc_reset(orc_batch *b, const uint8_t *mask) {
     for (int i = 0; i < b->n; i++)
-        if (!mask || mask[i]) env_reset(&b->e[i]);
+        if (!mask || mask[i]) batch_reset_env(b, i);
 }
 
 typedef struct {
@@ -545,7 +610,7 @@ static void step_walking_range(void *ctx, int64_t lo, int64_t hi) {
     for (int64_t i = lo; i < hi; i++) {
         orc_env *e = &s->b->e[i];
         orc_action a;
-        if (s->auto_reset && e->done_prev) env_reset(e);
+        if (s->auto_reset && e->done_prev) batch_reset_env(s->b, i);
         parse_walking_discrete(s->actions[i], &a);
         env_step(s->b, e, &a, &s->reward[i], &s->done[i]);
     }
@@ -563,7 +628,7 @@ static void step_flying_range(void *ctx, int64_t lo, int64_t hi) {
     for (int64_t i = lo; i < hi; i++) {
         orc_env *e = &s->b->e[i];
         orc_action a;
-        if (s->auto_reset && e->done_prev) env_reset(e);
+        if (s->auto_reset && e->done_prev) batch_reset_env(s->b, i);
         memset(&a, 0, sizeof(a));
         a.strafe[0] = s->movement[3 * i + 0];
         a.strafe[1] = s->movement[3 * i + 1];
@@ -594,7 +659,7 @@ static void step_walking_dict_range(void *ctx, int64_t lo, int64_t hi) {
         orc_env *e = &b->e[i];
         const int32_t *k = s->buttons + 8 * i;
         orc_action a;
-        if (s->auto_reset && e->done_prev) env_reset(e);
+        if (s->auto_reset && e->done_prev) batch_reset_env(s->b, i);
         memset(&a, 0, sizeof(a));
         if (k[0]) a.strafe[0] += -1;
         if (k[1]) a.strafe[0] += 1;

@@ -514,12 +514,119 @@ def gen_misc(Task, Tasks):
     print('misc.npz', out['gi_value'][:8], out['st_start'], out['st_goal'], out['st_steps'].tolist())
 
 
+def gen_generator(gym, Task, Tasks):
+    """env.set_task_generator (reference env.py:166-172, 213-216): every reset first asks the generator for
+    the next task. The generator is a finite pool drawn with np.random.choice, like RandomTasks(max_cache=m)
+    .reset (task_set.py:120-127) -- but with starting_grid=[] / real starting grids, because a Task whose
+    starting_grid is None crashes GridWorld.step. The chosen indices are recorded so that the
+    batched build can be driven through the same sequence."""
+    rng = np.random.RandomState(5)
+    out, names = {}, []
+
+    class PoolGen(Tasks):
+        def __init__(self, tasks):
+            self.tasks = tasks
+            self.choices = []
+            self.current = None
+
+        def reset(self):
+            j = int(np.random.choice(len(self.tasks)))
+            self.choices.append(j)
+            self.current = self.tasks[j]
+            return self.current
+
+    # where does "select BLUE, look down 45 degrees, place" put its block from the spawn pose? (dry run)
+    SCRIPT = [6] + [14] * 9 + [17]
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking')
+    far = np.zeros((9, 11, 11), np.int32)
+    far[0, 0, 0] = 3
+    env.set_task(Task('', far, starting_grid=[]))
+    for a in SCRIPT:
+        env.step(a)
+    tiny = env.unwrapped.grid.astype(np.int8).copy()
+    assert np.count_nonzero(tiny) == 1, np.argwhere(tiny)
+    print('  scripted placement lands at dense', np.argwhere(tiny)[0], 'colour', int(tiny.max()))
+
+    def pool(m, with_start):
+        ts, ss = [], []
+        for j in range(m):
+            t = synth_target(rng, (0.03, 0.08, 0.2)[j % 3], 'compact')
+            t[0, 5, 6] = 1 + j % 6  # one block right in front of the spawn point: reachable 'done' for tiny targets
+            s = None
+            if with_start and j % 2 == 1:
+                s = synth_target(rng, 0.04, 'compact')
+                s[:, 5, 5] = 0
+                s[2:] = 0
+            ts.append(t)
+            ss.append(np.zeros((9, 11, 11), np.int8) if s is None else s)
+        ts[0] = tiny.copy()  # a one-block task: completed (done) by the scripted placement
+        ss[0] = np.zeros((9, 11, 11), np.int8)
+        return np.array(ts, np.int8), np.array(ss, np.int8)
+
+    idx = 0
+    for name, space, n, max_steps, with_start in (('walking_pool', 'walking', 900, 30, True),
+                                                  ('walking_pool_nostart', 'walking', 600, 25, False),
+                                                  ('flying_pool', 'flying', 400, 40, True)):
+        ts, ss = pool(7, with_start)
+        tasks = [Task('', ts[j].astype(np.int32), starting_grid=dense_to_sparse_world(ss[j])) for j in range(len(ts))]
+        gen = PoolGen(tasks)
+        np.random.seed(100 + idx)  # the generator draws from numpy's global stream, like the reference's
+        env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, target_in_obs=True,
+                       action_space=space, max_steps=max_steps)
+        env.set_task_generator(gen)
+        rec = Recorder()
+        if space == 'walking':
+            a = walking_action_mix(rng, n, 'builder')
+            conv = lambda acts, t: int(acts[t])  # noqa: E731
+            acts = a
+            out[f't{idx}_actions'] = a
+        else:
+            mv = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+            cam = rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+            inv = rng.randint(0, 7, n).astype(np.int32)
+            pl = rng.choice([0, 0, 1, 1, 2], n).astype(np.int32)
+            acts = (mv, cam, inv, pl)
+            conv = lambda ac, t: {'movement': [float(v) for v in ac[0][t]], 'camera': [float(v) for v in ac[1][t]],  # noqa: E731
+                                  'inventory': int(ac[2][t]), 'placement': int(ac[3][t])}
+            out[f't{idx}_movement'], out[f't{idx}_camera'] = mv, cam
+            out[f't{idx}_inv'], out[f't{idx}_placement'] = inv, pl
+        done = False
+        task_at_step = []
+        ep_t = 0
+        for t in range(n):
+            if done:
+                env.reset()
+                ep_t = 0
+            if name == 'walking_pool' and ep_t < len(SCRIPT):
+                acts[t] = SCRIPT[ep_t]  # every episode opens with the scripted placement (completes the tiny task)
+            ep_t += 1
+            obs, reward, done, _ = env.step(conv(acts, t))
+            j = gen.choices[-1]
+            assert np.array_equal(np.asarray(obs['target_grid']), ts[j].astype(np.int32))
+            task_at_step.append(j)
+            rec.record(env, obs, reward, done, t)
+        p = f't{idx}_'
+        out[p + 'pool_targets'], out[p + 'pool_starts'] = ts, ss
+        out[p + 'choices'] = np.array(gen.choices, np.int32)
+        out[p + 'task_at_step'] = np.array(task_at_step, np.int32)
+        out[p + 'cfg'] = np.array([1, max_steps], np.int32)
+        out[p + 'space'] = np.array(space)
+        rec.pack(p, out)
+        names.append(name)
+        print('  generator', name, n, 'steps; resets', len(gen.choices), 'dones', int(np.sum(rec.d['done'])),
+              'early dones', int(np.sum(np.array(rec.d['done']) & (np.array(rec.d['step_no']) < max_steps))))
+        idx += 1
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'traces_generator.npz'), **out)
+    print('traces_generator.npz', idx, 'traces')
+
+
 def main():
     load_reference.load()
     import gym
     from gridworld.tasks import Task, Tasks
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc']
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator']
     if 'goals' in which:
         gen_goals(Task, Tasks)
     if 'pairs' in which:
@@ -532,6 +639,8 @@ def main():
         gen_dict(gym, Task)
     if 'misc' in which:
         gen_misc(Task, Tasks)
+    if 'generator' in which:
+        gen_generator(gym, Task, Tasks)
 
 
 if __name__ == '__main__':

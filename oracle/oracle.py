@@ -34,6 +34,12 @@ def lib():
         L.orc_destroy.argtypes = [vp]
         L.orc_set_task.argtypes = [vp, i32, vp, vp, vp]
         L.orc_reset.argtypes = [vp, vp]
+        L.orc_set_pool.argtypes = [vp, vp, vp, i64, C.c_uint64, i64]
+        L.orc_pool_next_task.restype = C.POINTER(C.c_int32)
+        L.orc_pool_next_task.argtypes = [vp]
+        L.orc_pool_task_id.restype = C.POINTER(C.c_int32)
+        L.orc_pool_task_id.argtypes = [vp]
+        L.orc_get_target.argtypes = [vp, vp]
         L.orc_step_walking.argtypes = [vp, vp, vp, vp, i32, i32]
         L.orc_step_flying.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32]
         L.orc_step_walking_dict.argtypes = [vp, vp, vp, vp, vp, i32, i32]
@@ -89,6 +95,21 @@ class OracleBatch:
         for i in range(self.n):
             self.set_task(i, targets[i], None if starts is None else starts[i],
                           None if poses is None else poses[i])
+
+    def set_pool(self, targets, starts=None, seed=0, env_offset=0):
+        """env.set_task_generator with a finite pool drawn at every reset (see iglu_oracle.c batch_reset_env)."""
+        t = _i8(targets)
+        m = t.shape[0]
+        t = t.reshape(m, CELLS)
+        s = None if starts is None else _i8(starts).reshape(m, CELLS)
+        lib().orc_set_pool(self._h, _p(t), _p(s), m, int(seed) & (2 ** 64 - 1), int(env_offset))
+        self.next_task = np.ctypeslib.as_array(lib().orc_pool_next_task(self._h), shape=(self.n,))
+        self.task_ids = np.ctypeslib.as_array(lib().orc_pool_task_id(self._h), shape=(self.n,))
+
+    def target_grids(self):
+        out = np.zeros((self.n, 9, 11, 11), np.int32)
+        lib().orc_get_target(self._h, _p(out))
+        return out
 
     def reset(self, mask=None):
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)

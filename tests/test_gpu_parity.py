@@ -340,6 +340,128 @@ def test_sharding_is_concatenation():
     assert torch.equal(full._pose, torch.cat([parts[0]._pose, parts[1]._pose], dim=1))
 
 
+@pytest.mark.parametrize('tr', G.generator_traces(), ids=lambda t: t['name'])
+def test_task_generator_golden(tr):
+    """env.set_task_generator on the reference (every reset draws the next task, env.py:213-216) vs the
+    device-resident pool: the indices the reference's generator drew are imposed through next_task, everything
+    else -- Task.__init__ products, starting grid, inventory, target_grid obs -- comes from the pool on device."""
+    import gridworld_b200 as gw
+    flying = tr['space'] == 'flying'
+    env = gw.make_vec(1, action_space=tr['space'], max_steps=tr['max_steps'], auto_reset=True, target_in_obs=True)
+    dev = env.device
+    ch = [int(c) for c in tr['choices']]
+    nt = torch.full((1,), ch.pop(0), dtype=torch.int32, device=dev)
+    env.set_task_pool(tr['pool_targets'], tr['pool_starts'], seed=11, next_task=nt)
+    a = tr['actions']
+    done = False
+    for t in range(tr['n']):
+        if done:
+            nt[0] = ch.pop(0)
+        if flying:
+            obs, r, d, _ = env.step({'movement': a['movement'][t][None], 'camera': a['camera'][t][None],
+                                     'inventory': a['inv'][t:t + 1], 'placement': a['placement'][t:t + 1]})
+        else:
+            obs, r, d, _ = env.step(a['actions'][t:t + 1])
+        done = bool(d[0])
+        ctx = f"{tr['name']} step {t}"
+        j = int(tr['task_at_step'][t])
+        assert int(env.task_ids[0]) == j and int(nt[0]) == -1, ctx
+        assert float(r[0]) == tr['reward'][t], ctx
+        assert done == bool(tr['done'][t]), ctx
+        assert np.array_equal(env.grid[0].cpu().numpy().reshape(-1), G.grid_at(tr, t)), ctx
+        assert np.array_equal(obs['grid'][0].cpu().numpy().reshape(-1), G.grid_at(tr, t).astype(np.int32)), ctx
+        assert np.array_equal(obs['target_grid'][0].cpu().numpy(), tr['pool_targets'][j].astype(np.int32)), ctx
+        assert env.inventory[0].cpu().numpy().tolist() == tr['inventory'][t].tolist(), ctx
+        assert int(env.max_int[0]) == tr['max_int'][t] and int(env.step_no[0]) == tr['step_no'][t], ctx
+        pos = env.position[0].cpu().numpy()
+        if flying:
+            assert np.abs(pos - tr['pos'][t]).max() <= POSE_TOL, ctx
+        else:
+            assert pos.tolist() == tr['pos'][t].tolist() and float(env.dy[0]) == tr['dy'][t], ctx
+            assert np.array_equal(obs['agentPos'][0].cpu().numpy(), tr['agentPos'][t]), ctx
+    assert not ch
+
+
+def _pool(rng, m):
+    T = _synth(rng, m, 0.1, 'compact')
+    S = _synth(rng, m, 0.04, 'compact')
+    S[:, 2:] = 0
+    S[:, :, 5, 5] = 0
+    S[::2] = 0
+    T[0] = 0
+    T[0, 0, 5, 4] = 1  # one-block task (finishes early when the block lands there)
+    return T, S
+
+
+@pytest.mark.parametrize('reward_mode,grid_obs', [('on_change', True), ('every_step', True),
+                                                  ('on_change', 'incremental')])
+def test_task_generator_batch_vs_oracle(reward_mode, grid_obs):
+    """Counter-based draws on device (fused and two-launch step forms) vs the oracle's restatement."""
+    import gridworld_b200 as gw
+    n, m, steps = 1536, 37, 260
+    rng = np.random.RandomState(21)
+    T, S = _pool(rng, m)
+    env = gw.make_vec(n, max_steps=24, auto_reset=True, reward_mode=reward_mode, grid_obs=grid_obs, target_in_obs=True)
+    env.set_task_pool(T, S, seed=0x1234567890ABCDEF, env_offset=5000)
+    orc = O.OracleBatch(n, 'walking', max_steps=24, threads=8)
+    orc.set_pool(T, S, seed=0x1234567890ABCDEF, env_offset=5000)
+    orc.reset()
+    assert np.array_equal(env.task_ids.cpu().numpy(), orc.task_ids)
+    p = np.array([1, 5, 2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+    for t in range(steps):
+        a = rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+        if t == 100:  # explicit masked reset in the middle: draws for the masked envs only
+            mask = (np.arange(n) % 3 == 0).astype(np.uint8)
+            env.reset(mask)
+            orc.reset(mask)
+        obs, r, d, _ = env.step(a)
+        ro, do = orc.step_walking(a, auto_reset=True)
+        assert np.array_equal(r.cpu().numpy(), ro), t
+        assert np.array_equal(d.cpu().numpy(), do), t
+        assert np.array_equal(env.task_ids.cpu().numpy(), orc.task_ids), t
+        if t % 20 == 19 or t == steps - 1:
+            s = orc.state()
+            assert np.array_equal(env.grid.cpu().numpy(), s['grid']), t
+            assert np.array_equal(env.position.cpu().numpy(), s['pos']), t
+            assert np.array_equal(env.inventory.cpu().numpy(), s['inventory']), t
+            assert np.array_equal(env.max_int.cpu().numpy(), s['max_int']), t
+            assert np.array_equal(obs['grid'].cpu().numpy(), orc.obs()['grid']), t
+            assert np.array_equal(obs['target_grid'].cpu().numpy(), orc.target_grids()), t
+            assert np.array_equal(obs['target_grid'].cpu().numpy(), T[orc.task_ids].astype(np.int32)), t
+    assert len(np.unique(orc.task_ids)) > m // 2
+
+
+def test_task_generator_sharding_and_checkpoint():
+    """env_offset makes shards draw what the single-device run draws; state_dict carries the cursor."""
+    import gridworld_b200 as gw
+    n, m, h = 1024, 19, 512
+    rng = np.random.RandomState(23)
+    T, S = _pool(rng, m)
+    full = gw.make_vec(n, max_steps=15)
+    full.set_task_pool(T, S, seed=77)
+    parts = [gw.make_vec(h, max_steps=15) for _ in range(2)]
+    parts[0].set_task_pool(T, S, seed=77, env_offset=0)
+    parts[1].set_task_pool(T, S, seed=77, env_offset=h)
+    acts = [torch.as_tensor(rng.randint(0, 18, n).astype(np.int32), device='cuda') for _ in range(70)]
+    for t, a in enumerate(acts):
+        if t == 40:
+            sd = full.state_dict()
+        _, r, d, _ = full.step(a)
+        r0 = parts[0].step(a[:h])[1]
+        r1 = parts[1].step(a[h:])[1]
+        assert torch.equal(r, torch.cat([r0, r1])), t
+        assert torch.equal(full.task_ids, torch.cat([parts[0].task_ids, parts[1].task_ids])), t
+    assert torch.equal(full.grid, torch.cat([parts[0].grid, parts[1].grid]))
+    # resume from the step-40 checkpoint in a fresh env: same continuation
+    again = gw.make_vec(n, max_steps=15)
+    again.set_task_pool(T, S, seed=77, reset=False)
+    again.load_state_dict(sd)
+    for a in acts[40:]:
+        again.step(a)
+    assert torch.equal(again.grid, full.grid) and torch.equal(again.task_ids, full.task_ids)
+    assert torch.equal(again._istate, full._istate)
+
+
 def test_full_size_invariants():
     """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
     import gridworld_b200 as gw

@@ -57,6 +57,76 @@ def test_walking_dict_traces(tr):
     _replay(tr, 'dict')
 
 
+@pytest.mark.parametrize('tr', G.generator_traces(), ids=lambda t: t['name'])
+def test_generator_traces(tr):
+    """env.set_task_generator: every reset draws the next task first (reference env.py:213-216). The indices the
+    reference's generator drew (numpy global stream) are imposed through next_task."""
+    b = O.OracleBatch(1, action_space=tr['space'], max_steps=tr['max_steps'])
+    b.set_pool(tr['pool_targets'], tr['pool_starts'], seed=3)
+    ch = list(tr['choices'])
+    b.next_task[0] = ch.pop(0)
+    b.reset()
+    a = tr['actions']
+    done = False
+    for t in range(tr['n']):
+        if done:
+            b.next_task[0] = ch.pop(0)
+        if tr['space'] == 'walking':
+            r, d = b.step_walking(a['actions'][t:t + 1], auto_reset=True)
+        else:
+            r, d = b.step_flying(a['movement'][t], a['camera'][t], a['inv'][t:t + 1], a['placement'][t:t + 1],
+                                 auto_reset=True)
+        done = bool(d[0])
+        s = b.state()
+        ctx = f"{tr['name']} step {t}"
+        assert b.task_ids[0] == tr['task_at_step'][t], ctx
+        assert s['pos'][0].tolist() == tr['pos'][t].tolist(), ctx
+        assert s['rot'][0].tolist() == tr['rot'][t].tolist(), ctx
+        assert s['dy'][0] == tr['dy'][t], ctx
+        assert s['inventory'][0].tolist() == tr['inventory'][t].tolist(), ctx
+        assert r[0] == tr['reward'][t], ctx
+        assert done == bool(tr['done'][t]), ctx
+        assert s['max_int'][0] == tr['max_int'][t], ctx
+        assert s['step_no'][0] == tr['step_no'][t], ctx
+        assert np.array_equal(s['grid'][0].reshape(-1), G.grid_at(tr, t)), ctx
+        assert np.array_equal(b.target_grids()[0], tr['pool_targets'][tr['task_at_step'][t]]), ctx
+    assert not ch
+
+
+def test_generator_draw_formula():
+    """The counter-based draw published in include/iglu_b200.h, restated in plain Python integers."""
+    M64 = (1 << 64) - 1
+
+    def draw(seed, env, ep, m):
+        x = (seed + 0x9E3779B97F4A7C15 * (env + 1) + 0xD1B54A32D192ED03 * ep) & M64
+        x ^= x >> 30
+        x = (x * 0xBF58476D1CE4E5B9) & M64
+        x ^= x >> 27
+        x = (x * 0x94D049BB133111EB) & M64
+        x ^= x >> 31
+        return ((x >> 32) * m) >> 32
+
+    n, m, seed, off = 64, 13, 0xDEADBEEFCAFE1234, 1000
+    rng = np.random.RandomState(0)
+    T = (rng.rand(m, 9, 11, 11) < 0.05).astype(np.int8)
+    b = O.OracleBatch(n, max_steps=2)
+    b.set_pool(T, None, seed=seed, env_offset=off)
+    b.reset()
+    ids = lambda ep: [draw(seed, off + e, ep, m) for e in range(n)]  # noqa: E731
+    assert b.task_ids.tolist() == ids(0)
+    for _ in range(3):  # max_steps = 2: done on the 2nd step, auto-reset (= next draw) inside the 3rd
+        b.step_walking(np.zeros(n, np.int32), auto_reset=True)
+    assert b.task_ids.tolist() == ids(1)
+    b.reset()  # an explicit reset draws as well; the episode counter keeps counting
+    assert b.task_ids.tolist() == ids(2)
+    b.next_task[5] = 7  # imposed index: used once, then consumed
+    b.reset()
+    want = ids(3)
+    want[5] = 7
+    assert b.task_ids.tolist() == want and b.next_task[5] == -1
+    assert len(set(ids(0) + ids(1) + ids(2))) > m // 2
+
+
 def test_goals_known_answers():
     z = G.load('goals.npz')
     T = z['targets']
