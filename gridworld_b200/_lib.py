@@ -28,7 +28,7 @@ class Config(C.Structure):
 class State(C.Structure):
     _fields_ = [('n', C.c_int64), ('grid', C.c_void_p), ('init', C.c_void_p), ('target', C.c_void_p),
                 ('pose', C.c_void_p), ('init_pose', C.c_void_p), ('istate', C.c_void_p),
-                ('tlist', C.c_void_p), ('tmeta', C.c_void_p)]
+                ('tlist', C.c_void_p), ('tmeta', C.c_void_p), ('sched', C.c_void_p)]
 
 
 class Obs(C.Structure):

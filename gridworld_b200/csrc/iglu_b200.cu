@@ -55,6 +55,7 @@ struct StepParams {
     const int32_t *placement;  // flying [n]
     const int32_t *buttons;    // walking dict [n][8]
     iglu_task_pool pool;       // device-resident task generator (m == 0: none)
+    int dynamic;               // observe launch: groups handed out through st.sched[0] instead of a static deal
     int group;                 // envs per warp: 32, or 16 when there are too few envs to fill the SMs
 };
 
@@ -105,27 +106,18 @@ __device__ __forceinline__ void write_grid_obs(int32_t *__restrict__ obs_grid, i
         lo[it] = on ? sg[m] : 0u;
         hi[it] = on ? sg[m + 1] : 0u;
     }
+    // byte h + k of the pair {lo, hi}, sign-extended to 32 bits, is ONE prmt: selector nibble 8 | i replicates the
+    // sign of byte i (PTX prmt default mode; the __byte_perm intrinsic masks that bit, hence the inline PTX)
+    const uint32_t sel0 = 0x8880u + 0x1111u * (uint32_t)h;
 #pragma unroll
     for (int it = 0; it < 9; it++) {
         const int m = lane + 32 * it;
-        const uint32_t w = __funnelshift_r(lo[it], hi[it], 8 * h);  // bytes h + 4m .. h + 4m + 3
         int4 v;
-        v.x = (int)__byte_perm(w, 0, 0x4440);  // zero-extend each byte (one PRMT) ...
-        v.y = (int)__byte_perm(w, 0, 0x4441);
-        v.z = (int)__byte_perm(w, 0, 0x4442);
-        v.w = (int)__byte_perm(w, 0, 0x4443);
-        if (w & 0x80808080u) {                  // ... and sign-extend in the rare word that holds a negative cell
-            v.x = (int)(int8_t)(w); v.y = (int)(int8_t)(w >> 8); v.z = (int)(int8_t)(w >> 16); v.w = (int)(int8_t)(w >> 24);
-        }
-#if defined(IGLU_OBS_ST_DEFAULT)
-        if (it < 8 || m < nbody) o4[m] = v;
-#elif defined(IGLU_OBS_ST_WT)
-        if (it < 8 || m < nbody) __stwt(o4 + m, v);
-#elif defined(IGLU_OBS_ST_CG)
-        if (it < 8 || m < nbody) __stcg(o4 + m, v);
-#else
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v.x) : "r"(lo[it]), "r"(hi[it]), "r"(sel0));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v.y) : "r"(lo[it]), "r"(hi[it]), "r"(sel0 + 0x1111u));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v.z) : "r"(lo[it]), "r"(hi[it]), "r"(sel0 + 0x2222u));
+        asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v.w) : "r"(lo[it]), "r"(hi[it]), "r"(sel0 + 0x3333u));
         if (it < 8 || m < nbody) __stcs(o4 + m, v);
-#endif
     }
     const int t0 = h + 4 * nbody;
     if (lane < CELLS - t0) og[t0 + lane] = (int32_t)sg8[t0 + lane];
@@ -192,6 +184,9 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #ifndef IGLU_OBS_RING
 #define IGLU_OBS_RING 2
 #endif
+#ifndef IGLU_OBS_DYN_GROUP
+#define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
+#endif
 template <int PHASES> struct StepCfg {
     static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
     static constexpr int NBUF = PHASES == 2 ? IGLU_OBS_RING : NB;
@@ -249,7 +244,16 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 
     // groups are dealt warp-major (warp w of every CTA before warp w + 1 of any) so that a partial last
     // wave spreads evenly over the SMs
-    for (int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x; grp < ngroups; grp += (int64_t)gridDim.x * WPC) {
+    // The observe launch hands groups out dynamically (one atomic per group on a counter the physics launch
+    // zeroed; the next index is fetched while the current group is processed): per-env cost varies with the
+    // evaluation, and a static deal leaves the SMs unevenly loaded in the single wave.
+    const bool dynamic = PHASES == 2 && p.dynamic;
+    if (PHASES == 1 && p.st.sched != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.st.sched[0] = 0;
+    int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x;
+    if (dynamic) grp = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(p.st.sched, 1) : 0, 0);
+    while (grp < ngroups) {
+        int grp_next = 0;
+        if (dynamic && lane == 0) grp_next = atomicAdd(p.st.sched, 1);
         auto env_of = [&](int j) -> int64_t { return grp * GS + j; };
         const int64_t i = env_of(lane);
         const bool valid = lane < GS && i < n;
@@ -524,6 +528,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 p.st.istate[6 * n + i] = mi;
             }
         }
+        grp = dynamic ? (int64_t)__shfl_sync(0xffffffffu, grp_next, 0) : grp + (int64_t)gridDim.x * WPC;
     }
 }
 
@@ -932,6 +937,16 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
     const int64_t warp_slots = resident_ctas * StepCfg<2>::WPC;
     int64_t chunk = (n + warp_slots - 1) / warp_slots;
+    // dynamic hand-out pays when every env has ring work in this launch (measured: profiles/r01_launch_policy.txt);
+    // with on_change reward and no full obs rewrite only ~6 % of the envs do, and big static chunks are cheaper
+    const bool dynamic = p.st.sched != nullptr && !(p.cfg.reserved & 8) &&
+                         (p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP || (p.cfg.write_grid_obs == 1 && p.obs.grid));
+    p.dynamic = dynamic;
+    if (dynamic) {  // small groups handed out dynamically: >= ~6 per warp, 2..IGLU_OBS_DYN_GROUP envs each (measured)
+        chunk /= 6;
+        chunk = chunk < 2 ? 2 : (chunk > IGLU_OBS_DYN_GROUP ? IGLU_OBS_DYN_GROUP : chunk);
+    }
+    if ((p.cfg.reserved >> 8) & 63) chunk = (p.cfg.reserved >> 8) & 63;     // tuning override
     p.group = (int)(chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk));
     const int64_t groups_b = (n + p.group - 1) / p.group;
     const int64_t ctas_b = (groups_b + StepCfg<2>::WPC - 1) / StepCfg<2>::WPC;

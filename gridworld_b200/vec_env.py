@@ -79,7 +79,8 @@ class IGLUVecEnv:
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
-                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None, split_launch=True):
+                 grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None, split_launch=True,
+                 _sched_bits=0):
         if render:
             raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
         if reward_mode not in ('on_change', 'every_step'):
@@ -129,6 +130,7 @@ class IGLUVecEnv:
             raise ValueError(f'max_target_blocks must be <= {_lib.TLIST_MAX}')
         self._tlist = z(n, tlist_cap, dtype=torch.int16)
         self._tmeta = z(8, n, dtype=torch.int32)
+        self._sched = z(8, dtype=torch.int32)
         # ---- observations / results ----
         self._obs_grid = z(n, 9, 11, 11, dtype=torch.int32) if self.grid_obs else None
         self._obs_target = z(n, 9, 11, 11, dtype=torch.int32) if self.target_in_obs else None
@@ -141,12 +143,13 @@ class IGLUVecEnv:
 
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._st = _lib.State(n, p(self._grid), p(self._init), p(self._target), p(self._pose),
-                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._tmeta))
+                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._tmeta), p(self._sched))
         self._ob = _lib.Obs(p(self._obs_grid), p(self._obs_target), p(self._obs_pos), p(self._obs_inv),
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),
                           _lib.REWARD_EVERY_STEP if reward_mode == 'every_step' else _lib.REWARD_ON_CHANGE,
-                          int(self.grid_obs_mode), int(tlist_cap), (0 if alternate_phases else 1) | (0 if split_launch else 2) | (4 if split_launch == 'force' else 0),
+                          int(self.grid_obs_mode), int(tlist_cap), (0 if alternate_phases else 1) | (0 if split_launch else 2) | (4 if split_launch == 'force' else 0)
+                          | int(_sched_bits),
                           float(right_placement_scale), float(wrong_placement_scale))
         self._ctx = C.c_void_p()
         with torch.cuda.device(dev):

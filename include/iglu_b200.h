@@ -77,7 +77,9 @@ typedef struct iglu_config {
     int32_t reserved;           /* scheduling switches (results identical): bit 0 = 1 disables the observation-first /
                                    physics-first warp alternation of the fused launch; bit 1 = 1 forces the fused
                                    launch where the library would use two launches (physics, then observe);
-                                   bit 2 = 1 forces the two-launch form */
+                                   bit 2 = 1 forces the two-launch form; bit 3 = 1 deals the observe launch's env
+                                   groups statically even when iglu_state.sched is given; bits 8-13: envs per
+                                   group of the observe launch (0 = automatic) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
 } iglu_config;
@@ -104,6 +106,8 @@ typedef struct iglu_state {
     int32_t *tmeta;    /* [8][n]  w0: number of tlist entries; w1: target_size (task.py:35);
                                   w2..w4: inventory after reset, 6 x int16 (env.py:243-246);
                                   w5: 1 if the starting grid is non-empty; w6: 1 once a task is set; w7: reserved */
+    int32_t *sched;    /* [8] launch-to-launch scratch (work counter of the observe launch), or NULL = groups of
+                                  envs are dealt statically */
 } iglu_state;
 
 /* Observation / result buffers (reference env.py:283-303). They persist between steps and are

@@ -462,6 +462,23 @@ def test_task_generator_sharding_and_checkpoint():
     assert torch.equal(again._istate, full._istate)
 
 
+def test_obs_grid_negative_cells_and_all_alignments():
+    """obs['grid'] is the sign-extended int8 state for every value and every 16-byte phase of the row
+    (WHITE = -1 is a legal value of the observation space, env.py:88)."""
+    import gridworld_b200 as gw
+    n = 67
+    rng = np.random.RandomState(4)
+    for kw in (dict(reward_mode='every_step'), dict(reward_mode='on_change')):
+        env = gw.make_vec(n, max_steps=1000, **kw)
+        env.set_tasks(_synth(rng, n, 0.1, 'compact'))
+        g = rng.randint(-6, 7, (n, 1089)).astype(np.int8)
+        g[rng.random_sample((n, 1089)) < 0.5] = 0
+        g.reshape(n, 9, 11, 11)[:, 0:4, 4:7, 4:7] = 0  # free space around the agent
+        env._grid[:, :1089] = torch.as_tensor(g, device=env.device)
+        obs, _, _, _ = env.step(np.zeros(n, np.int32))
+        assert np.array_equal(obs['grid'].cpu().numpy().reshape(n, 1089), g.astype(np.int32))
+
+
 def test_full_size_invariants():
     """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
     import gridworld_b200 as gw
