@@ -12,9 +12,12 @@ actions, full maximal_intersection evaluated on EVERY step, int32 obs['grid'] ma
 auto-reset on done. A "step" = one call of the step path over all envs of the rank.
 
 value  = env-steps/s with the action tensors already resident in HBM (CUDA events, max over ranks).
-e2e    = the same metric through the host-buffer C-ABI call iglu_step_walking_host: every step copies the
-         int32 actions from pinned host memory to the device and reads reward (f64) + done (u8) back;
-         observations stay on the device for an on-device policy (BASELINE configs[4]).
+e2e    = the same metric through the host-buffer C-ABI call iglu_step_walking_host: every step takes the
+         int32 actions from pinned host memory and delivers reward (f64) + done (u8) into pinned host memory,
+         stream synchronised per step. The buffers are pinned, so the kernels move these bytes over PCIe
+         themselves (zero-copy reads / writes inside the step kernels) instead of staging them through
+         cudaMemcpyAsync before / after the step; `e2e.staged_value` is the same call with the staged copies
+         forced. Observations stay on the device for an on-device policy (BASELINE configs[4]).
 roofline: HBM. achieved = A_walk * envs / mean step-kernel duration, A_walk = 5,634 algorithmic bytes per
          env-step (4,413 B of observations/results written, 1,089 B grid + 4 B action read,
          64 B state read + 64 B written), peak = MEASURED_PEAKS.json hbm_gbs.
@@ -246,6 +249,19 @@ def run_b200_arm(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
     e2e_value = n * world * Ke / D.max_over_ranks(e2e_s, dev)
+    # the same call with the transfers staged through cudaMemcpyAsync (reserved bit 4), for comparison
+    env_st = gw.make_vec(n, device=dev, action_space='walking', select_and_place=True, max_steps=MAX_STEPS,
+                         auto_reset=True, reward_mode=args.reward_mode, grid_obs=not args.inplace, _sched_bits=16)
+    env_st.load_state_dict(env.state_dict())
+    for t in range(3):
+        env_st.step_host(acts_host[t % P], r_host, d_host)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Ke):
+        env_st.step_host(acts_host[t % P], r_host, d_host)
+    torch.cuda.synchronize(dev)
+    e2e_staged = n * world * Ke / D.max_over_ranks(time.perf_counter() - t0, dev)
+    del env_st
 
     # ---- second half of BASELINE.json's metric: max-intersection evals/sec (stateless sweep, config 4) ----
     mi_evals = None
@@ -287,7 +303,8 @@ def run_b200_arm(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * n,
                     'd2h_bytes_per_step': 9 * n, 'steps': Ke,
-                    'api': 'IGLUVecEnv.step_host -> iglu_step_walking_host (pinned host buffers)'},
+                    'api': 'IGLUVecEnv.step_host -> iglu_step_walking_host (pinned host buffers, read / written by '
+                           'the step kernels over PCIe)', 'staged_value': e2e_staged},
             'gpu_launches': int(launches),
             'max_intersection': {'evals_per_sec': mi_evals, 'pairs_per_gpu': 1_000_000,
                                  'inputs': 'config 4: compact targets rho=0.20; half of the grids independent, half '

@@ -55,6 +55,8 @@ struct StepParams {
     const int32_t *placement;  // flying [n]
     const int32_t *buttons;    // walking dict [n][8]
     iglu_task_pool pool;       // device-resident task generator (m == 0: none)
+    double *reward_host;       // mapped pinned host copies of obs.reward / obs.done (iglu_step_walking_host), or null
+    uint8_t *done_host;
     int dynamic;               // observe launch: groups handed out through st.sched[0] instead of a static deal
     int group;                 // envs per warp: 32, or 16 when there are too few envs to fill the SMs
 };
@@ -524,6 +526,10 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                                                  : (double)right * p.cfg.right_placement_scale;
                 p.obs.reward[i] = reward;
                 p.obs.done[i] = (uint8_t)done;
+                if (p.reward_host) {  // host-buffer step: results also go straight to mapped host memory over PCIe
+                    p.reward_host[i] = reward;
+                    p.done_host[i] = (uint8_t)done;
+                }
                 p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
                 p.st.istate[6 * n + i] = mi;
             }
@@ -997,20 +1003,46 @@ extern "C" int iglu_step_walking_dict(iglu_ctx *ctx, const iglu_state *st, const
     return launch_step<IGLU_WALKING_DICT>(ctx, p, stream);
 }
 
+// Device-visible alias of a pinned (page-locked, UVA-mapped) host pointer, or null for pageable memory.
+static void *mapped_alias(const void *host) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 extern "C" int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
                                       int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
                                       uint8_t *done_host, void *stream) {
     if (!ctx || !state_ok(st, obs) || !actions_host || !actions_dev || !reward_host || !done_host)
         return IGLU_ERR_INVALID_ARG;
+    if (ctx->cfg.action_space != IGLU_WALKING_DISCRETE) return IGLU_ERR_INVALID_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = check(cudaMemcpyAsync(actions_dev, actions_host, sizeof(int32_t) * st->n, cudaMemcpyHostToDevice, s));
+    // Pinned host buffers are read / written by the kernels directly over PCIe (zero-copy): the actions are
+    // fetched by the physics launch and reward / done are stored to the host by the observe launch as it goes,
+    // so no transfer is serialised before or after the step. Pageable buffers take the staged-copy route.
+    const int32_t *a_map = static_cast<const int32_t *>(mapped_alias(actions_host));
+    // (queried on every call, not cached: a freed pinned buffer's address can come back as pageable memory)
+    double *r_map = static_cast<double *>(mapped_alias(reward_host));
+    uint8_t *d_map = static_cast<uint8_t *>(mapped_alias(done_host));
+    const bool zero_copy = a_map && r_map && d_map && !(ctx->cfg.reserved & 16);
+    int rc;
+    if (!zero_copy) {
+        rc = check(cudaMemcpyAsync(actions_dev, actions_host, sizeof(int32_t) * st->n, cudaMemcpyHostToDevice, s));
+        if (rc) return rc;
+    }
+    StepParams p;
+    memset(&p, 0, sizeof(p));
+    p.st = *st; p.obs = *obs; p.cfg = ctx->cfg; p.pool = ctx->pool;
+    p.actions = zero_copy ? a_map : actions_dev;
+    if (zero_copy) { p.reward_host = r_map; p.done_host = d_map; }
+    rc = launch_step<IGLU_WALKING_DISCRETE>(ctx, p, stream);
     if (rc) return rc;
-    rc = iglu_step_walking(ctx, st, actions_dev, obs, stream);
-    if (rc) return rc;
-    rc = check(cudaMemcpyAsync(reward_host, obs->reward, sizeof(double) * st->n, cudaMemcpyDeviceToHost, s));
-    if (rc) return rc;
-    rc = check(cudaMemcpyAsync(done_host, obs->done, sizeof(uint8_t) * st->n, cudaMemcpyDeviceToHost, s));
-    if (rc) return rc;
+    if (!zero_copy) {
+        rc = check(cudaMemcpyAsync(reward_host, obs->reward, sizeof(double) * st->n, cudaMemcpyDeviceToHost, s));
+        if (rc) return rc;
+        rc = check(cudaMemcpyAsync(done_host, obs->done, sizeof(uint8_t) * st->n, cudaMemcpyDeviceToHost, s));
+        if (rc) return rc;
+    }
     return check(cudaStreamSynchronize(s));
 }
 

@@ -78,7 +78,8 @@ typedef struct iglu_config {
                                    physics-first warp alternation of the fused launch; bit 1 = 1 forces the fused
                                    launch where the library would use two launches (physics, then observe);
                                    bit 2 = 1 forces the two-launch form; bit 3 = 1 deals the observe launch's env
-                                   groups statically even when iglu_state.sched is given; bits 8-13: envs per
+                                   groups statically even when iglu_state.sched is given; bit 4 = 1 makes
+                                   iglu_step_walking_host stage pinned buffers through copies too; bits 8-13: envs per
                                    group of the observe launch (0 = automatic) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
@@ -200,9 +201,13 @@ int iglu_step_flying(iglu_ctx *ctx, const iglu_state *st, const float *movement,
 int iglu_step_walking_dict(iglu_ctx *ctx, const iglu_state *st, const int32_t *buttons, const float *camera,
                            const iglu_obs *obs, void *stream);
 
-/* Host-buffer form of iglu_step_walking: actions_host int32 [n] (pinned or pageable) is copied to the
- * device scratch `actions_dev`, the step runs, reward/done are copied back into reward_host /
- * done_host, and the stream is synchronised. This is the call bench.py's e2e number times. */
+/* Host-buffer form of iglu_step_walking: actions_host int32 [n] in, reward_host f64 [n] / done_host u8 [n]
+ * out, stream synchronised on return. This is the call bench.py's e2e number times.
+ * Pinned (page-locked) buffers are accessed by the kernels directly over PCIe -- the physics launch reads
+ * the actions from host memory and the observe launch stores reward/done to host memory (as well as to
+ * obs->reward / obs->done) -- so no copy is serialised around the step; pageable buffers are staged through
+ * `actions_dev` (device int32 [n] scratch) and copied back after the step. config.reserved bit 4 = 1 forces
+ * the staged route. */
 int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
                            int32_t *actions_dev, const iglu_obs *obs, double *reward_host, uint8_t *done_host,
                            void *stream);

@@ -479,6 +479,35 @@ def test_obs_grid_negative_cells_and_all_alignments():
         assert np.array_equal(obs['grid'].cpu().numpy().reshape(n, 1089), g.astype(np.int32))
 
 
+def test_step_host_routes():
+    """iglu_step_walking_host: pinned buffers (kernels read / write host memory over PCIe), pageable buffers and
+    the forced staged-copy route all equal the device-tensor step."""
+    import gridworld_b200 as gw
+    n, steps = 3000, 120
+    rng = np.random.RandomState(31)
+    T, S, poses = _tasks(rng, n)
+    ref = gw.make_vec(n, max_steps=50, reward_mode='every_step')
+    ref.set_tasks(T, S, poses)
+    variants = []
+    for pinned, bits in ((True, 0), (False, 0), (True, 16)):
+        env = gw.make_vec(n, max_steps=50, reward_mode='every_step', _sched_bits=bits)
+        env.set_tasks(T, S, poses)
+        mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+        variants.append((env, mk(torch.zeros(n, dtype=torch.int32)), mk(torch.zeros(n, dtype=torch.float64)),
+                         mk(torch.zeros(n, dtype=torch.uint8))))
+    for t in range(steps):
+        a = torch.as_tensor(rng.randint(0, 18, n).astype(np.int32))
+        _, r, d, _ = ref.step(a.cuda())
+        r, d = r.cpu(), d.cpu().to(torch.uint8)
+        for env, ah, rh, dh in variants:
+            ah.copy_(a)
+            env.step_host(ah, rh, dh)
+            assert torch.equal(rh, r) and torch.equal(dh, d), t
+            assert torch.equal(env._reward.cpu(), r), t  # the device-side result buffers are written as well
+    for env, *_ in variants:
+        assert torch.equal(env.grid, ref.grid) and torch.equal(env._pose, ref._pose)
+
+
 def test_full_size_invariants():
     """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
     import gridworld_b200 as gw
