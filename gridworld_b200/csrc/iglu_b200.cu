@@ -760,9 +760,14 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
             n_rot = 4;
         }
         __syncwarp();
-        build_rows(ps.es, ps.grid, nullptr, false, lane);
-        int key = -1;
-        const int best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);
+        int key = -1, best;
+        if (!CLIP && single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
+            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(ps.grid), ps.list, nout, rc, n_rot,
+                                               lane, &key);
+        } else {
+            build_rows(ps.es, ps.grid, nullptr, false, lane);
+            best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);
+        }
         if (lane == 0) {
             out[pr] = best;
             if (WANT_KEY) {

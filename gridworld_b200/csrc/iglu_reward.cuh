@@ -291,4 +291,59 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
     return best;
 }
 
+// Direct evaluation for tasks whose every rotation admits exactly ONE shift (targets spanning the whole zone in
+// x and z, or invariant=False): per target block and rotation one byte of the staged grid is compared -- no
+// occupancy rows, no shift vectors. Lane L takes blocks L, L + 32, ...
+//   g8 : staged grid (shared memory, dense 1089 bytes); tlist / rc / n_rot as for eval_max_intersection
+__device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
+    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n_rot) ok = ok && ((rw[k] >> 8) & 0x1F) == 1 && ((rw[k] >> 24) & 0xFF) == 1;
+    return ok;
+}
+
+template <bool WANT_KEY>
+__device__ __forceinline__ int eval_single_shift(const int8_t *g8, const uint16_t *__restrict__ tlist, int nblk,
+                                                 int4 rc, int n_rot, int lane, int *key_out) {
+    const int dx0 = rect_byte(rc.x, 0), dz0 = rect_byte(rc.x, 2), dx1 = rect_byte(rc.y, 0), dz1 = rect_byte(rc.y, 2);
+    const int dx2 = rect_byte(rc.z, 0), dz2 = rect_byte(rc.z, 2), dx3 = rect_byte(rc.w, 0), dz3 = rect_byte(rc.w, 2);
+    // cell index of (y, x_k - dx_k, z_k - dz_k) = 121 y + a_k x + b_k z + o_k  with the rotations of task.py:52-53
+    const int o0 = -11 * dx0 - dz0;                       // x_0 = x,      z_0 = z
+    const int o1 = -11 * dx1 + 10 - dz1;                  // x_1 = z,      z_1 = 10 - x
+    const int o2 = 11 * (10 - dx2) + 10 - dz2;            // x_2 = 10 - x, z_2 = 10 - z
+    const int o3 = 11 * (10 - dx3) - dz3;                 // x_3 = 10 - z, z_3 = x
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int b = lane; b < nblk; b += 32) {
+        const uint32_t e = tlist[b];
+        const int y = e & 15, x = (e >> 4) & 15, z = (e >> 8) & 15, code = e >> 12;
+        if (code == 8) continue;                          // not a colour difference: matches nothing
+        const int v = code < 8 ? code : code - 16;
+        const int base = 121 * y;
+        c0 += g8[base + 11 * x + z + o0] == v;
+        if (n_rot > 1) {
+            c1 += g8[base + 11 * z - x + o1] == v;
+            c2 += g8[base - 11 * x - z + o2] == v;
+            c3 += g8[base - 11 * z + x + o3] == v;
+        }
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    int best = c0, kbest = 0;
+    if (n_rot > 1) {
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 > best) { best = c1; kbest = 1; }          // strict: the first rotation reaching the max wins
+        if (c2 > best) { best = c2; kbest = 2; }
+        if (c3 > best) { best = c3; kbest = 3; }
+    }
+    if (WANT_KEY) {
+        const int dx = kbest == 0 ? dx0 : (kbest == 1 ? dx1 : (kbest == 2 ? dx2 : dx3));
+        const int dz = kbest == 0 ? dz0 : (kbest == 1 ? dz1 : (kbest == 2 ? dz2 : dz3));
+        *key_out = best > 0 ? kbest * 441 + (dx + 10) * 21 + (dz + 10) : -1;
+    }
+    return best;
+}
+
 }  // namespace iglu
