@@ -436,11 +436,17 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 }
                 if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
                 if (ev) {
-                    build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
                     const int nb = __shfl_sync(0xffffffffu, nblk, j);
                     const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
                     const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
-                    const int r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
+                    int r;
+                    if (single_shift_rects(rc, 4)) {  // zone-spanning target: one shift per rotation, compare bytes
+                        r = eval_single_shift<false>(reinterpret_cast<const int8_t *>(sl.grid),
+                                                     hs ? p.st.init + ej * GSTRIDE : nullptr, tl, nb, rc, 4, lane, nullptr);
+                    } else {
+                        build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
+                        r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
+                    }
                     if (keep && lane == j) mi_eval = r;
                 }
                 __syncwarp();  // every lane is done with the slot before it is refilled
@@ -762,8 +768,8 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
         __syncwarp();
         int key = -1, best;
         if (!CLIP && single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
-            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(ps.grid), ps.list, nout, rc, n_rot,
-                                               lane, &key);
+            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(ps.grid), nullptr, ps.list, nout, rc,
+                                               n_rot, lane, &key);
         } else {
             build_rows(ps.es, ps.grid, nullptr, false, lane);
             best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);

@@ -294,7 +294,8 @@ __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const unsi
 // Direct evaluation for tasks whose every rotation admits exactly ONE shift (targets spanning the whole zone in
 // x and z, or invariant=False): per target block and rotation one byte of the staged grid is compared -- no
 // occupancy rows, no shift vectors. Lane L takes blocks L, L + 32, ...
-//   g8 : staged grid (shared memory, dense 1089 bytes); tlist / rc / n_rot as for eval_max_intersection
+//   g8 : staged grid (shared memory, dense 1089 bytes); sub : starting grid to subtract cell-wise (global memory)
+//        or nullptr; tlist / rc / n_rot as for eval_max_intersection
 __device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
     const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
     bool ok = true;
@@ -305,8 +306,10 @@ __device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
 }
 
 template <bool WANT_KEY>
-__device__ __forceinline__ int eval_single_shift(const int8_t *g8, const uint16_t *__restrict__ tlist, int nblk,
-                                                 int4 rc, int n_rot, int lane, int *key_out) {
+__device__ __forceinline__ int eval_single_shift(const int8_t *g8, const int8_t *__restrict__ sub,
+                                                 const uint16_t *__restrict__ tlist, int nblk, int4 rc, int n_rot,
+                                                 int lane, int *key_out) {
+    auto at = [&](int idx) -> int { return sub ? (int)g8[idx] - (int)sub[idx] : (int)g8[idx]; };
     const int dx0 = rect_byte(rc.x, 0), dz0 = rect_byte(rc.x, 2), dx1 = rect_byte(rc.y, 0), dz1 = rect_byte(rc.y, 2);
     const int dx2 = rect_byte(rc.z, 0), dz2 = rect_byte(rc.z, 2), dx3 = rect_byte(rc.w, 0), dz3 = rect_byte(rc.w, 2);
     // cell index of (y, x_k - dx_k, z_k - dz_k) = 121 y + a_k x + b_k z + o_k  with the rotations of task.py:52-53
@@ -321,11 +324,11 @@ __device__ __forceinline__ int eval_single_shift(const int8_t *g8, const uint16_
         if (code == 8) continue;                          // not a colour difference: matches nothing
         const int v = code < 8 ? code : code - 16;
         const int base = 121 * y;
-        c0 += g8[base + 11 * x + z + o0] == v;
+        c0 += at(base + 11 * x + z + o0) == v;
         if (n_rot > 1) {
-            c1 += g8[base + 11 * z - x + o1] == v;
-            c2 += g8[base - 11 * x - z + o2] == v;
-            c3 += g8[base - 11 * z + x + o3] == v;
+            c1 += at(base + 11 * z - x + o1) == v;
+            c2 += at(base - 11 * x - z + o2) == v;
+            c3 += at(base - 11 * z + x + o3) == v;
         }
     }
     c0 = __reduce_add_sync(0xffffffffu, c0);

@@ -286,6 +286,38 @@ def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs):
             assert np.array_equal(ob['inventory'].cpu().numpy(), o['inventory']), t
 
 
+@pytest.mark.parametrize('reward_mode', ['on_change', 'every_step'])
+def test_walking_zone_spanning_targets_vs_oracle(reward_mode):
+    """Targets that span the zone in x and z admit one shift per rotation (task.py:57-72): the kernels then
+    compare grid bytes directly instead of building occupancy rows. With and without starting grids."""
+    import gridworld_b200 as gw
+    n, steps = 1024, 300
+    rng = np.random.RandomState(17)
+    T = _synth(rng, n, 0.15, 'full')
+    T[:, :, 0, :] = 1  # make sure x and z extents are 0..10 for every env
+    T[:, :, 10, :] = 2
+    T[:, :, :, 0] = 3
+    T[:, :, :, 10] = 4
+    T[:, 2:] = 0
+    T[::4] = _synth(rng, len(T[::4]), 0.1, 'compact')  # a quarter keeps many shifts (row path in the same launch)
+    _, S, poses = _tasks(rng, n)
+    env = gw.make_vec(n, max_steps=90, auto_reset=True, reward_mode=reward_mode)
+    env.set_tasks(T, S, poses)
+    orc = O.OracleBatch(n, 'walking', max_steps=90, threads=8)
+    orc.set_tasks(T, S, poses)
+    p = np.array([1, 5, 2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+    for t in range(steps):
+        a = rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+        _, r, d, _ = env.step(a)
+        ro, do = orc.step_walking(a, auto_reset=True)
+        assert np.array_equal(r.cpu().numpy(), ro), t
+        assert np.array_equal(d.cpu().numpy(), do), t
+    s = orc.state()
+    assert np.array_equal(env.grid.cpu().numpy(), s['grid'])
+    assert np.array_equal(env.max_int.cpu().numpy(), s['max_int'])
+    assert (s['max_int'] > 0).mean() > 0.1  # the scenario really scores
+
+
 def test_flying_batch_vs_oracle():
     import gridworld_b200 as gw
     n, steps = 1024, 300
