@@ -124,36 +124,34 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
     // faces need their two neighbour cells is known from the incoming position: fetch only those,
     // all loads issued before any is used.
     const double ex = px - (double)nx, ey = py - (double)ny, ez = pz - (double)nz;
+    const bool on[6] = {ey >= pad, -ey >= pad, -ex >= pad, ex >= pad, ez >= pad, -ez >= pad};
+    // The 12 neighbour cells use 3 x, 4 y and 3 z coordinates: zone / floor tests once per coordinate,
+    // cell indices as offsets from the centre cell.
+    const bool xz[3] = {(unsigned)(nx + 4) <= 10u, (unsigned)(nx + 5) <= 10u, (unsigned)(nx + 6) <= 10u};  // nx-1, nx, nx+1
+    const bool zz[3] = {(unsigned)(nz + 4) <= 10u, (unsigned)(nz + 5) <= 10u, (unsigned)(nz + 6) <= 10u};
+    const bool yz[4] = {(unsigned)(ny - 1) <= 8u, (unsigned)ny <= 8u, (unsigned)(ny + 1) <= 8u,
+                        (unsigned)(ny + 2) <= 8u};                                                       // ny-2 .. ny+1
+    const bool xf[3] = {(unsigned)(nx + 17) <= 36u, (unsigned)(nx + 18) <= 36u, (unsigned)(nx + 19) <= 36u};  // |x| <= 18
+    const bool zf[3] = {(unsigned)(nz + 17) <= 36u, (unsigned)(nz + 18) <= 36u, (unsigned)(nz + 19) <= 36u};
+    const bool yf[4] = {ny == 0, ny == -1, ny == -2, ny == -3};                                          // y == -2
+    const int c0 = cell_of(nx, ny, nz);
+    // per (face, height): index into the x / y / z coordinate tables and the cell offset
+    //                      +y        -y        -x        +x        +z        -z
+    constexpr int XI[12] = {1, 1,     1, 1,     0, 0,     2, 2,     1, 1,     1, 1};
+    constexpr int YI[12] = {3, 2,     1, 0,     2, 1,     2, 1,     2, 1,     2, 1};
+    constexpr int ZI[12] = {1, 1,     1, 1,     1, 1,     1, 1,     2, 2,     0, 0};
     int cv[12];
 #pragma unroll
-    for (int f = 0; f < 6; f++) {
-        const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
-        const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
-        const double e = (axis == 0) ? ex : (axis == 1 ? ey : ez);
-        const bool face_on = e * (double)sgn >= pad;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int ox = nx, oy = ny - h, oz = nz;
-            if (axis == 0) ox += sgn;
-            else if (axis == 1) oy += sgn;
-            else oz += sgn;
-            const bool need = face_on && in_zone(ox, oy, oz);
-            cv[2 * f + h] = ld_s8_if(g + (need ? cell_of(ox, oy, oz) : 0), need);
-        }
+    for (int c = 0; c < 12; c++) {
+        const bool need = on[c >> 1] && xz[XI[c]] && yz[YI[c]] && zz[ZI[c]];
+        const int off = (XI[c] - 1) * 11 + (YI[c] - 2) * 121 + (ZI[c] - 1);
+        cv[c] = ld_s8_if(g + (need ? c0 + off : 0), need);
     }
     unsigned solid = 0;
 #pragma unroll
-    for (int f = 0; f < 6; f++) {
-        const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
-        const int sgn = (f == 0 || f == 3 || f == 4) ? 1 : -1;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            int ox = nx, oy = ny - h, oz = nz;
-            if (axis == 0) ox += sgn;
-            else if (axis == 1) oy += sgn;
-            else oz += sgn;
-            solid |= (unsigned)world_has(cv[2 * f + h], ox, oy, oz) << (2 * f + h);
-        }
+    for (int c = 0; c < 12; c++) {
+        const bool floor_hit = yf[YI[c]] && xf[XI[c]] && zf[ZI[c]];
+        solid |= (unsigned)(floor_hit || cv[c] != 0) << c;
     }
 #pragma unroll
     for (int f = 0; f < 6; f++) {
@@ -228,40 +226,47 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         // hit_test (73-99): 40 samples, step 1/5; lookups gathered 8 at a time
         const double sx = vx / 5.0, syy = vy / 5.0, sz = vz / 5.0;
         double px = a.x, py = a.y, pz = a.z;
-        int kx = 0, ky = 0, kz = 0, qx = 0, qy = 0, qz = 0;
-        bool has_prev = false, hit = false;
+        // Keys are compared in packed form (x + 1024 y + 2^20 z, offset 512 each): consecutive samples differ by at
+        // most one cell per axis, so equality of packed keys is exact whatever the magnitude; only keys of a hit
+        // (which lie in the zone or on the floor) and of the sample before it are unpacked.
+        // `previous` (world.py:97) is always the key of the sample before, so "key != previous" is `fresh`.
+        uint32_t kkey = 0, qkey = 0, last = 0;
+        bool has_prev = false, hit = false, lvalid = false;
         for (int i0 = 0; i0 < 40 && !hit; i0 += 8) {
-            int bx[8], by[8], bz[8], cv[8];
-            int lx = qx, ly = qy, lz = qz;  // key of the sample before this batch (valid when has_prev)
-            bool lvalid = has_prev;
+            uint32_t key[8];
+            int cv[8];
+            unsigned fresh = 0, solid = 0;
+            const uint32_t last_in = last;
+            const bool lvalid_in = lvalid;
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                bx[j] = (int)rint(px); by[j] = (int)rint(py); bz[j] = (int)rint(pz);
+                const int bx = (int)rint(px), by = (int)rint(py), bz = (int)rint(pz);
+                key[j] = (uint32_t)(bx + 512) + ((uint32_t)(by + 512) << 10) + ((uint32_t)(bz + 512) << 20);
                 // a sample whose key equals the previous sample's key is never looked up (world.py:95)
-                const bool fresh = !lvalid || bx[j] != lx || by[j] != ly || bz[j] != lz;
-                const bool need = fresh && in_zone(bx[j], by[j], bz[j]);
-                cv[j] = ld_s8_if(g + (need ? cell_of(bx[j], by[j], bz[j]) : 0), need);
-                lx = bx[j]; ly = by[j]; lz = bz[j];
+                const bool fr = !lvalid || key[j] != last;
+                const bool need = fr && in_zone(bx, by, bz);
+                cv[j] = ld_s8_if(g + (need ? cell_of(bx, by, bz) : 0), need);
+                const bool floor_hit = by == -2 && (unsigned)(bx + 18) <= 36u && (unsigned)(bz + 18) <= 36u;
+                fresh |= (unsigned)fr << j;
+                solid |= (unsigned)floor_hit << j;
+                last = key[j];
                 lvalid = true;
                 px = px + sx; py = py + syy; pz = pz + sz;
             }
-            unsigned solid = 0;
 #pragma unroll
-            for (int j = 0; j < 8; j++) solid |= (unsigned)world_has(cv[j], bx[j], by[j], bz[j]) << j;
+            for (int j = 0; j < 8; j++) solid |= (unsigned)(cv[j] != 0) << j;  // cv is 0 for keys outside the zone
+            const unsigned hm = fresh & solid;
+            if (hm) {  // first fresh sample whose key is in the world: (block, previous) = (its key, the key before)
+                hit = true;
+                const int jh = __ffs(hm) - 1;
+                kkey = key[0]; qkey = last_in; has_prev = lvalid_in;
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (!hit) {
-                    kx = bx[j]; ky = by[j]; kz = bz[j];
-                    const bool differs = !has_prev || kx != qx || ky != qy || kz != qz;
-                    if (differs && ((solid >> j) & 1u)) {
-                        hit = true;
-                    } else {
-                        qx = kx; qy = ky; qz = kz;
-                        has_prev = true;
-                    }
-                }
+                for (int j = 1; j < 8; j++)
+                    if (jh == j) { kkey = key[j]; qkey = key[j - 1]; has_prev = true; }
             }
         }
+        const int kx = (int)(kkey & 1023u) - 512, ky = (int)((kkey >> 10) & 1023u) - 512, kz = (int)(kkey >> 20) - 512;
+        const int qx = (int)(qkey & 1023u) - 512, qy = (int)((qkey >> 10) & 1023u) - 512, qz = (int)(qkey >> 20) - 512;
         int cell = -1, newv = 0;
         if (act.add) {
             if (hit && has_prev) {
