@@ -31,7 +31,16 @@ namespace iglu {
 #define IGLU_RING 4
 #endif
 constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
-constexpr int CTA_THREADS = WARPS_PER_CTA * 32;
+#ifndef IGLU_MI_WARPS
+#define IGLU_MI_WARPS 24
+#endif
+#ifndef IGLU_MI_CTAS
+#define IGLU_MI_CTAS 1
+#endif
+// stateless reward sweep: one 24-warp CTA per SM (198 KB of shared memory). Measured on 1 M pairs, compact rho=0.2:
+// 8x2 warps 2.38 ms, 10x2 2.24, 12x2 2.10, 24x1 1.97, 27x1 1.97 (profiles/r01_mi_occupancy_variants.log)
+constexpr int MI_WARPS = IGLU_MI_WARPS;
+constexpr int MI_CTAS = IGLU_MI_CTAS;
 constexpr int CTAS_PER_SM = 2;   // 16 warps / SM: measured faster than 20 / 24 / 32 warps with fewer registers (profiles/)
 constexpr int NB = IGLU_RING;    // TMA ring depth per warp
 constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
@@ -728,7 +737,7 @@ __device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list,
 }
 
 template <bool CLIP, bool WANT_KEY>
-__global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(const int8_t *__restrict__ grids,
+__global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
                                                                      const int8_t *__restrict__ fulls,
                                                                      int invariant, int32_t *__restrict__ out,
@@ -738,7 +747,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
     PairScratch *scratch = reinterpret_cast<PairScratch *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     PairScratch &ps = scratch[wid];
-    build_spread_table(tbl, threadIdx.x, CTA_THREADS);
+    build_spread_table(tbl, threadIdx.x, MI_WARPS * 32);
     __syncthreads();
     const int64_t total_bytes = count * CELLS;
     auto last_word_of = [&](const int8_t *base) {
@@ -746,8 +755,7 @@ __global__ void __launch_bounds__(CTA_THREADS, CTAS_PER_SM) k_max_intersection(c
     };
     const uint32_t *glast = last_word_of(grids), *tlast = last_word_of(targets);
     const uint32_t *flast = fulls ? last_word_of(fulls) : nullptr;
-    for (int64_t pr = (int64_t)blockIdx.x * WARPS_PER_CTA + wid; pr < count;
-         pr += (int64_t)gridDim.x * WARPS_PER_CTA) {
+    for (int64_t pr = (int64_t)blockIdx.x * MI_WARPS + wid; pr < count; pr += (int64_t)gridDim.x * MI_WARPS) {
         load_cells_smem(ps.grid, grids + pr * CELLS, glast, lane);
         load_cells_smem(ps.tgt, targets + pr * CELLS, tlast, lane);
         __syncwarp();
@@ -1063,7 +1071,7 @@ static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *f
     int rc = check(cudaFuncSetAttribute(k_max_intersection<CLIP, WANT_KEY>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
-    k_max_intersection<CLIP, WANT_KEY><<<grid, CTA_THREADS, smem, s>>>(grids, targets, fulls, invariant, out,
+    k_max_intersection<CLIP, WANT_KEY><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, invariant, out,
                                                                         argmax, count);
     return check(cudaPeekAtLastError());
 }
@@ -1075,9 +1083,9 @@ extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets,
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return IGLU_ERR_CUDA;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IGLU_ERR_CUDA;
-    const size_t smem = TABLE_BYTES + WARPS_PER_CTA * sizeof(PairScratch);
-    const int64_t ctas = (count + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    const int64_t resident = (int64_t)sms * CTAS_PER_SM;
+    const size_t smem = TABLE_BYTES + MI_WARPS * sizeof(PairScratch);
+    const int64_t ctas = (count + MI_WARPS - 1) / MI_WARPS;
+    const int64_t resident = (int64_t)sms * MI_CTAS;
     const unsigned grid = (unsigned)(ctas < resident ? ctas : resident);
     cudaStream_t s = (cudaStream_t)stream;
     const bool clip = fulls && invariant;
