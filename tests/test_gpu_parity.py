@@ -540,6 +540,47 @@ def test_step_host_routes():
         assert torch.equal(env.grid, ref.grid) and torch.equal(env._pose, ref._pose)
 
 
+@pytest.mark.parametrize('reward_mode', ['on_change', 'every_step'])
+def test_step_is_cuda_graph_capturable(reward_mode):
+    """The step entry points only enqueue work on the caller's stream (no allocation, no sync), so a sequence of
+    steps can be captured once and replayed; replays equal eager stepping."""
+    import gridworld_b200 as gw
+    n, per = 700, 6
+    rng = np.random.RandomState(41)
+    T, S, poses = _tasks(rng, n)
+    eager = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+    eager.set_tasks(T, S, poses)
+    graphed = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+    graphed.set_tasks(T, S, poses)
+    acts = torch.zeros(per, n, dtype=torch.int32, device='cuda')  # static input buffer of the graph
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):  # warm-up on a side stream (lazy module loading must not happen during capture)
+        warm = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+        warm.set_tasks(T, S, poses)
+        warm.step(acts[0])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    rsum = torch.zeros(n, dtype=torch.float64, device='cuda')
+    with torch.cuda.graph(g):
+        for k in range(per):
+            _, r, _, _ = graphed.step(acts[k])
+            rsum += r
+    # the capture itself does not execute anything: state is still the reset state
+    want = torch.zeros(n, dtype=torch.float64, device='cuda')
+    for rep in range(7):
+        a = torch.as_tensor(rng.randint(0, 18, (per, n)).astype(np.int32), device='cuda')
+        acts.copy_(a)
+        g.replay()
+        for k in range(per):
+            _, r, _, _ = eager.step(a[k])
+            want += r
+    torch.cuda.synchronize()
+    assert torch.equal(rsum, want)
+    assert torch.equal(graphed.grid, eager.grid) and torch.equal(graphed._pose, eager._pose)
+    assert torch.equal(graphed._istate, eager._istate)
+
+
 def test_full_size_invariants():
     """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
     import gridworld_b200 as gw
