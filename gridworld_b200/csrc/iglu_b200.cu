@@ -1,16 +1,21 @@
 // iglu_b200.cu -- sm_100a kernels + C ABI (include/iglu_b200.h) of the IGLU Gridworld step path.
 //
-// k_step: one warp owns 32 consecutive envs ("group"), persistent CTAs loop over groups.
-//   phase A (one thread per env): auto-reset, action parse, World.step in fp64 (iglu_physics.cuh),
-//            small observations (agentPos / inventory / compass);
-//   phase B (warp-cooperative, one env at a time): the env's int8 grid and its target block list are
-//            brought into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) through a
-//            4-deep per-warp ring that is filled BEFORE phase A, so the HBM latency hides behind the
-//            physics; the grid is widened into the int32 obs['grid'] with 16-byte streaming stores and
+// k_step<KIND, PHASES>: one source, three instantiations (launch_step picks):
+//   PHASES = 1  physics launch: phase A only (one thread per env, no shared memory);
+//   PHASES = 2  observe launch: phases B + C, persistent 16-warp CTAs, env groups handed out dynamically;
+//   PHASES = 3  fused launch:   A + B + C, the TMA ring filled BEFORE phase A so that the HBM latency hides
+//               behind the physics.
+//   phase A (one thread per env): auto-reset (drawing from the task pool when one is attached), action parse,
+//            World.step in fp64 (iglu_physics.cuh), small observations (agentPos / inventory / compass);
+//   phase B (warp-cooperative, one env at a time): the env's int8 grid and its target block list are brought
+//            into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) through a per-warp ring; the
+//            grid is widened into the int32 obs['grid'] with 16-byte streaming stores and
 //            Task.maximal_intersection is evaluated (iglu_reward.cuh) when required;
 //   phase C (one thread per env): Task.step_intersection bookkeeping, reward, done (task.py:103-119,
 //            env.py:290-296).
-// No collective, no host round trip; every entry point only enqueues work on the caller's stream.
+// k_task_prep (Task.__init__), k_reset (GridWorld.reset), k_max_intersection (stateless reward sweep).
+// No collective, no host round trip; every entry point only enqueues work on the caller's stream
+// (iglu_step_walking_host additionally synchronises it).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -67,7 +72,7 @@ struct StepParams {
     double *reward_host;       // mapped pinned host copies of obs.reward / obs.done (iglu_step_walking_host), or null
     uint8_t *done_host;
     int dynamic;               // observe launch: groups handed out through st.sched[0] instead of a static deal
-    int group;                 // envs per warp: 32, or 16 when there are too few envs to fill the SMs
+    int group;                 // envs per group (<= 32): a warp handles one group at a time, lane j <-> env j of it
 };
 
 // ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------

@@ -33,8 +33,15 @@ def _worker(rank, world, port, tmpdir):
     for t in range(steps):
         rew[t], _ = b.step_walking(acts[t, lo:hi], auto_reset=True)
     D.barrier()
+    # task generator: a shard passes env_offset = lo, so its envs draw what they draw in the unsharded batch
+    g = O.OracleBatch(hi - lo, 'walking', max_steps=7)
+    g.set_pool(T[:13], None, seed=99, env_offset=lo)
+    g.reset()
+    grew = np.zeros((steps, hi - lo))
+    for t in range(steps):
+        grew[t], _ = g.step_walking(acts[t, lo:hi], auto_reset=True)
     np.savez(os.path.join(tmpdir, f'shard{rank}.npz'), lo=lo, hi=hi, rew=rew, grid=b.state()['grid'],
-             pos=b.state()['pos'])
+             pos=b.state()['pos'], grew=grew, gids=g.task_ids.copy(), ggrid=g.state()['grid'])
     # timing helpers: the slowest rank defines the time, the env counts add up
     assert D.max_over_ranks(1.0 + rank) == float(world)
     assert D.sum_over_ranks(hi - lo) == float(n)
@@ -62,6 +69,15 @@ def test_two_ranks_shard_and_concatenate(tmp_path):
     assert np.array_equal(np.concatenate([s['rew'] for s in shards], axis=1), rew)
     assert np.array_equal(np.concatenate([s['grid'] for s in shards]), full.state()['grid'])
     assert np.array_equal(np.concatenate([s['pos'] for s in shards]), full.state()['pos'])
+    gfull = O.OracleBatch(n, 'walking', max_steps=7)
+    gfull.set_pool(T[:13], None, seed=99, env_offset=0)
+    gfull.reset()
+    grew = np.zeros((steps, n))
+    for t in range(steps):
+        grew[t], _ = gfull.step_walking(acts[t], auto_reset=True)
+    assert np.array_equal(np.concatenate([s['grew'] for s in shards], axis=1), grew)
+    assert np.array_equal(np.concatenate([s['gids'] for s in shards]), gfull.task_ids)
+    assert np.array_equal(np.concatenate([s['ggrid'] for s in shards]), gfull.state()['grid'])
     # uneven split
     assert [D.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
 
