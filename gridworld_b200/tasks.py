@@ -2,6 +2,8 @@
 task_set.py). They only carry data; maximal_intersection / argmax_intersection run on the GPU
 through iglu_max_intersection, and inside an env the synthetic task is prepared on the device by
 iglu_set_tasks (rotations, admissible rectangles, block list)."""
+import io
+import pickle
 import uuid
 
 import numpy as np
@@ -343,3 +345,75 @@ class Subtasks(Tasks):
         self.task_id = None
         self.current = task
         return self.current
+
+
+# ---------------------------------------------------------------------------------------------------
+# Feeding task collections to the device-resident task generator (IGLUVecEnv.set_task_pool)
+
+def enumerate_tasks(tasks):
+    """All Task objects of a Task / Tasks-like collection, in a stable order.
+
+    Handles the reference's container shapes: objects with a `.tasks` dict or list (CustomTasks, RandomTasks with
+    max_cache > 0 -- whose __iter__ yields dict KEYS in the reference, task_set.py:107-109), Subtasks (one Task
+    per turn, task.py:251-253), a plain Task, or any iterable of Tasks."""
+    if isinstance(tasks, Task):
+        return [tasks]
+    inner = getattr(tasks, '__dict__', {}).get('tasks')
+    if isinstance(inner, dict):
+        return [t for v in inner.values() for t in enumerate_tasks(v)]
+    if isinstance(inner, (list, tuple)):
+        return [t for v in inner for t in enumerate_tasks(v)]
+    out = []
+    for t in tasks:
+        out.extend(enumerate_tasks(t) if not isinstance(t, Task) else [t])
+    return out
+
+
+def pool_arrays(tasks):
+    """(targets int8 [m, 9, 11, 11], starts int8 [m, 9, 11, 11], chats list[str]) of a task collection: the
+    inputs of IGLUVecEnv.set_task_pool (starting_grid None is treated as [] like everywhere in this package)."""
+    ts = enumerate_tasks(tasks)
+    if not ts:
+        raise ValueError('empty task collection')
+    targets = np.zeros((len(ts), *BUILD_ZONE_SIZE), np.int8)
+    starts = np.zeros((len(ts), *BUILD_ZONE_SIZE), np.int8)
+    chats = []
+    for i, t in enumerate(ts):
+        targets[i] = np.asarray(t.target_grid).astype(np.int8)
+        sg = t.starting_grid
+        if sg is not None and len(sg) > 0:
+            starts[i] = np.asarray(Tasks.to_dense([tuple(int(v) for v in b) for b in sg])).astype(np.int8)
+        chats.append(t.chat)
+    return targets, starts, chats
+
+
+class _GoalsUnpickler(pickle.Unpickler):
+    """goals.pkl holds {name: [(x, y, z, colour), ...]} with numpy integer scalars: only
+    what is needed to rebuild those is allowed, so that loading a file cannot run arbitrary code."""
+    _ALLOWED = {('numpy.core.multiarray', 'scalar'), ('numpy._core.multiarray', 'scalar'), ('numpy', 'dtype'),
+                ('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+                ('numpy', 'ndarray'), ('builtins', 'tuple'), ('builtins', 'list'), ('builtins', 'dict'),
+                ('collections', 'OrderedDict')}
+
+    def find_class(self, module, name):
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f'goals file refers to {module}.{name}: not allowed')
+
+
+def load_goals(path):
+    """Reads a structure file in the format of the reference's skills/goals.pkl and returns CustomTasks-style
+    goals [(name, [(x, y, z, colour), ...]), ...] sorted by name (C1, C2, ...)."""
+    with open(path, 'rb') as f:
+        raw = f.read()
+    goals = _GoalsUnpickler(io.BytesIO(raw)).load()
+    if not isinstance(goals, dict):
+        raise ValueError('goals file must hold a dict name -> block list')
+
+    def key(nm):
+        digits = ''.join(ch for ch in str(nm) if ch.isdigit())
+        return (int(digits) if digits else 0, str(nm))
+    out = []
+    for nm in sorted(goals.keys(), key=key):
+        out.append((str(nm), [tuple(int(v) for v in b) for b in goals[nm]]))
+    return out

@@ -117,6 +117,7 @@ class IGLUVecEnv:
         self._L = _lib.load()
         self._tasks_set = False
         self._pool = None
+        self.dialogs = None
 
         dev = self.device
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -275,6 +276,19 @@ class IGLUVecEnv:
         self._pool = bufs  # the ctx retains these device pointers: keep the tensors alive
         self._tasks_set = True
         return self.reset() if reset else None
+
+    def set_task_generator(self, tasks, seed=0, env_offset=0, next_task=None, reset=True):
+        """env.set_task_generator (reference env.py:166-172) for a task COLLECTION (Task, CustomTasks, RandomTasks
+        with max_cache > 0, Subtasks, or any iterable of Tasks): its tasks are enumerated once into the
+        device-resident pool (set_task_pool) and every reset draws one of them on the device.
+        obs['dialog'] of env e is `self.dialogs[self.task_ids[e]]` (kept on the host, like the reference)."""
+        from .tasks import pool_arrays
+        if tasks is None:
+            self.dialogs = None
+            return self.set_task_pool(None)
+        targets, starts, chats = pool_arrays(tasks)
+        self.dialogs = chats
+        return self.set_task_pool(targets, starts, seed=seed, env_offset=env_offset, next_task=next_task, reset=reset)
 
     @property
     def task_ids(self):

@@ -463,6 +463,32 @@ def test_task_generator_batch_vs_oracle(reward_mode, grid_obs):
     assert len(np.unique(orc.task_ids)) > m // 2
 
 
+def test_set_task_generator_from_task_collection():
+    """set_task_generator(collection): the collection is enumerated into the device pool; targets / starting grids /
+    dialogs of the drawn tasks are what the host objects say."""
+    import gridworld_b200 as gw
+    z = G.load('goals.npz')
+    names = [str(nm) for nm in z['names'][:20]]
+    start = [(0, -1, 1, 3), (1, -1, 1, 4)]
+    tasks = [gw.Task(nm, z['targets'][i].astype(np.int32), starting_grid=start if i % 3 == 0 else [])
+             for i, nm in enumerate(names)]
+    n = 256
+    env = gw.make_vec(n, max_steps=5, target_in_obs=True)
+    obs = env.set_task_generator(tasks, seed=3)
+    T, S, chats = gw.pool_arrays(tasks)
+    for t in range(12):  # two auto-resets per env
+        ids = env.task_ids.cpu().numpy()
+        assert np.array_equal(obs['target_grid'].cpu().numpy(), T[ids].astype(np.int32))
+        assert np.array_equal(env.starting_grid.cpu().numpy(), S[ids])
+        assert [env.dialogs[j] for j in ids[:5]] == [names[j] for j in ids[:5]]
+        obs, _, _, _ = env.step(np.zeros(n, np.int32))
+    ids = env.task_ids.cpu().numpy()
+    assert len(np.unique(ids)) > 10
+    inv = env.inventory.cpu().numpy()  # envs whose task has the 2-block starting grid hold 19 of colours 3 and 4
+    has = (ids % 3 == 0)
+    assert (inv[has][:, 2] == 19).all() and (inv[has][:, 3] == 19).all() and (inv[~has] == 20).all()
+
+
 def test_task_generator_sharding_and_checkpoint():
     """env_offset makes shards draw what the single-device run draws; state_dict carries the cursor."""
     import gridworld_b200 as gw

@@ -104,3 +104,44 @@ def test_spaces():
     assert ob['grid'].shape == (9, 11, 11) and ob['grid'].dtype == np.int32
     assert ob['agentPos'].shape == (5,) and ob['target_grid'].shape == (9, 11, 11)
     assert fl.contains(fl.sample())
+
+
+def test_pool_arrays_and_goal_file_loader(tmp_path):
+    """Task collections -> the arrays IGLUVecEnv.set_task_pool takes; goals.pkl-format loader (restricted unpickler)."""
+    import pickle
+    from gridworld_b200.tasks import CustomTasks, Task, Tasks, enumerate_tasks, load_goals, pool_arrays
+    from tests import golden_io as G
+    z = G.load('goals.npz')
+    dense = z['targets'][:12]
+    goals = {}
+    for nm, t in zip(z['names'][:12], dense):
+        goals[str(nm)] = [(np.int64(x - 5), np.int64(y - 1), np.int64(zz - 5), np.int64(t[y, x, zz]))
+                          for y, x, zz in np.argwhere(t)]
+    path = tmp_path / 'goals.pkl'
+    path.write_bytes(pickle.dumps(goals))
+    loaded = load_goals(str(path))
+    assert [nm for nm, _ in loaded] == sorted(goals, key=lambda s: int(s[1:]))
+    for nm, blocks in loaded:
+        assert all(type(v) is int for b in blocks for v in b)
+        assert np.array_equal(np.asarray(Tasks.to_dense(blocks)).astype(np.int8), dense[list(z['names'][:12]).index(nm)])
+    # pool arrays of a plain list of Tasks (with and without starting grids) and of a CustomTasks collection
+    start = [(0, -1, 1, 3), (1, -1, 1, 4)]
+    tasks = [Task(nm, np.asarray(Tasks.to_dense(blocks)), starting_grid=start if i % 2 else [])
+             for i, (nm, blocks) in enumerate(loaded)]
+    T, S, chats = pool_arrays(tasks)
+    order = [list(z['names'][:12]).index(nm) for nm, _ in loaded]
+    assert T.dtype == np.int8 and np.array_equal(T, dense[order]) and chats == [nm for nm, _ in loaded]
+    assert S[0].sum() == 0 and S[1][0, 5, 6] == 3 and S[1][0, 6, 6] == 4 and np.count_nonzero(S[1]) == 2
+    np.random.seed(0)
+    ct = CustomTasks(loaded)
+    assert len(enumerate_tasks(ct)) == 12
+    assert np.array_equal(np.sort(pool_arrays(ct)[0].reshape(12, -1), axis=0), np.sort(dense.reshape(12, -1), axis=0))
+    # a pickle that wants to import anything else is refused before it can run
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ('echo pwned',))
+    bad = tmp_path / 'bad.pkl'
+    bad.write_bytes(pickle.dumps({'C1': Evil()}))
+    with pytest.raises(pickle.UnpicklingError):
+        load_goals(str(bad))
