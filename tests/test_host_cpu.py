@@ -145,3 +145,22 @@ def test_pool_arrays_and_goal_file_loader(tmp_path):
     bad.write_bytes(pickle.dumps({'C1': Evil()}))
     with pytest.raises(pickle.UnpicklingError):
         load_goals(str(bad))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints ONE JSON line with the
+    contract's keys; it never touches CUDA."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '3',
+                          '--warmup', '1'], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'env_steps_per_sec' and d['unit'] == 'env-steps/s'
+    assert d['higher_is_better'] is True and d['steps'] == 3 and d['value'] > 0 and d['ms_per_step'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
