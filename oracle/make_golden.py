@@ -337,6 +337,11 @@ def scripted_walking():
     out.append(dict(name='odd_rotation', cfg=dict(action_space='walking', target=T2,
                                                   pose=(0.3, -0.25, 0.1, 33.3, -41.7)),
                     a=[1, 1, 3, 17, 2, 4, 16, 13, 1, 17, 14, 14, 17, 5, 1, 1, 1]))
+    # spawned outside the 37 x 37 floor: nothing below, the agent falls at terminal velocity for the whole episode
+    # (y ~ -600: ray-cast keys far outside any table; every action kind keeps being applied), then the auto-reset
+    a = [17, 1, 16, 13, 5, 6, 14, 3, 0, 12, 9, 4, 15, 2] * 20
+    out.append(dict(name='void_fall', cfg=dict(action_space='walking', target=T2, pose=(25.0, 1.0, -22.0, 45.0, -30.0)),
+                    a=a[:270]))
     return out
 
 
