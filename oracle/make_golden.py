@@ -337,6 +337,11 @@ def scripted_walking():
     out.append(dict(name='odd_rotation', cfg=dict(action_space='walking', target=T2,
                                                   pose=(0.3, -0.25, 0.1, 33.3, -41.7)),
                     a=[1, 1, 3, 17, 2, 4, 16, 13, 1, 17, 14, 14, 17, 5, 1, 1, 1]))
+    # building-zone border: place / break attempts on the floor outside the 11 x 11 zone (rejected, world.py:318),
+    # on the border column, breaking the WHITE / GREY floor (not removable), then the same inside
+    a = [4] * 24 + [14] * 18 + [17, 16, 17] + [3] * 4 + [17, 16] + [3] * 4 + [17, 5, 17, 16, 16] + [15] * 6 + [17, 16] \
+        + [2] * 30 + [17, 16, 17] + [1] * 60 + [17, 16]
+    out.append(dict(name='border_place', cfg=dict(action_space='walking', target=T2, select_and_place=False), a=a))
     # spawned outside the 37 x 37 floor: nothing below, the agent falls at terminal velocity for the whole episode
     # (y ~ -600: ray-cast keys far outside any table; every action kind keeps being applied), then the auto-reset
     a = [17, 1, 16, 13, 5, 6, 14, 3, 0, 12, 9, 4, 15, 2] * 20
