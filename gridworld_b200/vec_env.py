@@ -221,6 +221,7 @@ class IGLUVecEnv:
                                               pp(ip), pp(idx), k, self._stream()))
             self._count()
         self._tasks_set = True
+        self._check_block_capacity(self._tmeta)
         if reset:
             mask = None
             if idx is not None:
@@ -273,6 +274,7 @@ class IGLUVecEnv:
                                                       None if s is None else s.data_ptr(), self._stream()))
             self._count()
             _lib.check(self._L.iglu_task_pool_attach(self._ctx, C.byref(pool)))
+        self._check_block_capacity(bufs['tmeta'])
         self._pool = bufs  # the ctx retains these device pointers: keep the tensors alive
         self._tasks_set = True
         return self.reset() if reset else None
@@ -297,6 +299,15 @@ class IGLUVecEnv:
         if getattr(self, '_pool', None) is None:
             raise ValueError('no task pool attached')
         return self._pool['cursor'][0]
+
+    def _check_block_capacity(self, tmeta):
+        """A block list longer than the row capacity chosen with max_target_blocks would be truncated by the
+        device-side Task.__init__; refuse instead (only checked when the capacity is below the 1089-cell maximum,
+        because it needs a device -> host read)."""
+        room = self._tlist.shape[1] - _lib.TLIST_HDR
+        if room < _lib.CELLS and bool((tmeta[1] > room).any()):
+            raise ValueError(f'a task has {int(tmeta[1].max())} blocks to place / remove but max_target_blocks '
+                             f'allows {room}; create the env with a larger max_target_blocks')
 
     def _check_task(self):
         if not self._tasks_set:

@@ -607,6 +607,17 @@ def test_step_is_cuda_graph_capturable(reward_mode):
     assert torch.equal(graphed._istate, eager._istate)
 
 
+def test_block_list_capacity_is_enforced():
+    import gridworld_b200 as gw
+    rng = np.random.RandomState(2)
+    env = gw.make_vec(8, max_target_blocks=64)
+    env.set_tasks(_synth(rng, 8, 0.03, 'full'))          # ~33 blocks: fits
+    with pytest.raises(ValueError, match='max_target_blocks'):
+        env.set_tasks(_synth(rng, 8, 0.3, 'full'))       # ~330 blocks: refused, not truncated
+    with pytest.raises(ValueError, match='max_target_blocks'):
+        env.set_task_pool(_synth(rng, 5, 0.3, 'full'))
+
+
 def test_full_size_invariants():
     """BASELINE config 2 size (65,536 envs): properties that need no oracle."""
     import gridworld_b200 as gw
