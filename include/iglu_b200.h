@@ -12,10 +12,12 @@
  * Conventions
  *  - Every pointer in iglu_state / iglu_obs and every array argument is DEVICE memory owned by
  *    the caller (PyTorch hands the tensors out) unless the name ends in _host.  The library
- *    allocates nothing persistent except the small iglu_ctx (config copy + trig tables).
+ *    allocates nothing persistent except the small iglu_ctx (config copy + trig tables); the only
+ *    pointers it retains between calls are those of an attached iglu_task_pool.
  *  - All work is enqueued on the caller's stream (a cudaStream_t passed as void*); device-
  *    buffer entry points never synchronise, so they are CUDA-graph capturable.  *_host entry
- *    points copy host<->device on that stream and synchronise it before returning.
+ *    points move their host buffers on that stream (pinned buffers: directly from the kernels
+ *    over PCIe; pageable ones: staged copies) and synchronise it before returning.
  *  - Return value: IGLU_OK (0) or a negative iglu_status; iglu_strerror() describes it.
  *  - Grids are int8, cell (y, x, z) of env i at  i * IGLU_GRID_STRIDE + y*121 + x*11 + z
  *    (dense index = [y+1, x+5, z+5] of the world block (x, y, z), reference env.py:136-142);
