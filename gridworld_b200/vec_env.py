@@ -158,7 +158,6 @@ class IGLUVecEnv:
         with torch.cuda.device(dev):
             _lib.check(self._L.iglu_ctx_create(C.byref(cfg), C.byref(self._ctx)))
         self.gpu_launches = 0  # kernels launched by this env so far
-        self._host_ok = set()
         self._st_ref, self._ob_ref = C.byref(self._st), C.byref(self._ob)
         self._actions_ptr = self._actions_dev.data_ptr()
 
@@ -373,17 +372,18 @@ class IGLUVecEnv:
         """End-to-end host-buffer step (walking Discrete): actions int32 [n] in (pinned) host memory are
         copied to the device, the step runs, reward (float64 [n]) / done (uint8 [n]) are copied back
         into the given host tensors and the stream is synchronised. Observations stay on the device."""
-        pa, pr, pd = actions_host.data_ptr(), reward_host.data_ptr(), done_host.data_ptr()
-        if (pa, pr, pd) not in self._host_ok:  # validate a buffer triple once: this call is latency-critical
+        if not self._tasks_set:
             self._check_task()
-            if self._kind != _lib.WALKING_DISCRETE:
-                raise NotImplementedError('step_host is provided for the Discrete(18) action space')
-            for t, dt in ((actions_host, torch.int32), (reward_host, torch.float64), (done_host, torch.uint8)):
-                if t.device.type != 'cpu' or t.dtype != dt or not t.is_contiguous() or t.numel() != self.num_envs:
-                    raise ValueError('step_host needs contiguous CPU tensors of dtype int32 / float64 / uint8, [n]')
-            if len(self._host_ok) > 4096:
-                self._host_ok.clear()
-            self._host_ok.add((pa, pr, pd))
+        if self._kind != _lib.WALKING_DISCRETE:
+            raise NotImplementedError('step_host is provided for the Discrete(18) action space')
+        n = self.num_envs
+        # validated on every call (a cache keyed by address would go stale when buffers are freed and reused)
+        if (actions_host.dtype != torch.int32 or reward_host.dtype != torch.float64 or done_host.dtype != torch.uint8
+                or actions_host.numel() != n or reward_host.numel() != n or done_host.numel() != n
+                or not (actions_host.is_contiguous() and reward_host.is_contiguous() and done_host.is_contiguous())
+                or actions_host.is_cuda or reward_host.is_cuda or done_host.is_cuda):
+            raise ValueError('step_host needs contiguous CPU tensors of dtype int32 / float64 / uint8, [n]')
+        pa, pr, pd = actions_host.data_ptr(), reward_host.data_ptr(), done_host.data_ptr()
         with self._guard():
             rc = self._L.iglu_step_walking_host(self._ctx, self._st_ref, pa, self._actions_ptr, self._ob_ref,
                                                 pr, pd, self._stream())
