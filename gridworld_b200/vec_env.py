@@ -71,11 +71,14 @@ class IGLUVecEnv:
       on every step; outputs are identical), grid_obs (True: rewrite the int32 obs['grid'] in full every step;
       'incremental': keep the persistent obs['grid'] buffer up to date cell by cell -- same contents, ~20x
       fewer bytes; False: no int32 copy, obs['grid'] is the int8 state view),
-      alternate_phases (scheduling only: half of the warps write observations before the physics),
-      split_launch (scheduling only: physics and observation/reward as two launches when every env needs
-      observation or reward work).
+      alternate_phases (scheduling only: in the fused launch half of the warps write observations before the
+      physics), split_launch (scheduling only: True = the library's measured policy -- physics and
+      observation/reward as two launches except for on_change reward with a full obs rewrite; False = always one
+      fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list).
 
     step() returns device tensors that alias persistent buffers: a policy reads them in place.
+    set_tasks / set_task_pool / set_task_generator assign tasks (the latter two keep a device-resident generator
+    that every reset draws from); step_host is the host-buffer form of step (actions in, reward / done out).
     """
 
     def __init__(self, num_envs, device='cuda', action_space='walking', discretize=True,
