@@ -2,25 +2,37 @@
 """bench.py -- env-steps/sec of the IGLU Gridworld step path (BASELINE.json metric) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
-    python bench.py --impl reference [--gpus N] ...                # the CPU arm (oracle port, all host threads)
+    python bench.py --impl reference [--gpus N] ...                # the CPU arm (the reference itself, all host cores)
     torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, envs sharded, no collective
 
-Workload (config.workload): BASELINE.json configs[1] -- walking Discrete(18), 65,536 envs per GPU,
+Headline workload (config.workload): BASELINE.json configs[1] -- walking Discrete(18), 65,536 envs per GPU,
 random synthetic target structures (SURVEY 8(d) generator, compact support, density 0.20: ~25 blocks and
-~196 admissible (rotation, shift) pairs per task, close to the real goals.pkl mix), uniform random
-actions, full maximal_intersection evaluated on EVERY step, int32 obs['grid'] materialised every step,
-auto-reset on done. A "step" = one call of the step path over all envs of the rank.
+~196 admissible (rotation, shift) pairs per task, close to the real goals.pkl mix), uniform random actions,
+full maximal_intersection evaluated on EVERY step for every env whose grid is non-empty, int32 obs['grid']
+materialised every step, auto-reset on done.
+
+What is timed. Whatever --warmup says, the envs are first brought, untimed, into a DESYNCHRONISED STEADY STATE:
+env e is reset at step phase[e] (uniform over one 250-step episode) of a pre-roll, so that afterwards 1/250 of the
+envs reset on every step and the block-count distribution is the stationary one of the workload. (Timing the
+first steps after a common reset measures empty grids: there the reward evaluation is skipped for ~98 % of the
+envs.) `config.evaluated_frac` is the fraction of env-steps of the timed window in which maximal_intersection
+really ran, counted on the device. The `dense` object is the same step on worlds that all hold a half-built
+target (evaluated_frac = 1: what a policy that builds sees).
 
 value  = env-steps/s with the action tensors already resident in HBM (CUDA events, max over ranks).
-e2e    = the same metric through the host-buffer C-ABI call iglu_step_walking_host: every step takes the
-         int32 actions from pinned host memory and delivers reward (f64) + done (u8) into pinned host memory,
-         stream synchronised per step. The buffers are pinned, so the kernels move these bytes over PCIe
-         themselves (zero-copy reads / writes inside the step kernels) instead of staging them through
-         cudaMemcpyAsync before / after the step; `e2e.staged_value` is the same call with the staged copies
-         forced. Observations stay on the device for an on-device policy (BASELINE configs[4]).
-roofline: HBM. achieved = A_walk * envs / mean step-kernel duration, A_walk = 5,634 algorithmic bytes per
-         env-step (4,413 B of observations/results written, 1,089 B grid + 4 B action read,
-         64 B state read + 64 B written), peak = MEASURED_PEAKS.json hbm_gbs.
+e2e    = the same metric through the host-buffer C-ABI call iglu_step_walking_host_async + iglu_wait: every
+         step takes the int32 actions from pinned host memory and delivers reward (f64) + done (u8) into pinned
+         host memory; the host needs a step's results before it issues that env group's next actions, and keeps
+         two env groups in flight (EnvPool-style) so that one group's host round trip hides under the other's
+         kernels. `e2e.sync_value` is the single-group, synchronise-every-step form.
+roofline: HBM. achieved = A_walk * envs / mean step duration, A_walk = 5,634 algorithmic bytes per env-step
+         (4,413 B of observations/results written, 1,089 B grid + 4 B action read, 64 B state read
+         + 64 B written), peak = MEASURED_PEAKS.json hbm_gbs.
+max_intersection: evals/s of the stateless sweep (config 4) on four workloads with an integer-pipe roofline
+         object each: achieved = evals/s x P_eval (SURVEY 8(d) popcount-ANDs per evaluation, computed from the
+         targets), peak = POPC thread-ops/s measured in this run by csrc/iglu_microbench.cu.
+config3 / config5: BASELINE.json configs[2] (flying + target_in_obs, 262,144 envs) and configs[4] (1,048,576
+         envs per GPU, in-place observations consumed by a torch policy on the device).
 """
 import argparse
 import json
@@ -35,24 +47,53 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 A_WALK_BYTES = 5634          # SURVEY 8(d) algorithmic bytes per walking env-step, materialised obs
+A_FLY_BYTES = 11103          # flying + target_in_obs as the reference does it (target re-copied per step)
+A_FLY_OURS = 5634 + 24       # what this implementation moves: obs['target_grid'] is written once by set_tasks
+A_INPLACE_BYTES = 189
 ENVS_PER_GPU = 65536         # BASELINE.json configs[1]
 DENSITY = 0.20
 MAX_STEPS = 250
 FALLBACK_HBM_GBS = 6650.0    # /opt/skills/guides/B200_PROFILING.md fallback
 
 
-def synth_targets(n, rho, support, seed):
-    """target = (u < rho) ? 1 + floor(6 v) : 0, u, v ~ U[0,1) from torch.Generator('cpu')."""
+def synth_targets(n, rho, support, seed, device='cpu'):
+    """target = (u < rho) ? 1 + floor(6 v) : 0, u, v ~ U[0,1) from a seeded torch.Generator
+    (CPU generator for env tasks and parity runs; device generator for the 1 M-pair throughput sweeps)."""
     import torch
-    g = torch.Generator('cpu').manual_seed(seed)
-    u = torch.rand(n, 9, 11, 11, generator=g)
-    v = torch.rand(n, 9, 11, 11, generator=g)
-    t = torch.where(u < rho, 1 + torch.floor(6 * v), torch.zeros(())).to(torch.int8)
+    g = torch.Generator(device).manual_seed(seed)
+    u = torch.rand(n, 9, 11, 11, generator=g, device=device)
+    v = torch.rand(n, 9, 11, 11, generator=g, device=device)
+    t = torch.where(u < rho, 1 + torch.floor(6 * v), torch.zeros((), device=device)).to(torch.int8)
     if support == 'compact':
-        m = torch.zeros(9, 11, 11, dtype=torch.bool)
+        m = torch.zeros(9, 11, 11, dtype=torch.bool, device=device)
         m[:5, 3:8, 3:8] = True
-        t = torch.where(m, t, torch.zeros((), dtype=torch.int8))
+        t = torch.where(m, t, torch.zeros((), dtype=torch.int8, device=device))
     return t
+
+
+def p_eval_mean(T):
+    """SURVEY 8(d) algorithmic work of one evaluation, mean over the targets T [m, 9, 11, 11]:
+    P_eval = sum_k S_k * NR_k with S_k the admissible shifts of rotation k (a rectangle given by the bounding
+    box) and NR_k the non-empty (class, y, x_k) rows of the rotated target."""
+    import torch
+    T = T.to(torch.int16)
+    occ = T != 0
+    ax = occ.any(dim=1).any(dim=2)       # [m, 11] x occupied
+    az = occ.any(dim=1).any(dim=1)       # [m, 11] z occupied
+    idx = torch.arange(11, device=T.device)
+
+    def span(a):
+        lo = torch.where(a, idx, 11).min(1).values
+        hi = torch.where(a, idx, -1).max(1).values
+        return lo, hi
+    xlo, xhi = span(ax)
+    zlo, zhi = span(az)
+    empty = ~ax.any(1)
+    S = (xlo - (xhi - 10) + 1) * (zlo - (zhi - 10) + 1)
+    S = torch.where(empty, torch.full_like(S, 441), S)
+    nr_x = sum(((T == c).any(dim=3)).flatten(1).sum(1) for c in range(1, 7))   # rows along x: rotations 0, 2
+    nr_z = sum(((T == c).any(dim=2)).flatten(1).sum(1) for c in range(1, 7))   # rows along z: rotations 1, 3
+    return float((S * (2 * nr_x + 2 * nr_z)).double().mean().item())
 
 
 class ClockSampler(threading.Thread):
@@ -79,22 +120,25 @@ class ClockSampler(threading.Thread):
              0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
              0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
 
+    def sample(self):
+        nv = self.nv
+        try:
+            self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            try:
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:  # noqa: BLE001
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.NAMES.items():
+                if r & bit and name != 'gpu_idle':
+                    self.reasons.add(name)
+        except Exception:  # noqa: BLE001
+            pass
+
     def run(self):
         if not self.ok:
             return
-        nv = self.nv
         while not self._stop_evt.is_set():
-            try:
-                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:  # noqa: BLE001
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.NAMES.items():
-                    if r & bit and name != 'gpu_idle':
-                        self.reasons.add(name)
-            except Exception:  # noqa: BLE001
-                pass
+            self.sample()
             time.sleep(self.period)
 
     def stop(self):
@@ -125,12 +169,12 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
 
 
-def recorded_traffic():
-    """dram bytes per launch of the step kernel from the committed ncu --set full capture, or None."""
-    p = os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')
+def recorded(name, key):
+    """a figure taken from a committed ncu capture (profiles/<name>), or None."""
+    p = os.path.join(ROOT, 'profiles', name)
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get('dram_bytes_per_launch')
+            return json.load(open(p)).get(key)
         except Exception:  # noqa: BLE001
             return None
     return None
@@ -138,26 +182,99 @@ def recorded_traffic():
 
 WORKLOAD = (f'configs[1]: walking Discrete(18), {ENVS_PER_GPU} envs/GPU, synthetic compact targets rho={DENSITY} '
             f'(~25 blocks, ~196 admissible rot x shift), uniform random actions, maximal_intersection every step, '
-            f'int32 grid obs materialised, auto-reset, max_steps={MAX_STEPS}')
+            f'int32 grid obs materialised, auto-reset, max_steps={MAX_STEPS}, desynchronised steady state '
+            f'(env e reset at a uniform phase of a {MAX_STEPS}-step pre-roll)')
+
+PREROLL_EXTRA = 30   # steps after the last staggered reset of the pre-roll
 
 
-# --------------------------------------------------------------------------------------- CPU arm
+def phases(n, seed):
+    return np.random.RandomState(seed).randint(0, MAX_STEPS, n)
 
-def cpu_sample(n_envs, steps, threads, seed=1234 + 1, warmup=0):
-    """Times the oracle port (C restatement of the reference step) on `n_envs` envs of the workload."""
+
+# --------------------------------------------------------------------------------------- CPU arms
+
+def cpu_port_sample(n_envs, steps, threads, seed=1234 + 1, warmup=0, preroll=True):
+    """Times the oracle port (C restatement of the reference step) on `n_envs` envs of the workload, from the
+    same desynchronised steady state as the GPU arm."""
     from oracle import oracle as O
     T = synth_targets(n_envs, DENSITY, 'compact', seed).numpy()
     b = O.OracleBatch(n_envs, 'walking', select_and_place=True, max_steps=MAX_STEPS, threads=threads)
     b.set_tasks(T)
     rng = np.random.RandomState(0)
     acts = rng.randint(0, 18, (64, n_envs)).astype(np.int32)
-    for t in range(warmup):
-        b.step_walking(acts[t % 64], auto_reset=True)
+    t = 0
+    if preroll:
+        ph = phases(n_envs, 7)
+        for t in range(MAX_STEPS + PREROLL_EXTRA):
+            if t < MAX_STEPS:
+                b.reset((ph == t).astype(np.uint8))
+            b.step_walking(acts[t % 64], auto_reset=True)
+        t += 1
+    for k in range(warmup):
+        b.step_walking(acts[(t + k) % 64], auto_reset=True)
+    t += warmup
     t0 = time.perf_counter()
-    for t in range(steps):
-        b.step_walking(acts[t % 64], auto_reset=True)
+    for k in range(steps):
+        b.step_walking(acts[(t + k) % 64], auto_reset=True)
     dt = time.perf_counter() - t0
-    return n_envs * steps / dt, dt
+    evaluated = float((b.state()['grid'].reshape(n_envs, -1) != 0).any(1).mean())
+    return n_envs * steps / dt, dt, evaluated
+
+
+REF_DIR = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def python_reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, 'gridworld'))
+
+
+def _pyref_worker(args):
+    """One process = one UNMODIFIED reference env (render=False, vector_state=True) from baseline/_ref, driven
+    like examples/run_env.py: random Discrete(18) actions, reset on done. Returns the wall time of `steps` steps
+    after a warm-up (numba JIT) and a pre-roll to this env's own phase of the episode."""
+    idx, steps, warmup = args
+    os.environ['IGLU_REFERENCE_ROOT'] = REF_DIR
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'refharness'))
+    import load_reference
+    load_reference.load()
+    import gym
+    from gridworld.tasks import Task
+    env = gym.make('IGLUGridworld-v0', action_space='walking', render=False, vector_state=True, size_reward=False,
+                   select_and_place=True, max_steps=MAX_STEPS)
+    T = synth_targets(idx + 1, DENSITY, 'compact', 1234 + 1)[idx].numpy().astype(int)
+    env.set_task(Task('', T, starting_grid=[], invariant=True))
+    env.reset()
+    rng = np.random.RandomState(100 + idx)
+    pre = 200 + int(phases(idx + 1, 7)[idx]) + warmup
+    for _ in range(pre):
+        _, _, done, _ = env.step(int(rng.randint(18)))
+        if done:
+            env.reset()
+    _PYREF_BARRIER.wait()   # all workers start their timed region together
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, _, done, _ = env.step(int(rng.randint(18)))
+        if done:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+_PYREF_BARRIER = None
+
+
+def _pyref_init(barrier):
+    global _PYREF_BARRIER
+    _PYREF_BARRIER = barrier
+
+
+def python_reference_sample(steps, warmup, procs):
+    """env-steps/s of `procs` reference processes (one env each) stepping `steps` steps at the same time."""
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    with ctx.Pool(procs, initializer=_pyref_init, initargs=(ctx.Barrier(procs),)) as pool:
+        walls = pool.map(_pyref_worker, [(i, steps, warmup) for i in range(procs)], chunksize=1)
+    return procs * steps / max(walls), max(walls)
 
 
 def run_reference_arm(args):
@@ -165,25 +282,36 @@ def run_reference_arm(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # C port (always available): bounded sample, same steady state as the GPU arm
     n_envs = 8192
-    # size the per-step sample so that steps + warmup finish within a few minutes
-    rate, _ = cpu_sample(2048, 20, threads)
-    budget_s = 120.0
-    per_step = n_envs / rate
-    if per_step * (args.steps + args.warmup) > budget_s:
-        n_envs = max(256, int(rate * budget_s / (args.steps + args.warmup)) // 256 * 256)
-    value, dt = cpu_sample(n_envs, args.steps, threads, warmup=args.warmup)
+    rate, _, _ = cpu_port_sample(2048, 20, threads, preroll=False)
+    budget_s = 60.0
+    total_steps = args.steps + args.warmup + MAX_STEPS + PREROLL_EXTRA
+    if n_envs / rate * total_steps > budget_s:
+        n_envs = max(256, int(rate * budget_s / total_steps) // 256 * 256)
+    port_v, port_dt, port_eval = cpu_port_sample(n_envs, args.steps, threads, warmup=args.warmup)
+    port = {'value': port_v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
+            'sample': f'{n_envs} envs x {args.steps} steps, oracle/iglu_oracle.c (C restatement pinned bit-exact to '
+                      f'the executed reference), one pthread per core, reward gate as in the reference',
+            'nonempty_grid_frac': port_eval}
+    note = ('the reference is pure Python; its unmodified package (pip --target baseline/_ref, git-ignored) is timed '
+            'through its own gym.make / step API with one process per host core; cpu_port is its C restatement')
+    if python_reference_available():
+        value, wall = python_reference_sample(args.steps, args.warmup, threads)
+        base = {'value': value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'reference',
+                'sample': f'{threads} processes x 1 env x {args.steps} steps of the workload (unmodified Python '
+                          f'reference from baseline/_ref, render=False, vector_state=True)'}
+        ms = 1e3 * wall / args.steps
+    else:
+        value, base, ms = port_v, dict(port), 1e3 * port_dt / args.steps
+        note = 'baseline/_ref is absent on this box: the C restatement of the reference (oracle port) is timed instead'
     line = {
         'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': value, 'unit': 'env-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'envs_per_step_sample': n_envs,
-                   'note': 'reference is pure Python (cannot travel to the GPU box); this arm times its C '
-                           'restatement (oracle/iglu_oracle.c, pinned bit-exact to the executed reference) '
-                           'with one pthread per host core; reward gate as in the reference (on change)'},
-        'cpu_baseline': {'value': value, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                         'sample': f'{n_envs} envs x {args.steps} steps of the workload'},
+        'config': {'workload': WORKLOAD, 'note': note},
+        'cpu_baseline': base, 'cpu_port': port,
         'e2e': {'value': value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -191,6 +319,89 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
+
+def preroll(env, actions, n, seed):
+    """Desynchronise: env e is reset at pre-roll step phase[e]; afterwards 1/MAX_STEPS of the envs reset per step."""
+    import torch
+    ph = torch.as_tensor(phases(n, seed), device=env.device)
+    P = actions.shape[0]
+    for t in range(MAX_STEPS + PREROLL_EXTRA):
+        if t < MAX_STEPS:
+            env.reset((ph == t).to(torch.uint8))
+        env.step(actions[t % P])
+    return MAX_STEPS + PREROLL_EXTRA
+
+
+def timed_steps(env, step_fn, K, W, dev, barrier, mid=None):
+    """W untimed + K timed calls of step_fn(t); CUDA events on the launching stream. Returns (ms total,
+    evaluations counted on the device during the timed window)."""
+    import torch
+    for t in range(W):
+        step_fn(t)
+    barrier()
+    env.reset_evaluation_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        step_fn(W + t)
+    e1.record()
+    if mid is not None:
+        mid()   # the GPU is still working through the enqueued steps here
+    barrier()
+    return e0.elapsed_time(e1), env.evaluations
+
+
+def shard_state(sd, lo, hi):
+    """Envs [lo, hi) of an IGLUVecEnv.state_dict() (SoA arrays are [k][n], per-env rows [n][...])."""
+    out = {}
+    for k, v in sd.items():
+        if k in ('pose', 'init_pose', 'istate', 'tmeta'):
+            out[k] = v[:, lo:hi].contiguous()
+        elif k == 'was_reset':
+            out[k] = v
+        else:
+            out[k] = v[lo:hi].contiguous()
+    return out
+
+
+def int_peaks():
+    """thread-ops/s of the POPC(+IADD), LOP3, IADD3, IMAD chains measured by csrc/iglu_microbench.cu now."""
+    import ctypes as C
+    import torch
+    from gridworld_b200 import build as B
+    lib = C.CDLL(B.build_microbench())
+    out = (C.c_double * 4)()
+    lib.iglu_mb_int_peak.argtypes = [C.POINTER(C.c_double), C.c_void_p]
+    torch.cuda.synchronize()
+    if lib.iglu_mb_int_peak(out, None) != 0:
+        return None
+    return dict(zip(('popc', 'lop3', 'iadd3', 'imad'), [float(v) for v in out]))
+
+
+def reward_sweep(gw, D, dev, world, barrier, peaks, name, T, G, reps=5):
+    """evals/s of the stateless sweep on the pairs (G, T) + its integer-pipe roofline object."""
+    import torch
+    n = T.shape[0]
+    gw.max_intersection(G, T)
+    barrier()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record()
+    for _ in range(reps):
+        gw.max_intersection(G, T)
+    m1.record()
+    barrier()
+    ms = D.max_over_ranks(m0.elapsed_time(m1), dev) / reps
+    evals = world * n / (ms * 1e-3)
+    pe = p_eval_mean(T[:20000])
+    out = {'workload': name, 'pairs_per_gpu': n, 'ms': ms, 'evals_per_sec': evals, 'p_eval_mean': pe,
+           'hbm_gbs': evals / world * (2 * 1089 + 4) / 1e9}
+    if peaks:
+        ach = evals / world * pe
+        out['roofline'] = {'bound': 'int_pipe', 'achieved': ach, 'unit': 'popcount-ANDs/s (evals/s x P_eval)',
+                           'popc_peak': peaks['popc'], 'frac': ach / peaks['popc'],
+                           'alu_pipe_pct': recorded('max_intersection_ncu.json', 'alu_pipe_pct')}
+    return out
+
 
 def run_b200_arm(args):
     import torch
@@ -205,85 +416,112 @@ def run_b200_arm(args):
 
     import gridworld_b200 as gw
     n = args.envs
-    env = gw.make_vec(n, device=dev, action_space='walking', select_and_place=True, max_steps=MAX_STEPS,
-                      auto_reset=True, reward_mode=args.reward_mode, grid_obs=not args.inplace)
-    targets = synth_targets(n, DENSITY, args.support, 1234 + 1 + rank)
-    env.set_tasks(targets.to(dev))
-    P = 64
-    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
-    actions = torch.randint(0, 18, (P, n), device=dev, dtype=torch.int32, generator=gen)
     K, W = args.steps, args.warmup
+    P = 64
+    extra = set(args.legs.split(',')) if args.legs else set()
 
     def barrier():
         D.barrier(dev)
 
-    for t in range(W):
-        env.step(actions[t % P])
-    barrier()
+    def make(nn, **kw):
+        base = dict(device=dev, action_space='walking', select_and_place=True, max_steps=MAX_STEPS, auto_reset=True,
+                    reward_mode=args.reward_mode, grid_obs=not args.inplace)
+        base.update(kw)
+        return gw.make_vec(nn, **base)
+
+    env = make(n)
+    targets = synth_targets(n, DENSITY, args.support, 1234 + 1 + rank).to(dev)
+    env.set_tasks(targets)
+    gen = torch.Generator(device=dev).manual_seed(4321 + rank)
+    actions = torch.randint(0, 18, (P, n), device=dev, dtype=torch.int32, generator=gen)
+    t_off = preroll(env, actions, n, 7 + rank)
+    steady = env.state_dict()
+
+    # ---- headline: K timed steps from the desynchronised steady state ----
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     launches0 = env.gpu_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()  # CUDA events on the launching (current) stream bracket the K back-to-back step launches
-    for t in range(K):
-        env.step(actions[(W + t) % P])
-    ev1.record()
-    barrier()
+    total_ms, evals = timed_steps(env, lambda t: env.step(actions[(t_off + t) % P]), K, W, dev, barrier,
+                                  mid=sampler.sample if sampler.ok else None)
+    launches = (env.gpu_launches - launches0) * K // (K + W)
     clocks = sampler.stop()
-    total_ms = ev0.elapsed_time(ev1)
-    launches = env.gpu_launches - launches0
     total_ms_max = D.max_over_ranks(total_ms, dev)
     value = n * world * K / (total_ms_max * 1e-3)
+    evaluated_frac = D.sum_over_ranks(evals, dev) / (n * world * K)
 
-    # ---- e2e through the host-buffer C-ABI call (pinned host actions in, reward/done out) ----
+    # ---- e2e: host-buffer C-ABI call, two env groups in flight ----
     acts_host = actions.cpu().pin_memory()
+    Ke = min(K, 500)
+    h = n // 2
+    groups = []
+    for lo, hi in ((0, h), (h, n)):
+        e = make(hi - lo)
+        e.load_state_dict(shard_state(steady, lo, hi))
+        groups.append((e, torch.cuda.Stream(dev), acts_host[:, lo:hi].contiguous().pin_memory(),
+                       torch.zeros(hi - lo, dtype=torch.float64).pin_memory(),
+                       torch.zeros(hi - lo, dtype=torch.uint8).pin_memory()))
+    ret = np.zeros(1)
+
+    def issue(g, t):
+        e, s, a, r, d = g
+        with torch.cuda.stream(s):
+            e.step_host(a[t % P], r, d, wait=False)
+
+    def consume(g):
+        g[0].wait()
+        ret[0] += float(g[3][0])   # the host touches the step's results before it issues the group's next step
+
+    def e2e_loop(steps):
+        for g in groups:
+            issue(g, 0)
+        for t in range(1, steps):
+            for g in groups:
+                consume(g)
+                issue(g, t)
+        for g in groups:
+            consume(g)
+    e2e_loop(max(3, W))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop(Ke)
+    torch.cuda.synchronize(dev)
+    e2e_value = n * world * Ke / D.max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_launches = sum(g[0].gpu_launches for g in groups)
+    del groups
+    # single group, synchronise every step (round 1's e2e definition), for comparison
+    env_s = make(n)
+    env_s.load_state_dict(steady)
     r_host = torch.zeros(n, dtype=torch.float64).pin_memory()
     d_host = torch.zeros(n, dtype=torch.uint8).pin_memory()
-    Ke = min(K, 500)
     for t in range(3):
-        env.step_host(acts_host[t % P], r_host, d_host)
+        env_s.step_host(acts_host[t % P], r_host, d_host)
     barrier()
     t0 = time.perf_counter()
     for t in range(Ke):
-        env.step_host(acts_host[t % P], r_host, d_host)
+        env_s.step_host(acts_host[t % P], r_host, d_host)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    e2e_value = n * world * Ke / D.max_over_ranks(e2e_s, dev)
-    # the same call with the transfers staged through cudaMemcpyAsync (reserved bit 4), for comparison
-    env_st = gw.make_vec(n, device=dev, action_space='walking', select_and_place=True, max_steps=MAX_STEPS,
-                         auto_reset=True, reward_mode=args.reward_mode, grid_obs=not args.inplace, _sched_bits=16)
-    env_st.load_state_dict(env.state_dict())
-    for t in range(3):
-        env_st.step_host(acts_host[t % P], r_host, d_host)
-    barrier()
-    t0 = time.perf_counter()
-    for t in range(Ke):
-        env_st.step_host(acts_host[t % P], r_host, d_host)
-    torch.cuda.synchronize(dev)
-    e2e_staged = n * world * Ke / D.max_over_ranks(time.perf_counter() - t0, dev)
-    del env_st
+    e2e_sync = n * world * Ke / D.max_over_ranks(time.perf_counter() - t0, dev)
+    del env_s
 
-    # ---- second half of BASELINE.json's metric: max-intersection evals/sec (stateless sweep, config 4) ----
-    mi_evals = None
-    if not args.no_mi:
-        npairs = 1_000_000
-        Tp = synth_targets(npairs, DENSITY, 'compact', 1237).to(dev)
-        Gp = synth_targets(npairs, DENSITY, 'compact', 1238).to(dev)
-        Gp[:npairs // 2] = torch.rot90(Tp[:npairs // 2], k=1, dims=(2, 3))  # half are rotated copies
-        gw.max_intersection(Gp, Tp)
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        for _ in range(5):
-            gw.max_intersection(Gp, Tp)
-        m1.record()
-        barrier()
-        mi_evals = world * npairs * 5 / (D.max_over_ranks(m0.elapsed_time(m1), dev) * 1e-3)
-        del Tp, Gp
+    # ---- dense: every world holds a half-built target, no episode limit -> every env is evaluated every step ----
+    Kd = min(K, 200)
+    env_d = make(n, max_steps=1 << 30)
+    env_d.set_tasks(targets)
+    keep = torch.rand(targets.shape, device=dev, generator=gen) < 0.5
+    built = torch.where(keep, targets, torch.zeros((), dtype=torch.int8, device=dev))
+    built[:, :3, 5, 5] = 0   # leave the spawn column free
+    env_d.set_grids(built)
+    for t in range(20):
+        env_d.step(actions[t % P])
+    dense_ms, dense_evals = timed_steps(env_d, lambda t: env_d.step(actions[t % P]), Kd, max(3, W), dev, barrier)
+    dense_ms = D.max_over_ranks(dense_ms, dev) / Kd
+    dense_frac = D.sum_over_ranks(dense_evals, dev) / (n * world * Kd)
+    del env_d, built, keep
 
+    peak, peak_src = hbm_peak()
+    line = None
     if rank == 0:
-        peak, peak_src = hbm_peak()
-        bytes_per_env = A_WALK_BYTES if not args.inplace else 189
+        bytes_per_env = A_WALK_BYTES if not args.inplace else A_INPLACE_BYTES
         # A step is two launches (physics k_step<0,1>, then observe k_step<0,2>, which moves ~all the bytes).
         # They are timed together: dividing the step's algorithmic bytes by the whole step duration charges the
         # physics launch to the observe kernel, i.e. the fraction below is a lower bound for the dominant kernel.
@@ -296,6 +534,8 @@ def run_b200_arm(args):
             'config': {'workload': WORKLOAD if not args.inplace else WORKLOAD.replace(
                            'int32 grid obs materialised', 'in-place int8 state (no int32 grid copy)'),
                        'envs_per_gpu': n, 'support': args.support, 'reward_mode': args.reward_mode,
+                       'evaluated_frac': evaluated_frac,
+                       'preroll_steps': t_off,
                        'parallelism': f'envs sharded x{world}, no collective',
                        'l2': f'per-step HBM traffic ~{bytes_per_env * n / 1e6:.0f} MB vs 126 MB L2 '
                              '(inputs larger than L2, no flush needed)',
@@ -303,28 +543,173 @@ def run_b200_arm(args):
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * n,
                     'd2h_bytes_per_step': 9 * n, 'steps': Ke,
-                    'api': 'IGLUVecEnv.step_host -> iglu_step_walking_host (pinned host buffers, read / written by '
-                           'the step kernels over PCIe)', 'staged_value': e2e_staged},
+                    'api': 'IGLUVecEnv.step_host(wait=False) + wait() -> iglu_step_walking_host_async / iglu_wait: '
+                           'pinned host actions in, reward / done out, read / written by the step kernels over PCIe; two '
+                           f'groups of {h} envs in flight, each group waits for its own results before its next step',
+                    'sync_value': e2e_sync, 'gpu_launches': int(e2e_launches)},
             'gpu_launches': int(launches),
-            'max_intersection': {'evals_per_sec': mi_evals, 'pairs_per_gpu': 1_000_000,
-                                 'inputs': 'config 4: compact targets rho=0.20; half of the grids independent, half '
-                                           'a rotated copy of the target; int8 [n,9,11,11] resident in HBM'},
+            'dense': {'ms_per_step': dense_ms, 'value': n * world / (dense_ms * 1e-3), 'evaluated_frac': dense_frac,
+                      'steps': Kd, 'roofline_frac': bytes_per_env * n / (dense_ms * 1e-3) / 1e9 / peak,
+                      'worlds': 'each env starts from a random half of its target already built (IGLUVecEnv.set_grids), '
+                                'no episode limit: a policy that builds keeps every grid non-empty'},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': recorded_traffic(),
-                         'kernel': 'iglu::k_step<0,2> (observe) timed together with iglu::k_step<0,1> (physics)',
+                         'frac': achieved / peak, 'traffic': recorded('step_kernel_traffic.json', 'dram_bytes_per_launch'),
+                         'kernel': recorded('step_kernel_traffic.json', 'kernels'),
                          'kernel_ms': kernel_ms, 'launches_per_step': launches / K,
                          'algorithmic_bytes_per_launch': bytes_per_env * n, 'peak_source': peak_src},
         }
+
+    # ---- config 3: flying + target_in_obs, 262,144 envs ----
+    if 'noconfig3' not in extra:
+        n3 = 262144
+        K3 = min(K, 100)
+        env3 = gw.make_vec(n3, device=dev, action_space='flying', target_in_obs=True, select_and_place=True,
+                           max_steps=MAX_STEPS, auto_reset=True, reward_mode=args.reward_mode)
+        env3.set_tasks(synth_targets(n3, DENSITY, args.support, 77 + rank).to(dev))
+        P3 = 8
+        fa = [{'movement': torch.rand(n3, 3, device=dev, generator=gen) * 2 - 1,
+               'camera': torch.rand(n3, 2, device=dev, generator=gen) * 10 - 5,
+               'inventory': torch.randint(0, 7, (n3,), device=dev, dtype=torch.int32, generator=gen),
+               'placement': torch.randint(0, 3, (n3,), device=dev, dtype=torch.int32, generator=gen)} for _ in range(P3)]
+        ph3 = torch.as_tensor(phases(n3, 11 + rank), device=dev)
+        for t in range(MAX_STEPS + PREROLL_EXTRA):
+            if t < MAX_STEPS:
+                env3.reset((ph3 == t).to(torch.uint8))
+            env3.step(fa[t % P3])
+        ms3, ev3 = timed_steps(env3, lambda t: env3.step(fa[t % P3]), K3, max(3, W), dev, barrier)
+        ms3 = D.max_over_ranks(ms3, dev) / K3
+        ev3 = D.sum_over_ranks(ev3, dev) / (n3 * world * K3)
+        if rank == 0:
+            line['config3'] = {
+                'workload': 'configs[2]: flying Dict + target_in_obs=True, 262,144 envs/GPU, continuous random actions, '
+                            'every-step reward, int32 grid obs materialised, desynchronised steady state',
+                'envs_per_gpu': n3, 'steps': K3, 'ms_per_step': ms3, 'value': n3 * world / (ms3 * 1e-3),
+                'evaluated_frac': ev3,
+                'roofline': {'bound': 'hbm', 'unit': 'GB/s', 'peak': peak,
+                             'achieved_reference_bytes': A_FLY_BYTES * n3 / (ms3 * 1e-3) / 1e9,
+                             'frac_reference_bytes': A_FLY_BYTES * n3 / (ms3 * 1e-3) / 1e9 / peak,
+                             'achieved': A_FLY_OURS * n3 / (ms3 * 1e-3) / 1e9,
+                             'frac': A_FLY_OURS * n3 / (ms3 * 1e-3) / 1e9 / peak,
+                             'note': 'A_fly = 11,103 B/step counts the per-step re-copy of target_grid the reference does; '
+                                     'here obs[target_grid] is persistent (written by set_tasks / the task generator), so '
+                                     f'{A_FLY_OURS} B/step really move: `frac` uses those'}}
+        del env3, fa
+
+    # ---- config 5: 1,048,576 envs per GPU, in-place observations, torch policy on the device ----
+    if world > 1 or 'config5' in extra:
+        n5 = 1048576
+        K5 = min(K, 50)
+        env5 = gw.make_vec(n5, device=dev, action_space='walking', select_and_place=True, max_steps=MAX_STEPS,
+                           auto_reset=True, reward_mode='on_change', grid_obs=False, max_target_blocks=64)
+        env5.set_tasks(synth_targets(n5, DENSITY, 'compact', 99 + rank, device=dev))
+        torch.manual_seed(rank)
+        w1 = torch.randn(1089 + 5 + 6, 64, device=dev, dtype=torch.bfloat16) * 0.05
+        w2 = torch.randn(64, 18, device=dev, dtype=torch.bfloat16) * 0.5
+
+        def policy(o):   # the policy of examples/policy_loop.py: reads the int8 voxel state and the small obs in place
+            x = torch.cat([o['grid'].reshape(n5, -1).to(torch.bfloat16), o['agentPos'].to(torch.bfloat16),
+                           o['inventory'].to(torch.bfloat16) * 0.05], dim=1)
+            logits = torch.relu(x @ w1) @ w2
+            return torch.distributions.Categorical(logits=logits.float()).sample().to(torch.int32)
+        obs5 = [env5.reset()]
+        a5 = torch.randint(0, 18, (n5,), device=dev, dtype=torch.int32, generator=gen)
+        ph5 = torch.as_tensor(phases(n5, 13 + rank), device=dev)
+        for t in range(MAX_STEPS + PREROLL_EXTRA):
+            if t < MAX_STEPS:
+                env5.reset((ph5 == t).to(torch.uint8))
+            obs5[0] = env5.step(a5)[0]
+
+        def step5(t):
+            obs5[0] = env5.step(policy(obs5[0]))[0]
+        ms5, _ = timed_steps(env5, step5, K5, max(3, W), dev, barrier)
+        ms5 = D.max_over_ranks(ms5, dev) / K5
+        ms5e, _ = timed_steps(env5, lambda t: env5.step(a5), K5, 3, dev, barrier)
+        ms5e = D.max_over_ranks(ms5e, dev) / K5
+        if rank == 0:
+            line['config5'] = {
+                'workload': 'configs[4]: walking, 1,048,576 envs/GPU, reward on change (reference gate), observations '
+                            'consumed IN PLACE by a torch bf16 MLP policy on the device (int8 voxel state + agentPos + '
+                            'inventory -> Categorical over 18 actions), desynchronised steady state',
+                'envs_per_gpu': n5, 'steps': K5, 'ms_per_step': ms5, 'value': n5 * world / (ms5 * 1e-3),
+                'env_only_ms_per_step': ms5e, 'env_only_value': n5 * world / (ms5e * 1e-3),
+                'hbm_frac_info': A_INPLACE_BYTES * n5 / (ms5e * 1e-3) / 1e9 / peak}
+        del env5
+
+    # ---- second half of BASELINE.json's metric: max-intersection evals/sec (stateless sweep, config 4) ----
+    if not args.no_mi:
+        peaks = int_peaks()
+        npairs = 1_000_000
+        sweeps = []
+        for rho in (0.05, 0.20, 0.50):
+            Tp = synth_targets(npairs, rho, 'compact', 1237, device=dev)
+            Gp = synth_targets(npairs, rho, 'compact', 1238, device=dev)
+            Gp[:npairs // 2] = torch.rot90(Tp[:npairs // 2], k=1, dims=(2, 3))  # half are rotated copies
+            sweeps.append(reward_sweep(gw, D, dev, world, barrier, peaks, f'compact rho={rho:.2f}', Tp, Gp))
+            del Tp, Gp
+        gpath = os.path.join(ROOT, 'tests', 'golden', 'goals.npz')
+        if os.path.exists(gpath):
+            goals = torch.as_tensor(np.load(gpath)['targets']).to(torch.int8)
+            idx = torch.arange(npairs) % goals.shape[0]
+            Tp = goals[idx].to(dev)
+            keep = torch.rand(Tp.shape, device=dev, generator=gen) < 0.5
+            Gp = torch.rot90(torch.where(keep, Tp, torch.zeros((), dtype=torch.int8, device=dev)), k=1, dims=(2, 3))
+            sweeps.append(reward_sweep(gw, D, dev, world, barrier, peaks,
+                                       'goals.pkl structures tiled; grid = rotated random half of the target', Tp, Gp))
+            del Tp, Gp
+        if rank == 0:
+            main_sw = sweeps[1]
+            line['max_intersection'] = {
+                'evals_per_sec': main_sw['evals_per_sec'], 'pairs_per_gpu': npairs,
+                'inputs': 'config 4: compact targets rho=0.20 (headline); half of the grids independent, half a rotated '
+                          'copy of the target; int8 [n,9,11,11] resident in HBM, generated on the device',
+                'roofline': main_sw.get('roofline'), 'int_peaks': peaks, 'sweeps': sweeps}
+
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            rate, _ = cpu_sample(2048, 20, threads)
-            steps_cpu = max(20, int(rate * 8.0 / 8192))  # ~8 s of wall time on all cores
-            v, dt = cpu_sample(8192, steps_cpu, threads, warmup=5)
+            rate, _, _ = cpu_port_sample(2048, 20, threads, preroll=False)
+            steps_cpu = max(20, int(rate * 8.0 / 8192))  # ~8 s of wall time on all cores after the pre-roll
+            v, dt, nz = cpu_port_sample(8192, steps_cpu, threads, warmup=5)
             line['cpu_baseline'] = {'value': v, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'port',
-                                    'sample': f'8192 envs x {steps_cpu} steps of the workload, {dt:.1f} s wall, '
-                                              'oracle/iglu_oracle.c (C port of the reference step), reward on change'}
+                                    'sample': f'8192 envs x {steps_cpu} steps of the workload from the same '
+                                              f'desynchronised steady state, {dt:.1f} s wall, oracle/iglu_oracle.c (C '
+                                              'port of the reference step), reward on change',
+                                    'nonempty_grid_frac': nz}
+            if python_reference_available() and 'nopyref' not in extra:
+                pv, pw = python_reference_sample(2000, 0, threads)
+                line['cpu_baseline']['python_reference'] = {
+                    'value': pv, 'unit': 'env-steps/s', 'cores': threads, 'kind': 'reference',
+                    'sample': f'{threads} processes x 1 env x 2000 steps, unmodified reference package (baseline/_ref) '
+                              f'through gym.make / env.step, {pw:.1f} s wall'}
+            if 'nodropin' not in extra:
+                line['dropin_n1'] = dropin_n1(gw, dev)
         print(json.dumps(line), flush=True)
     D.shutdown()
+
+
+def dropin_n1(gw, dev):
+    """The N = 1 gym drop-in (gw.make(...).step, numpy observations on the host) against the reference's own
+    per-step latency (~590 us mean on this workload)."""
+    env = gw.make('IGLUGridworld-v0', action_space='walking', render=False, vector_state=True, size_reward=False,
+                  select_and_place=True, max_steps=MAX_STEPS, device=dev)
+    T = synth_targets(1, DENSITY, 'compact', 1234 + 1)[0].numpy().astype(int)
+    env.set_task(gw.Task('', T, starting_grid=[]))
+    env.reset()
+    rng = np.random.RandomState(100)
+    for _ in range(50):
+        _, _, done, _ = env.step(int(rng.randint(18)))
+        if done:
+            env.reset()
+    n = 1000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        _, _, done, _ = env.step(int(rng.randint(18)))
+        if done:
+            env.reset()
+    us = 1e6 * (time.perf_counter() - t0) / n
+    return {'us_per_step': us, 'steps': n, 'reference_us_per_step': 590.0,
+            'note': 'gw.make(IGLUGridworld-v0).step incl. resets, numpy obs on the host: one step call (2 launches) + one '
+                    'snapshot kernel + one device->host copy + one synchronisation per step; reference figure: SURVEY 6'}
 
 
 def main():
@@ -339,6 +724,7 @@ def main():
     ap.add_argument('--inplace', action='store_true', help='do not materialise the int32 grid obs')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-mi', action='store_true', help='skip the max-intersection evals/sec leg')
+    ap.add_argument('--legs', default='', help='comma list: config5 (force at 1 GPU), noconfig3, nopyref, nodropin')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -43,10 +43,21 @@ class TaskPool(C.Structure):
                 ('seed', C.c_uint64), ('env_offset', C.c_int64)]
 
 
+class EnvSnapshot(C.Structure):
+    """iglu_env_snapshot (include/iglu_b200.h)"""
+    _fields_ = [('pose', C.c_double * 6), ('reward', C.c_double), ('agent_pos', C.c_float * 5),
+                ('inventory_obs', C.c_float * 6), ('compass', C.c_float), ('inventory', C.c_int32 * 6),
+                ('active_block', C.c_int32), ('time_int_steps', C.c_int32), ('error', C.c_int32),
+                ('step_no', C.c_int32), ('grid_size', C.c_int32), ('max_int', C.c_int32),
+                ('target_size', C.c_int32), ('done', C.c_int32),
+                ('grid', C.c_int32 * CELLS), ('target_grid', C.c_int32 * CELLS)]
+
+
 EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_destroy', 'iglu_set_tasks',
            'iglu_reset', 'iglu_step_walking', 'iglu_step_flying', 'iglu_step_walking_dict',
            'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
-           'iglu_task_pool_prepare', 'iglu_task_pool_attach')
+           'iglu_task_pool_prepare', 'iglu_task_pool_attach', 'iglu_step_walking_host_async', 'iglu_wait',
+           'iglu_fetch_env_host')
 
 _lib = None
 
@@ -77,6 +88,9 @@ def load():
     L.iglu_step_flying.argtypes = [vp, C.POINTER(State), vp, vp, vp, vp, C.POINTER(Obs), vp]
     L.iglu_step_walking_dict.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp]
     L.iglu_step_walking_host.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp, vp, vp]
+    L.iglu_step_walking_host_async.argtypes = [vp, C.POINTER(State), vp, vp, C.POINTER(Obs), vp, vp, vp]
+    L.iglu_wait.argtypes = [vp]
+    L.iglu_fetch_env_host.argtypes = [vp, C.POINTER(State), C.POINTER(Obs), i64, vp, vp, vp]
     L.iglu_max_intersection.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp]
     L.iglu_last_launch_count.argtypes = [vp]
     L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]

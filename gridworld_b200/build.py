@@ -40,7 +40,7 @@ MB_SO = os.path.join(CSRC, 'libiglu_microbench.so')
 
 
 def build_microbench(force=False):
-    """Integer-pipe peak microbenchmark (measurement aid used by scripts/reward_roofline.py)."""
+    """Integer-pipe peak microbenchmark (POPC / LOP3 / IADD3 / IMAD issue rates; bench.py's reward roofline)."""
     src = os.path.join(CSRC, 'iglu_microbench.cu')
     if not force and os.path.exists(MB_SO) and os.path.getmtime(MB_SO) >= os.path.getmtime(src):
         return MB_SO
@@ -73,15 +73,29 @@ def build_library(force=False, verbose=False):
         return override
     if not force and not needs_build():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + ['-o', SO] + [os.path.join(CSRC, f) for f in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(CSRC, 'build.log'), 'w') as f:
-        f.write(' '.join(cmd) + '\n' + log)
-    if verbose or res.returncode != 0:
-        print(log)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed building libiglu_b200.so (see gridworld_b200/csrc/build.log)')
+    # Several ranks may get here at once (bench.py under torchrun): one builds, under a file lock, into a
+    # temporary name that is moved into place atomically; the others wait and then find a fresh library.
+    import fcntl
+    with open(os.path.join(CSRC, '.build.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return SO
+            tmp = f'{SO}.{os.getpid()}.tmp'
+            cmd = [_nvcc()] + NVCC_FLAGS + ['-o', tmp] + [os.path.join(CSRC, f) for f in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log = res.stdout + res.stderr
+            with open(os.path.join(CSRC, 'build.log'), 'w') as f:
+                f.write(' '.join(cmd) + '\n' + log)
+            if verbose or res.returncode != 0:
+                print(log)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed building libiglu_b200.so (see gridworld_b200/csrc/build.log)')
+            os.replace(tmp, SO)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return SO
 
 

@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     const bool alternate = (p.cfg.reserved & 1) == 0;  // reserved bit 0 = 1 disables the phase alternation
     const int cap = p.cfg.tlist_cap;
     uint32_t seq_issue = 0, seq_cons = 0;  // ring sequence numbers (warp-uniform, live across groups)
+    int evals_done = 0;                    // committed-candidate evaluations of this warp (measurement: sched[2..3])
     uint32_t slot_addr[NBUF], bar_addr[NBUF];  // shared-window addresses of the ring (computed once)
 #pragma unroll
     for (int s = 0; s < NBUF; s++) {
@@ -462,6 +463,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                         r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
                     }
                     if (keep && lane == j) mi_eval = r;
+                    if (keep) evals_done++;
                 }
                 __syncwarp();  // every lane is done with the slot before it is refilled
                 seq_cons++;
@@ -556,6 +558,10 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
         }
         grp = dynamic ? (int64_t)__shfl_sync(0xffffffffu, grp_next, 0) : grp + (int64_t)gridDim.x * WPC;
     }
+    // how many maximal_intersection evaluations really ran (bench.py's evaluated_frac): one fire-and-forget
+    // 64-bit add per warp and launch
+    if (HAS_B && p.st.sched != nullptr && lane == 0 && evals_done)
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.st.sched + 2), (unsigned long long)evals_done);
 }
 
 // ------------------------------------------------------------------ task preparation
@@ -1034,9 +1040,9 @@ static void *mapped_alias(const void *host) {
     return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
-extern "C" int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
-                                      int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
-                                      uint8_t *done_host, void *stream) {
+static int step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
+                             int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
+                             uint8_t *done_host, void *stream, bool sync) {
     if (!ctx || !state_ok(st, obs) || !actions_host || !actions_dev || !reward_host || !done_host)
         return IGLU_ERR_INVALID_ARG;
     if (ctx->cfg.action_space != IGLU_WALKING_DISCRETE) return IGLU_ERR_INVALID_ARG;
@@ -1067,6 +1073,65 @@ extern "C" int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const
         rc = check(cudaMemcpyAsync(done_host, obs->done, sizeof(uint8_t) * st->n, cudaMemcpyDeviceToHost, s));
         if (rc) return rc;
     }
+    return sync ? check(cudaStreamSynchronize(s)) : IGLU_OK;
+}
+
+extern "C" int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
+                                      int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
+                                      uint8_t *done_host, void *stream) {
+    return step_walking_host(ctx, st, actions_host, actions_dev, obs, reward_host, done_host, stream, true);
+}
+
+extern "C" int iglu_step_walking_host_async(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
+                                            int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
+                                            uint8_t *done_host, void *stream) {
+    return step_walking_host(ctx, st, actions_host, actions_dev, obs, reward_host, done_host, stream, false);
+}
+
+extern "C" int iglu_wait(void *stream) { return check(cudaStreamSynchronize((cudaStream_t)stream)); }
+
+// ------------------------------------------------------------------ single-env read-back (N = 1 drop-in surface)
+namespace iglu {
+__global__ void __launch_bounds__(256) k_fetch_env(iglu_state st, iglu_obs obs, int64_t e, iglu_env_snapshot *out) {
+    const int64_t n = st.n;
+    const int t = threadIdx.x;
+    const int8_t *g = st.grid + e * GSTRIDE, *tg = st.target + e * GSTRIDE;
+    for (int c = t; c < CELLS; c += blockDim.x) {
+        out->grid[c] = (int32_t)g[c];
+        out->target_grid[c] = (int32_t)tg[c];
+    }
+    if (t < 6) out->pose[t] = st.pose[t * n + e];
+    if (t < 5) out->agent_pos[t] = obs.agent_pos ? obs.agent_pos[5 * e + t] : 0.f;
+    if (t >= 32 && t < 38) out->inventory_obs[t - 32] = obs.inventory ? obs.inventory[6 * e + (t - 32)] : 0.f;
+    if (t == 64) {
+        const int w0 = st.istate[0 * n + e], w1 = st.istate[1 * n + e], w2 = st.istate[2 * n + e];
+        const int w3 = st.istate[3 * n + e];
+        out->inventory[0] = lo16(w0); out->inventory[1] = hi16(w0); out->inventory[2] = lo16(w1);
+        out->inventory[3] = hi16(w1); out->inventory[4] = lo16(w2); out->inventory[5] = hi16(w2);
+        out->active_block = w3 & 0xFF;
+        out->time_int_steps = (w3 >> 8) & 0xFF;
+        out->error = (w3 >> 24) & 0xFF;
+        out->step_no = st.istate[4 * n + e];
+        out->grid_size = st.istate[5 * n + e];
+        out->max_int = st.istate[6 * n + e];
+        out->target_size = st.tmeta[1 * n + e];
+        out->done = obs.done[e];
+        out->reward = obs.reward[e];
+        out->compass = obs.compass ? obs.compass[e] : 0.f;
+    }
+}
+}  // namespace iglu
+
+extern "C" int iglu_fetch_env_host(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, int64_t env,
+                                   iglu_env_snapshot *scratch_dev, iglu_env_snapshot *out_host, void *stream) {
+    if (!ctx || !state_ok(st, obs) || env < 0 || env >= st->n || !scratch_dev || !out_host) return IGLU_ERR_INVALID_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    k_fetch_env<<<1, 256, 0, s>>>(*st, *obs, env, scratch_dev);
+    ctx->last_launches = 1;
+    int rc = check(cudaPeekAtLastError());
+    if (rc) return rc;
+    rc = check(cudaMemcpyAsync(out_host, scratch_dev, sizeof(iglu_env_snapshot), cudaMemcpyDeviceToHost, s));
+    if (rc) return rc;
     return check(cudaStreamSynchronize(s));
 }
 

@@ -18,12 +18,18 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t *out, uint32_t seed) 
 #pragma unroll
     for (int c = 0; c < CHAINS; c++) a[c] = seed + threadIdx.x * 2654435761u + c * 40503u;
     const uint32_t k1 = seed | 1u, k2 = ~seed;
+    // LOP3 / IADD3 take their second and third operand from two OTHER chains (values of the previous iteration
+    // or of this one, whichever the unrolled order gives): a chain of constants would be folded by the compiler
+    // (round 1's (a & k1) ^ k2 collapsed to one instruction per loop, which is why its "peak" was impossible).
+    // The LOP3 is written as PTX so that exactly one three-input logic instruction is issued per op.
+#pragma unroll 8
     for (int i = 0; i < ITERS; i++) {
 #pragma unroll
         for (int c = 0; c < CHAINS; c++) {
+            const uint32_t b = a[(c + 1) % CHAINS], d = a[(c + 3) % CHAINS];
             if (OP == 0) a[c] = __popc(a[c]) + k1;               // POPC (+ IADD to keep the chain alive)
-            else if (OP == 1) a[c] = (a[c] & k1) ^ k2;           // one LOP3
-            else if (OP == 2) a[c] = a[c] + k1 + k2;             // one IADD3
+            else if (OP == 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x6A;" : "+r"(a[c]) : "r"(b), "r"(d));  // a ^ (b & d)
+            else if (OP == 2) a[c] = a[c] + b + d;               // one IADD3
             else a[c] = a[c] * k1 + k2;                          // one IMAD
         }
     }

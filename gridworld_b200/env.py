@@ -8,57 +8,61 @@ updates run in libiglu_b200.so on the GPU (no CPU fallback). render=True is not 
 import warnings
 
 import numpy as np
-import torch
 
 from .tasks import Task, Tasks
 from .vec_env import IGLUVecEnv
 
 
 class _AgentView:
-    """Read/write view of the device-resident Agent (reference core/world.py:8-29)."""
+    """Read/write view of the device-resident Agent (reference core/world.py:8-29). Reads come from the env's
+    last snapshot (one device -> host transfer per step, GridWorld._snapshot), writes go to the device."""
     PAD = 0.25
 
-    def __init__(self, vec, flying):
-        self._v = vec
+    def __init__(self, owner, flying):
+        self._o = owner
         self.flying = flying
         self.sustain = False
         self.strafe = [0, 0]
 
+    def _write(self, **kw):
+        self._o._vec.set_agent_state(0, **kw)
+        self._o._snap = None  # stale now
+
     @property
     def position(self):
-        return tuple(float(v) for v in self._v.position[0].tolist())
+        return tuple(self._o._snapshot().pose[0:3])
 
     @position.setter
     def position(self, p):
-        self._v.set_agent_state(0, position=p)
+        self._write(position=p)
 
     @property
     def rotation(self):
-        return tuple(float(v) for v in self._v.rotation[0].tolist())
+        return tuple(self._o._snapshot().pose[3:5])
 
     @rotation.setter
     def rotation(self, r):
-        self._v.set_agent_state(0, rotation=r)
+        self._write(rotation=r)
 
     @property
     def dy(self):
-        return float(self._v.dy[0].item())
+        return float(self._o._snapshot().pose[5])
 
     @dy.setter
     def dy(self, v):
-        self._v.set_agent_state(0, dy=v)
+        self._write(dy=v)
 
     @property
     def time_int_steps(self):
-        return int(self._v.time_int_steps[0].item())
+        return int(self._o._snapshot().time_int_steps)
 
     @property
     def active_block(self):
-        return int(self._v.active_block[0].item())
+        return int(self._o._snapshot().active_block)
 
     @property
     def inventory(self):
-        return [int(v) for v in self._v.inventory[0].tolist()]
+        return list(self._o._snapshot().inventory)
 
 
 class GridWorld:
@@ -77,7 +81,8 @@ class GridWorld:
                                wrong_placement_scale=wrong_placement_scale, target_in_obs=target_in_obs,
                                vector_state=vector_state, auto_reset=False, reward_mode='on_change',
                                grid_obs=True)
-        self.agent = _AgentView(self._vec, action_space == 'flying')
+        self._snap = None
+        self.agent = _AgentView(self, action_space == 'flying')
         self.world = None
         self._task = None
         self._task_generator = None
@@ -109,9 +114,16 @@ class GridWorld:
     def unwrapped(self):
         return self
 
+    def _snapshot(self):
+        """Host copy of this env's observation + agent state (iglu_fetch_env_host: one kernel, one copy, one
+        synchronisation), cached until the device state changes again."""
+        if self._snap is None:
+            self._snap = self._vec.fetch_env(0)
+        return self._snap
+
     @property
     def grid(self):
-        return self._vec.grid[0].to(torch.int32).cpu().numpy()
+        return np.ctypeslib.as_array(self._snapshot().grid).reshape(9, 11, 11).copy()
 
     def set_task(self, task):
         """env.py:155-166"""
@@ -156,15 +168,16 @@ class GridWorld:
             self.starting_grid = self._task.starting_grid
         return self._task
 
-    def _obs_numpy(self, reset):
-        v = self._vec
-        obs = {'inventory': v._obs_inv[0].cpu().numpy(), 'compass': v._obs_compass[0].cpu().numpy(),
+    def _obs_numpy(self):
+        sn = self._snapshot()
+        as_np = np.ctypeslib.as_array
+        obs = {'inventory': as_np(sn.inventory_obs).copy(), 'compass': np.array([sn.compass], dtype=np.float32),
                'dialog': self._task.chat}
         if self.vector_state:
-            obs['grid'] = v._obs_grid[0].cpu().numpy()
-            obs['agentPos'] = v._obs_pos[0].cpu().numpy()
+            obs['grid'] = as_np(sn.grid).reshape(9, 11, 11).copy()
+            obs['agentPos'] = as_np(sn.agent_pos).copy()
         if self.target_in_obs:
-            obs['target_grid'] = v._obs_target[0].cpu().numpy()
+            obs['target_grid'] = as_np(sn.target_grid).reshape(9, 11, 11).copy()
         return obs
 
     def reset(self):
@@ -188,9 +201,11 @@ class GridWorld:
         target = np.asarray(self._task.target_grid).astype(np.int8)
         pose = np.array([[*self.initial_position, *self.initial_rotation]], dtype=np.float64)
         self._vec.set_tasks(target[None], start_dense[None], pose, reset=True)
-        self.max_int = self._task.maximal_intersection(self.grid)
-        self.prev_grid_size = int((self.grid != 0).sum())
-        return self._obs_numpy(reset=True)
+        self._snap = None
+        grid = self.grid
+        self.max_int = self._task.maximal_intersection(grid)   # env.py:241 (never refreshed by step)
+        self.prev_grid_size = int(np.count_nonzero(grid))
+        return self._obs_numpy()
 
     def render(self):
         raise ValueError('create env with render=True')
@@ -217,14 +232,16 @@ class GridWorld:
             a = {k: np.asarray([int(action[k])], np.int32)
                  for k in ('forward', 'back', 'left', 'right', 'jump', 'attack', 'use', 'hotbar')}
             a['camera'] = np.asarray(action['camera'], np.float32)[None]
-        prev_max = int(v.max_int[0].item())
-        _, reward, done, _ = v.step(a)
-        self.step_no = int(v.step_no[0].item())
-        obs = self._obs_numpy(reset=False)
-        r = float(reward[0].item())
-        if int(v.max_int[0].item()) != prev_max and isinstance(self.right_placement_scale, int):
+        prev_max = self._snapshot().max_int
+        v.step(a)
+        self._snap = None
+        sn = self._snapshot()      # the step's single device -> host transfer
+        self.step_no = int(sn.step_no)
+        obs = self._obs_numpy()
+        r = float(sn.reward)
+        if sn.max_int != prev_max and isinstance(self.right_placement_scale, int):
             r = int(r)  # right_placement * int scale is a Python int in the reference (env.py:296)
-        return obs, r, bool(done[0].item()), {}
+        return obs, r, bool(sn.done), {}
 
 
 class Wrapper:

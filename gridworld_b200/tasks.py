@@ -4,7 +4,6 @@ through iglu_max_intersection, and inside an env the synthetic task is prepared 
 iglu_set_tasks (rotations, admissible rectangles, block list)."""
 import io
 import pickle
-import uuid
 
 import numpy as np
 
@@ -82,9 +81,8 @@ class Task:
         yield self
 
     def __repr__(self):
-        ins = self.last_instruction or ''
-        ins = ins if len(ins) < 20 else ins[:20] + '...'
-        return f'Task(instruction={ins})'
+        text = self.last_instruction or ''
+        return 'Task(instruction=%s)' % (text if len(text) < 20 else text[:20] + '...')
 
     def _gpu(self, grid, argmax):
         from .vec_env import max_intersection
@@ -117,273 +115,99 @@ class Task:
         return int(max_intersection(g, moved.astype(np.int8)[None], invariant=False)[0].item())
 
     def step_intersection(self, grid):
-        """task.py:103-119"""
-        grid = np.asarray(grid)
-        grid_size = int((grid != 0).sum())
-        wrong_placement = self.prev_grid_size - grid_size
-        max_int = self.maximal_intersection(grid) if wrong_placement != 0 else self.max_int
-        done = max_int == self.target_size
-        self.prev_grid_size = grid_size
-        right_placement = max_int - self.max_int
-        self.max_int = max_int
-        self.right_placement = right_placement
-        self.wrong_placement = wrong_placement
-        return right_placement, wrong_placement, done
+        """task.py:103-119: (right_placement, wrong_placement, done) of one step; the intersection is only
+        re-evaluated (on the GPU) when the number of blocks changed -- the reference's gate."""
+        blocks = int(np.count_nonzero(np.asarray(grid)))
+        self.wrong_placement = self.prev_grid_size - blocks
+        self.prev_grid_size = blocks
+        fresh = self.maximal_intersection(grid) if self.wrong_placement else self.max_int
+        self.right_placement, self.max_int = fresh - self.max_int, fresh
+        return self.right_placement, self.wrong_placement, fresh == self.target_size
 
 
 class Tasks:
-    """reference gridworld/tasks/task.py:163-205"""
+    """Base of task collections + the sparse <-> dense converters (interface of reference
+    gridworld/tasks/task.py:163-205). Written from the layout contract in include/iglu_b200.h: the world block
+    (x, y, z) lives at dense index [y + 1, x + 5, z + 5] of a 9 x 11 x 11 grid."""
+
+    _OFFSET = np.array([BUILD_ZONE_SIZE_X // 2, 1, BUILD_ZONE_SIZE_Z // 2])  # added to (x, y, z)
 
     @classmethod
     def to_dense(cls, blocks):
-        if isinstance(blocks, (list, tuple)):
-            if all(isinstance(b, (list, tuple)) for b in blocks):
-                grid = np.zeros(BUILD_ZONE_SIZE, dtype=int)
-                for x, y, z, block_id in blocks:
-                    grid[y + 1, x + BUILD_ZONE_SIZE_X // 2, z + BUILD_ZONE_SIZE_Z // 2] = block_id
-                blocks = grid
-        return blocks
+        """Block list [(x, y, z, colour), ...] -> dense grid; anything that is not a list / tuple of block
+        rows (e.g. an ndarray that is dense already) is handed back unchanged."""
+        if not isinstance(blocks, (list, tuple)) or not all(isinstance(b, (list, tuple)) for b in blocks):
+            return blocks
+        grid = np.zeros(BUILD_ZONE_SIZE, dtype=int)
+        if len(blocks):
+            rows = np.asarray(blocks, dtype=np.int64).reshape(-1, 4)
+            x, y, z = (rows[:, :3] + cls._OFFSET).T
+            flat = np.ravel_multi_index((y, x, z), BUILD_ZONE_SIZE)
+            # a cell listed twice keeps its LAST colour: np.unique on the reversed order finds the last mention
+            _, rev = np.unique(flat[::-1], return_index=True)
+            keep = len(flat) - 1 - rev
+            grid.flat[flat[keep]] = rows[keep, 3]
+        return grid
 
     @classmethod
     def to_sparse(cls, blocks):
-        # NB the reference treats axis 0 of an ndarray as x here (task.py:177-187); kept as is.
-        if isinstance(blocks, np.ndarray):
-            idx = blocks.nonzero()
-            types = [blocks[i] for i in zip(*idx)]
-            blocks = [(*i, t) for *i, t in zip(*idx, types)]
-            new_blocks = []
-            for x, y, z, bid in blocks:
-                new_blocks.append((x - BUILD_ZONE_SIZE_X // 2, y - 1, z - BUILD_ZONE_SIZE_Z // 2, bid))
-            blocks = new_blocks
-        return blocks
-
-    def reset(self):
-        return NotImplemented
-
-    def __len__(self):
-        return NotImplemented
-
-    def __iter__(self):
-        return NotImplemented
-
-    def set_task(self, task_id):
-        return NotImplemented
-
-    def get_target(self):
-        return NotImplemented
-
-    def set_task_obj(self, task):
-        return NotImplemented
-
-
-class CustomTasks(Tasks):
-    """reference gridworld/tasks/task_set.py:23-56"""
-
-    def __init__(self, goals, task_kwargs=None):
-        super().__init__()
-        self.task_kwargs = task_kwargs or {}
-        self.tasks = {str(uuid.uuid4().hex): Task(conv, self.to_dense(grid), **self.task_kwargs)
-                      for conv, grid in goals}
-        self.task_ids = list(self.tasks.keys())
-        self.reset()
-
-    def __getattr__(self, name):
-        if name in ('current', 'tasks', 'task_ids', 'task_kwargs'):
-            raise AttributeError(name)
-        return getattr(self.current, name)
-
-    def __len__(self):
-        return len(self.task_ids)
-
-    def __iter__(self):
-        for task in self.tasks.values():
-            yield from iter(task)
-
-    def reset(self):
-        task_id = np.random.choice(self.task_ids)
-        self.current = self.tasks[task_id].reset()
-        return self.current
-
-
-class RandomTasks(Tasks):
-    """reference gridworld/tasks/task_set.py:59-157 (same numpy global-RNG call order)"""
-
-    def __init__(self, max_blocks=4, height_levels=1, allow_float=False, max_dist=2, num_colors=1, max_cache=0):
-        self.height_levels = height_levels
-        self.max_blocks = max_blocks
-        self.allow_float = allow_float
-        self.max_dist = max_dist
-        self.num_colors = num_colors
-        self.max_cache = max_cache
-        self.tasks = {}
-        self.current = None
-        for _ in range(self.max_cache):
-            self.tasks[str(uuid.uuid4().hex)] = self.sample_task()
-        self.reset()
-
-    def __getattr__(self, name):
-        if name in ('current', 'tasks'):
-            raise AttributeError(name)
-        return getattr(self.current, name)
-
-    def __len__(self):
-        return self.max_cache
-
-    def __iter__(self):
-        for task in self.tasks:
-            yield task
-
-    def reset(self):
-        if self.max_cache > 0:
-            sample = np.random.choice(list(self.tasks.keys()))
-            self.current = self.tasks[sample]
-            self.current_id = sample
-            return self.current
-        self.current = self.sample_task()
-        return self.current
-
-    def set_task(self, task_id):
-        self.current = self.tasks[task_id]
-        return self.current
-
-    def sample_task(self):
-        target_grid = np.zeros(BUILD_ZONE_SIZE, dtype=np.int32)
-        for height in range(self.height_levels):
-            block_x = np.random.choice(BUILD_ZONE_SIZE_X)
-            block_z = np.random.choice(BUILD_ZONE_SIZE_Z)
-            color = np.random.choice(self.num_colors) + 1
-            target_grid[height, block_x, block_z] = color
-            for _ in range(self.max_blocks - 1):
-                ddx, ddz = 0, 0
-                while ddx == 0 and ddz == 0 \
-                        or block_x + ddx >= BUILD_ZONE_SIZE_X or block_z + ddz >= BUILD_ZONE_SIZE_Z \
-                        or block_x + ddx < 0 or block_z + ddz < 0 \
-                        or target_grid[height, block_x + ddx, block_z + ddz] != 0:
-                    ddx = np.random.choice(2 * self.max_dist + 1) - self.max_dist
-                    ddz = np.random.choice(2 * self.max_dist + 1) - self.max_dist
-                    color = np.random.choice(self.num_colors) + 1
-                target_grid[height, block_x + ddx, block_z + ddz] = color
-        return Task('', target_grid)
-
-
-class Subtasks(Tasks):
-    """Staged task where subtasks are separate segments (reference gridworld/tasks/task.py:208-308);
-    host-side task producer with the reference's interface and numpy global-RNG call order."""
-
-    def __init__(self, dialog, structure_seq, invariant=False, progressive=True):
-        self.dialog = dialog
-        self.invariant = invariant
-        self.progressive = progressive
-        self.structure_seq = structure_seq
-        self.next = None
-        self.full = False
-        self.task_start = 0
-        self.task_goal = 0
-        self.full_structure = self.to_dense(self.structure_seq[-1])
-        self.current = self.reset()
-
-    def __getattr__(self, name):
-        if name == 'current':
-            return None
-        return getattr(self.current, name)
-
-    def reset(self):
-        if self.next is None:
-            if len(self.structure_seq) == 1:
-                turn = -1
-            else:
-                turn = np.random.choice(len(self.structure_seq)) - 1
-            turn_goal = turn + 1
-        else:
-            turn = self.next
-            turn_goal = self.next + 1
-        self.task_start = turn
-        self.task_goal = turn_goal
-        self.current = self.create_task(self.task_start, self.task_goal)
-        return self.current
-
-    def __len__(self):
-        return len(self.structure_seq)
-
-    def __iter__(self):
-        for i in range(len(self)):
-            yield self.create_task(i - 1, i)
-
-    def __repr__(self):
-        return (f"Subtasks(total_steps={len(self.structure_seq)}, "
-                f"current_task_start={self.task_start}, current_task_end={self.task_goal})")
-
-    def create_task(self, turn_start, turn_goal):
-        dialog = ''
-        for turn in self.dialog[:turn_goal + 1]:
-            if isinstance(turn, list):
-                turn = '\n'.join(turn)
-            dialog += '\n' + turn if len(dialog) > 0 else turn
-        initial_blocks = [] if turn_start == -1 else self.structure_seq[turn_start]
-        tid = min(turn_goal, len(self.structure_seq) - 1) if not self.full else -1
-        target_grid = self.structure_seq[tid]
-        task = Task(dialog, target_grid=self.to_dense(target_grid), starting_grid=self.to_sparse(initial_blocks),
-                    full_grid=self.full_structure, last_instruction='\n'.join(self.dialog[tid]))
-        task.reset()
-        return task
-
-    def step_intersection(self, grid):
-        right_placement, wrong_placement, done = self.current.step_intersection(grid)
-        if done and len(self.structure_seq) > self.task_goal and self.progressive:
-            self.task_goal += 1
-            self.current = self.create_task(self.task_start, self.task_goal)
-            self.current.prev_grid_size = 0
-            _, _, done = self.current.step_intersection(grid)
-        return right_placement, wrong_placement, done
-
-    def set_task(self, task_id):
-        self.task_id = task_id
-        self.current = self.create_task(task_id - 1, task_id)
-        return self.current
-
-    def set_task_obj(self, task):
-        self.task_id = None
-        self.current = task
-        return self.current
+        """ndarray -> block list. NB the reference reads axis 0 of the array as x (task.py:177-187) although
+        to_dense writes y there; a drop-in has to give the same rows, so (i0 - 5, i1 - 1, i2 - 5, value)."""
+        if not isinstance(blocks, np.ndarray):
+            return blocks
+        idx = np.argwhere(blocks)
+        vals = blocks[tuple(idx.T)]
+        shifted = idx - cls._OFFSET
+        return [(*(int(v) for v in r), int(c)) for r, c in zip(shifted, vals)]
 
 
 # ---------------------------------------------------------------------------------------------------
 # Feeding task collections to the device-resident task generator (IGLUVecEnv.set_task_pool)
 
-def enumerate_tasks(tasks):
-    """All Task objects of a Task / Tasks-like collection, in a stable order.
+def _is_task(obj):
+    """A leaf task (this package's Task, the reference's Task, or anything shaped like one): it carries its
+    own target_grid. Collections forward attribute look-ups to their current task, hence vars() not hasattr()."""
+    return isinstance(obj, Task) or 'target_grid' in getattr(obj, '__dict__', {})
 
-    Handles the reference's container shapes: objects with a `.tasks` dict or list (CustomTasks, RandomTasks with
-    max_cache > 0 -- whose __iter__ yields dict KEYS in the reference, task_set.py:107-109), Subtasks (one Task
-    per turn, task.py:251-253), a plain Task, or any iterable of Tasks."""
-    if isinstance(tasks, Task):
+
+def enumerate_tasks(tasks, samples=0):
+    """All task objects of a task / task collection, in a stable order. Collections are recognised by shape, not
+    by class, so the reference's own objects can be passed: a `.tasks` dict or list (CustomTasks, RandomTasks
+    with max_cache > 0 -- whose __iter__ yields dict KEYS in the reference, task_set.py:107-109), an iterable of
+    tasks (Subtasks yields one task per turn, task.py:251-253; plain lists), a single task. A generator without
+    a cache (RandomTasks(max_cache=0)) is sampled `samples` times through its sample_task()."""
+    if _is_task(tasks):
         return [tasks]
     inner = getattr(tasks, '__dict__', {}).get('tasks')
     if isinstance(inner, dict):
-        return [t for v in inner.values() for t in enumerate_tasks(v)]
-    if isinstance(inner, (list, tuple)):
+        inner = list(inner.values())
+    if isinstance(inner, (list, tuple)) and len(inner):
         return [t for v in inner for t in enumerate_tasks(v)]
-    out = []
-    for t in tasks:
-        out.extend(enumerate_tasks(t) if not isinstance(t, Task) else [t])
-    return out
+    if inner is not None and callable(getattr(tasks, 'sample_task', None)):
+        return [tasks.sample_task() for _ in range(int(samples))]
+    return [t for v in tasks for t in enumerate_tasks(v)]
 
 
-def pool_arrays(tasks):
+def _dense_int8(grid_or_blocks):
+    """Dense int8 grid of a starting / target grid given either as a block list or as a dense array."""
+    if grid_or_blocks is None:
+        return np.zeros(BUILD_ZONE_SIZE, np.int8)
+    if isinstance(grid_or_blocks, np.ndarray) and grid_or_blocks.shape == BUILD_ZONE_SIZE:
+        return grid_or_blocks.astype(np.int8)
+    rows = [tuple(int(v) for v in b) for b in grid_or_blocks]
+    return np.asarray(Tasks.to_dense(rows)).astype(np.int8)
+
+
+def pool_arrays(tasks, samples=0):
     """(targets int8 [m, 9, 11, 11], starts int8 [m, 9, 11, 11], chats list[str]) of a task collection: the
-    inputs of IGLUVecEnv.set_task_pool (starting_grid None is treated as [] like everywhere in this package)."""
-    ts = enumerate_tasks(tasks)
+    inputs of IGLUVecEnv.set_task_pool (starting_grid None is treated as [] like everywhere in this package;
+    starting grids may be block lists or dense arrays)."""
+    ts = enumerate_tasks(tasks, samples)
     if not ts:
         raise ValueError('empty task collection')
-    targets = np.zeros((len(ts), *BUILD_ZONE_SIZE), np.int8)
-    starts = np.zeros((len(ts), *BUILD_ZONE_SIZE), np.int8)
-    chats = []
-    for i, t in enumerate(ts):
-        targets[i] = np.asarray(t.target_grid).astype(np.int8)
-        sg = t.starting_grid
-        if sg is not None and len(sg) > 0:
-            starts[i] = np.asarray(Tasks.to_dense([tuple(int(v) for v in b) for b in sg])).astype(np.int8)
-        chats.append(t.chat)
+    targets = np.stack([_dense_int8(np.asarray(t.target_grid)) for t in ts])
+    starts = np.stack([_dense_int8(t.starting_grid) for t in ts])
+    chats = [getattr(t, 'chat', '') for t in ts]
     return targets, starts, chats
 
 

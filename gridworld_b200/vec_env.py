@@ -119,6 +119,8 @@ class IGLUVecEnv:
         self._kind = kind
         self._L = _lib.load()
         self._tasks_set = False
+        self._was_reset = False   # every env has been reset since its task rows were (re)written
+        self._reset_seen = None
         self._pool = None
         self.dialogs = None
 
@@ -161,6 +163,7 @@ class IGLUVecEnv:
         with torch.cuda.device(dev):
             _lib.check(self._L.iglu_ctx_create(C.byref(cfg), C.byref(self._ctx)))
         self.gpu_launches = 0  # kernels launched by this env so far
+        self._snap = None
         self._st_ref, self._ob_ref = C.byref(self._st), C.byref(self._ob)
         self._actions_ptr = self._actions_dev.data_ptr()
 
@@ -218,12 +221,14 @@ class IGLUVecEnv:
         else:
             idx = self._dev(env_idx, torch.int32, (k,))
         pp = lambda a: None if a is None else a.data_ptr()  # noqa: E731
+        self._check_block_capacity(t, s)  # refuse BEFORE anything is written to the env's task rows
         with torch.cuda.device(self.device):
             _lib.check(self._L.iglu_set_tasks(self._ctx, C.byref(self._st), C.byref(self._ob), pp(t), pp(s),
                                               pp(ip), pp(idx), k, self._stream()))
             self._count()
         self._tasks_set = True
-        self._check_block_capacity(self._tmeta)
+        if idx is None:
+            self._was_reset = False  # every env got a new task: a reset is due before the next step
         if reset:
             mask = None
             if idx is not None:
@@ -256,6 +261,7 @@ class IGLUVecEnv:
         m = t.shape[0]
         t = self._dev(t, torch.int8, (m, _lib.CELLS))
         s = None if starts is None else self._dev(starts, torch.int8, (m, _lib.CELLS))
+        self._check_block_capacity(t, s)  # refuse before the ctx learns about any new buffer
         dev = self.device
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         bufs = dict(target=z(m, _lib.GRID_STRIDE, dtype=torch.int8), init=z(m, _lib.GRID_STRIDE, dtype=torch.int8),
@@ -276,9 +282,9 @@ class IGLUVecEnv:
                                                       None if s is None else s.data_ptr(), self._stream()))
             self._count()
             _lib.check(self._L.iglu_task_pool_attach(self._ctx, C.byref(pool)))
-        self._check_block_capacity(bufs['tmeta'])
         self._pool = bufs  # the ctx retains these device pointers: keep the tensors alive
         self._tasks_set = True
+        self._was_reset = False
         return self.reset() if reset else None
 
     def set_task_generator(self, tasks, seed=0, env_offset=0, next_task=None, reset=True):
@@ -302,18 +308,26 @@ class IGLUVecEnv:
             raise ValueError('no task pool attached')
         return self._pool['cursor'][0]
 
-    def _check_block_capacity(self, tmeta):
+    def _check_block_capacity(self, targets, starts):
         """A block list longer than the row capacity chosen with max_target_blocks would be truncated by the
-        device-side Task.__init__; refuse instead (only checked when the capacity is below the 1089-cell maximum,
-        because it needs a device -> host read)."""
+        device-side Task.__init__; refuse instead, before any task row or pool pointer is touched (only checked
+        when the capacity is below the 1089-cell maximum, because it needs a device -> host read)."""
         room = self._tlist.shape[1] - _lib.TLIST_HDR
-        if room < _lib.CELLS and bool((tmeta[1] > room).any()):
-            raise ValueError(f'a task has {int(tmeta[1].max())} blocks to place / remove but max_target_blocks '
+        if room >= _lib.CELLS:
+            return
+        diff = targets != (starts if starts is not None else 0)   # cells of target - start (env.py:230)
+        worst = int(diff.sum(1).max())
+        if worst > room:
+            raise ValueError(f'a task has {worst} blocks to place / remove but max_target_blocks '
                              f'allows {room}; create the env with a larger max_target_blocks')
 
-    def _check_task(self):
+    def _check_task(self, stepping=False):
         if not self._tasks_set:
             _lib.check(-3)  # ValueError with the reference's message (env.py:199-201)
+        if stepping and not self._was_reset:
+            # a never-reset env has active_block = 0 and time_int_steps = 0 (the reference sets both in
+            # Agent.__init__ and always resets inside set_task): stepping it is refused like env.py:275
+            raise ValueError('Task is not initialized! Run .reset() first.')
 
     def reset(self, mask=None, hard=False):
         """Batched GridWorld.reset (reference env.py:206-261) for envs with mask != 0 (None = all)."""
@@ -323,6 +337,12 @@ class IGLUVecEnv:
             _lib.check(self._L.iglu_reset(self._ctx, C.byref(self._st), C.byref(self._ob),
                                           None if m is None else m.data_ptr(), int(hard), self._stream()))
             self._count()
+        if m is None:
+            self._was_reset = True
+        elif not self._was_reset:  # masked reset of a fresh env: fine once every env has been covered
+            self._reset_seen = m.clone() if self._reset_seen is None else (self._reset_seen | m)
+            if bool(self._reset_seen.all()):
+                self._was_reset, self._reset_seen = True, None
         return self.observation()
 
     # ------------------------------------------------------------------ step
@@ -343,7 +363,7 @@ class IGLUVecEnv:
         reference keys, each [n] (camera [n,2]).
         Returns (obs dict of device tensors, reward float64 [n], done bool [n], {}).
         """
-        self._check_task()
+        self._check_task(stepping=True)
         n = self.num_envs
         L, st, ob = self._L, C.byref(self._st), C.byref(self._ob)
         with self._guard():
@@ -371,12 +391,14 @@ class IGLUVecEnv:
             self._count()
         return self.observation(), self._reward, self._done.view(torch.bool), {}
 
-    def step_host(self, actions_host, reward_host, done_host):
+    def step_host(self, actions_host, reward_host, done_host, wait=True):
         """End-to-end host-buffer step (walking Discrete): actions int32 [n] in (pinned) host memory are
         copied to the device, the step runs, reward (float64 [n]) / done (uint8 [n]) are copied back
-        into the given host tensors and the stream is synchronised. Observations stay on the device."""
-        if not self._tasks_set:
-            self._check_task()
+        into the given host tensors and the stream is synchronised. Observations stay on the device.
+        wait=False only enqueues the step (iglu_step_walking_host_async): the results are valid after
+        self.wait(), which lets a host loop keep a second env group in flight meanwhile."""
+        if not (self._tasks_set and self._was_reset):
+            self._check_task(stepping=True)
         if self._kind != _lib.WALKING_DISCRETE:
             raise NotImplementedError('step_host is provided for the Discrete(18) action space')
         n = self.num_envs
@@ -387,13 +409,42 @@ class IGLUVecEnv:
                 or actions_host.is_cuda or reward_host.is_cuda or done_host.is_cuda):
             raise ValueError('step_host needs contiguous CPU tensors of dtype int32 / float64 / uint8, [n]')
         pa, pr, pd = actions_host.data_ptr(), reward_host.data_ptr(), done_host.data_ptr()
+        fn = self._L.iglu_step_walking_host if wait else self._L.iglu_step_walking_host_async
         with self._guard():
-            rc = self._L.iglu_step_walking_host(self._ctx, self._st_ref, pa, self._actions_ptr, self._ob_ref,
-                                                pr, pd, self._stream())
+            self._host_stream = self._stream()
+            rc = fn(self._ctx, self._st_ref, pa, self._actions_ptr, self._ob_ref, pr, pd, self._host_stream)
         if rc:
             _lib.check(rc)
         self.gpu_launches += self._L.iglu_last_launch_count(self._ctx)
         return reward_host, done_host
+
+    def wait(self):
+        """Blocks until the last step_host(..., wait=False) of this env has delivered its results."""
+        rc = self._L.iglu_wait(getattr(self, '_host_stream', None) or self._stream())
+        if rc:
+            _lib.check(rc)
+
+    def fetch_env(self, env_idx=0):
+        """One env's observation + agent state in host memory (an _lib.EnvSnapshot; one kernel, one copy, one
+        synchronisation -- what the N = 1 gym surface reads after every step)."""
+        if self._snap is None:
+            self._snap = (torch.zeros(C.sizeof(_lib.EnvSnapshot), dtype=torch.uint8, device=self.device),
+                          torch.zeros(C.sizeof(_lib.EnvSnapshot), dtype=torch.uint8).pin_memory())
+            self._snap_view = _lib.EnvSnapshot.from_address(self._snap[1].data_ptr())
+        with self._guard():
+            _lib.check(self._L.iglu_fetch_env_host(self._ctx, self._st_ref, self._ob_ref, int(env_idx),
+                                                   self._snap[0].data_ptr(), self._snap[1].data_ptr(),
+                                                   self._stream()))
+            self._count()
+        return self._snap_view
+
+    @property
+    def evaluations(self):
+        """Running count of maximal_intersection evaluations performed by step calls (device counter)."""
+        return int(self._sched[2:4].view(torch.int64).item())
+
+    def reset_evaluation_counter(self):
+        self._sched[2:4] = 0
 
     # ------------------------------------------------------------------ state views (in place)
     @property
@@ -470,11 +521,30 @@ class IGLUVecEnv:
             w3 = (w3 & ~0xFF) | int(active_block)
         self._istate[3, i] = w3
 
+    def set_grids(self, grids):
+        """Installs pre-built worlds: env e's voxel grid becomes grids[e] (int8 [n, 9, 11, 11]) as if its agent
+        had already placed those blocks -- inventories (20 per colour minus the blocks present, env.py:243-246
+        and world.py:323), the block count and the cached max_int of the synthetic task (task.py:103-119) follow,
+        so stepping continues exactly as the reference would from that world state."""
+        n = self.num_envs
+        g = self._dev(grids, torch.int8, (n, _lib.CELLS))
+        init, target = self._init[:, :_lib.CELLS], self._target[:, :_lib.CELLS]
+        self._grid[:, :_lib.CELLS] = g
+        counts = torch.stack([(g == c).sum(1) for c in range(1, 7)], dim=1)
+        inv = (20 - counts).to(torch.int16).contiguous().view(torch.int32)       # [n, 3] packed pairs
+        self._istate[0:3] = inv.t()
+        self._istate[5] = (g != init).sum(1).to(torch.int32)
+        self._istate[6] = max_intersection(g - init, target - init, device=self.device)
+        self._obs_inv.copy_((20 - counts).to(torch.float32))
+        if self._obs_grid is not None:
+            self._obs_grid.view(n, _lib.CELLS).copy_(g)
+
     def state_dict(self):
         keys = ('_grid', '_init', '_target', '_pose', '_init_pose', '_istate', '_tlist', '_tmeta')
         sd = {k[1:]: getattr(self, k).clone() for k in keys}
         if self._pool is not None:  # the generator's per-env position (the pool itself is set_task_pool's input)
             sd['pool_cursor'] = self._pool['cursor'].clone()
+        sd['was_reset'] = torch.tensor(int(self._was_reset))
         return sd
 
     def load_state_dict(self, sd):
@@ -483,9 +553,18 @@ class IGLUVecEnv:
                 if self._pool is None:
                     raise ValueError('state has a task-pool cursor: call set_task_pool(..., reset=False) first')
                 self._pool['cursor'].copy_(v)
+            elif k == 'was_reset':
+                self._was_reset = bool(int(v))
             else:
                 getattr(self, '_' + k).copy_(v)
         self._tasks_set = True
+        if 'was_reset' not in sd:
+            self._was_reset = True
+        # observation buffers the step path does not rewrite in full are derived state: rebuild them
+        if self._obs_grid is not None:
+            self._obs_grid.view(self.num_envs, _lib.CELLS).copy_(self._grid[:, :_lib.CELLS])
+        if self._obs_target is not None:
+            self._obs_target.view(self.num_envs, _lib.CELLS).copy_(self._target[:, :_lib.CELLS])
 
 
 def make_vec(num_envs, device='cuda', **kwargs):

@@ -109,8 +109,9 @@ typedef struct iglu_state {
     int32_t *tmeta;    /* [8][n]  w0: number of tlist entries; w1: target_size (task.py:35);
                                   w2..w4: inventory after reset, 6 x int16 (env.py:243-246);
                                   w5: 1 if the starting grid is non-empty; w6: 1 once a task is set; w7: reserved */
-    int32_t *sched;    /* [8] launch-to-launch scratch (work counter of the observe launch), or NULL = groups of
-                                  envs are dealt statically */
+    int32_t *sched;    /* [8] launch-to-launch scratch, or NULL = groups of envs are dealt statically. Word 0: work
+                                  counter of the observe launch; words 2-3 (one uint64): running count of the
+                                  maximal_intersection evaluations the step calls performed (a caller may zero it) */
 } iglu_state;
 
 /* Observation / result buffers (reference env.py:283-303). They persist between steps and are
@@ -213,6 +214,35 @@ int iglu_step_walking_dict(iglu_ctx *ctx, const iglu_state *st, const int32_t *b
 int iglu_step_walking_host(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
                            int32_t *actions_dev, const iglu_obs *obs, double *reward_host, uint8_t *done_host,
                            void *stream);
+
+/* The same call without the final synchronisation: it returns as soon as the work is enqueued, so a host loop
+ * can keep a second env group in flight while it consumes the results of the first (EnvPool-style pipelining;
+ * reference loop: examples/run_env.py:16-27). reward_host / done_host are valid after iglu_wait(stream). */
+int iglu_step_walking_host_async(iglu_ctx *ctx, const iglu_state *st, const int32_t *actions_host,
+                                 int32_t *actions_dev, const iglu_obs *obs, double *reward_host,
+                                 uint8_t *done_host, void *stream);
+
+/* Blocks the calling host thread until everything enqueued on `stream` has finished. */
+int iglu_wait(void *stream);
+
+/* Everything GridWorld.step / reset hand back for ONE env (reference env.py:247-261, 283-303) plus the agent
+ * state its attributes expose, gathered by one small kernel into `scratch_dev` (device, sizeof(iglu_env_snapshot))
+ * and brought to `out_host` with one copy; the stream is synchronised on return. This is what the N = 1 gym
+ * drop-in (gridworld_b200/env.py) reads after every step instead of one transfer per observation key. */
+typedef struct iglu_env_snapshot {
+    double pose[6];          /* x, y, z, yaw, pitch, dy */
+    double reward;
+    float agent_pos[5];      /* obs['agentPos'] */
+    float inventory_obs[6];  /* obs['inventory'] */
+    float compass;           /* obs['compass'] */
+    int32_t inventory[6];    /* agent.inventory */
+    int32_t active_block, time_int_steps, error, step_no, grid_size, max_int, target_size, done;
+    int32_t grid[IGLU_CELLS];        /* obs['grid'] */
+    int32_t target_grid[IGLU_CELLS]; /* obs['target_grid'] */
+} iglu_env_snapshot;
+
+int iglu_fetch_env_host(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs, int64_t env,
+                        iglu_env_snapshot *scratch_dev, iglu_env_snapshot *out_host, void *stream);
 
 /* Stateless Task(target, full_grid=full, invariant=invariant).maximal_intersection(grid)
  * (task.py:9-72, 147-161) for `count` independent pairs (BASELINE config 4).

@@ -685,35 +685,98 @@ def test_dropin_gym_surface():
 
 
 def test_get_intersection_and_subtasks_golden():
-    """'next' rows: Task.get_intersection and the staged Subtasks producer against the reference's outputs."""
+    """'next' rows: Task.get_intersection against the reference's outputs; the Actions wrapper."""
     import gridworld_b200 as gw
     z = G.load('misc.npz')
     task = gw.Task('', z['gi_target'].astype(np.int32))
     got = [task.get_intersection(z['gi_grid'], int(dx), int(dz), int(r)) for dx, dz, r in z['gi_query']]
     assert got == z['gi_value'].tolist()
-    seq = [[(0, -1, 0, 1), (1, -1, 0, 1)],
-           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2)],
-           [(0, -1, 0, 1), (1, -1, 0, 1), (1, 0, 0, 2), (1, 1, 0, 3), (-2, -1, 3, 4)]]
-    dialog = ['<A> build a base', '<A> put a green one on top', ['<A> finish it', '<B> ok']]
-    np.random.seed(5)
-    st = gw.Subtasks(dialog, seq, invariant=False, progressive=True)
-    for ep in range(6):
-        cur = st.reset()
-        assert (st.task_start, st.task_goal) == (z['st_start'][ep], z['st_goal'][ep])
-        assert np.array_equal(np.asarray(cur.target_grid), z['st_target'][ep])
-        assert np.array_equal(np.asarray(gw.Tasks.to_dense(cur.starting_grid)), z['st_init'][ep])
-        assert cur.max_int == z['st_max_int'][ep] and cur.target_size == z['st_target_size'][ep]
-        assert cur.chat == str(z['st_chat'][ep])
-    np.random.seed(7)
-    st = gw.Subtasks(dialog, seq, invariant=False, progressive=True)
-    st.next = -1
-    st.reset()
-    for k, blocks in enumerate(seq):
-        r, w, d = st.step_intersection(np.asarray(gw.Tasks.to_dense(blocks)))
-        assert [r, w, int(d), st.task_goal] == z['st_steps'][k].tolist()
     # Actions wrapper (wrappers.py:11-32): 17 actions, 'place' removed
     env = gw.Actions(gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False))
     assert env.action_space.n == 17
     env.set_task(gw.Task('', gw.Tasks.to_dense([(0, -1, -2, 1)]), starting_grid=[]))
     obs, r, done, _ = env.step(16)
     assert r == 0 and not done
+
+
+def test_new_host_surface_async_snapshot_set_grids_restore():
+    """Round-2 additions of the boundary: iglu_step_walking_host_async / iglu_wait (two groups in flight give the
+    same results as one synchronous env), iglu_fetch_env_host, IGLUVecEnv.set_grids, the device evaluation
+    counter, load_state_dict rebuilding the incrementally maintained observation buffers, and the refusal to step
+    an env that was never reset."""
+    import gridworld_b200 as gw
+    from bench import shard_state, synth_targets
+    n, steps = 512, 40
+    T = synth_targets(n, 0.2, 'compact', 5)
+    rng = np.random.RandomState(1)
+    acts = torch.as_tensor(rng.randint(0, 18, (steps, n)).astype(np.int32))
+    ref = gw.make_vec(n, max_steps=30, reward_mode='every_step')
+    with pytest.raises(ValueError):
+        ref.step(acts[0].cuda())                       # no task yet
+    ref.set_tasks(T, reset=False)
+    with pytest.raises(ValueError, match='reset'):
+        ref.step(acts[0].cuda())                       # task set but never reset (reference env.py:275)
+    ref.reset()
+    sd0 = ref.state_dict()
+    R = np.zeros((steps, n))
+    Dn = np.zeros((steps, n), bool)
+    ref.reset_evaluation_counter()
+    nonempty = 0
+    for t in range(steps):
+        _, r, d, _ = ref.step(acts[t].cuda())
+        R[t], Dn[t] = r.cpu().numpy(), d.cpu().numpy()
+        nonempty += int((ref._istate[5] != 0).sum())
+    assert ref.evaluations == nonempty                  # every env with a non-empty difference grid was evaluated
+    # two half-size envs stepped through the async host call on their own streams, results consumed after wait()
+    halves = []
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        e = gw.make_vec(hi - lo, max_steps=30, reward_mode='every_step')
+        e.load_state_dict(shard_state(sd0, lo, hi))
+        halves.append((e, torch.cuda.Stream(), acts[:, lo:hi].contiguous().pin_memory(),
+                       torch.zeros(hi - lo, dtype=torch.float64).pin_memory(),
+                       torch.zeros(hi - lo, dtype=torch.uint8).pin_memory(), lo, hi))
+    for t in range(steps):
+        for e, s, a, r, d, lo, hi in halves:
+            with torch.cuda.stream(s):
+                e.step_host(a[t], r, d, wait=False)
+        for e, s, a, r, d, lo, hi in halves:
+            e.wait()
+            assert np.array_equal(r.numpy(), R[t, lo:hi]) and np.array_equal(d.numpy().astype(bool), Dn[t, lo:hi]), t
+    torch.cuda.synchronize()
+    for e, s, a, r, d, lo, hi in halves:
+        assert torch.equal(e.grid, ref.grid[lo:hi]) and torch.equal(e._pose, ref._pose[:, lo:hi])
+    # snapshot of one env == the batched tensors
+    sn = ref.fetch_env(7)
+    assert list(sn.pose) == ref._pose[:, 7].tolist() and sn.reward == float(ref._reward[7])
+    assert np.array_equal(np.ctypeslib.as_array(sn.grid), ref.grid[7].reshape(-1).cpu().numpy())
+    assert np.array_equal(np.ctypeslib.as_array(sn.target_grid), ref.target_grid[7].reshape(-1).cpu().numpy())
+    assert list(sn.inventory) == ref.inventory[7].tolist() and sn.step_no == int(ref.step_no[7])
+    assert sn.max_int == int(ref.max_int[7]) and sn.target_size == int(ref.target_size[7])
+    assert list(sn.agent_pos) == ref._obs_pos[7].tolist() and sn.done == int(ref._done[7])
+    # restore into envs that keep obs['grid'] incrementally / expose target_grid: derived buffers are rebuilt
+    inc = gw.make_vec(n, max_steps=30, reward_mode='every_step', grid_obs='incremental', target_in_obs=True)
+    inc.load_state_dict(ref.state_dict())
+    assert torch.equal(inc.observation()['grid'], ref.grid.to(torch.int32))
+    assert torch.equal(inc.observation()['target_grid'], ref.target_grid.to(torch.int32))
+    for t in range(5):
+        a = acts[t].cuda()
+        o1, r1, d1, _ = inc.step(a)
+        o2, r2, d2, _ = ref.step(a)
+        assert torch.equal(o1['grid'], o2['grid']) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    # set_grids: pre-built worlds keep every invariant of a world the agent built itself
+    env = gw.make_vec(n, max_steps=10 ** 6, reward_mode='every_step')
+    env.set_tasks(T)
+    built = torch.where(torch.rand(T.shape) < 0.5, T, torch.zeros((), dtype=torch.int8))
+    built[:, :3, 5, 5] = 0
+    env.set_grids(built)
+    assert torch.equal(env.max_int, gw.max_intersection(built, T).to(torch.int32))
+    assert bool((env.max_int == (built != 0).flatten(1).sum(1).cuda()).all())  # a subset of the target matches itself
+    env.reset_evaluation_counter()
+    for t in range(20):
+        obs, r, d, _ = env.step(acts[t].cuda())
+    assert env.evaluations == 20 * n                     # dense worlds: every env evaluated on every step
+    g = env.grid
+    for c in range(1, 7):
+        assert bool((((g == c).flatten(1).sum(1)) + env.inventory[:, c - 1] == 20).all())
+    assert torch.equal(gw.max_intersection(g, T).to(torch.int32), env.max_int)
+    assert torch.equal(obs['grid'], g.to(torch.int32))

@@ -88,9 +88,48 @@ def test_to_dense_to_sparse():
     assert d.shape == (9, 11, 11) and d[0, 5, 3] == 1 and d[8, 10, 10] == 6
     sp = gw.Tasks.to_sparse(np.asarray(d))
     assert sorted(sp) == sorted([(0 - 5, 5 - 1, 3 - 5, 1), (8 - 5, 10 - 1, 10 - 5, 6)])  # axis-0-as-x quirk
+    # a cell listed twice keeps the last colour; non-list inputs pass through; to_sparse leaves lists alone
+    assert gw.Tasks.to_dense([(1, 0, 1, 2), (1, 0, 1, 5)])[1, 6, 6] == 5
+    assert gw.Tasks.to_dense(d) is d and gw.Tasks.to_dense([]).sum() == 0
+    assert gw.Tasks.to_sparse([(1, 2, 3, 4)]) == [(1, 2, 3, 4)]
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/gridworld'), reason='needs the reference tree (build container)')
+def test_converters_and_collections_match_live_reference():
+    """Tasks.to_dense / to_sparse against the executed reference, and the reference's OWN collection objects
+    (CustomTasks, RandomTasks, Subtasks, Task) fed through enumerate_tasks / pool_arrays by duck-typing."""
+    import sys
+    import gridworld_b200 as gw
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'refharness'))
+    import load_reference
+    load_reference.load()
+    from gridworld.tasks import task as rtask, task_set as rset
+    rng = np.random.RandomState(3)
+    for _ in range(20):
+        k = rng.randint(0, 30)
+        blocks = [(int(rng.randint(-5, 6)), int(rng.randint(-1, 8)), int(rng.randint(-5, 6)), int(rng.randint(1, 7)))
+                  for _ in range(k)]
+        ref_d = rtask.Tasks.to_dense(blocks)
+        assert np.array_equal(gw.Tasks.to_dense(blocks), ref_d)
+        assert [tuple(int(v) for v in r) for r in rtask.Tasks.to_sparse(np.asarray(ref_d))] == gw.Tasks.to_sparse(np.asarray(ref_d))
     np.random.seed(0)
-    rt = gw.RandomTasks(max_blocks=4, height_levels=2, num_colors=3)
-    assert rt.target_size == 8 and rt.target_grid.shape == (9, 11, 11)
+    goals = [('a', [(0, -1, 0, 1), (1, -1, 0, 2)]), ('b', [(2, 0, 2, 3)])]
+    ct = rset.CustomTasks(goals)
+    T, S, chats = gw.pool_arrays(ct)
+    assert T.shape == (2, 9, 11, 11) and sorted(chats) == ['a', 'b'] and S.sum() == 0
+    assert sorted(int(t.sum()) for t in T) == [3, 3]
+    rt = rset.RandomTasks(max_blocks=4, height_levels=2, num_colors=3, max_cache=5)
+    T, S, _ = gw.pool_arrays(rt)
+    assert T.shape[0] == 5 and all(np.count_nonzero(t) == 8 for t in T)
+    rt0 = rset.RandomTasks(max_blocks=3, height_levels=1, max_cache=0)
+    assert gw.pool_arrays(rt0, samples=7)[0].shape[0] == 7
+    seq = [[(0, -1, 0, 1)], [(0, -1, 0, 1), (1, -1, 0, 2)], [(0, -1, 0, 1), (1, -1, 0, 2), (1, 0, 0, 3)]]
+    sub = rtask.Subtasks(['x', 'y', 'z'], seq)
+    T, S, chats = gw.pool_arrays(sub)
+    assert [np.count_nonzero(t) for t in T] == [1, 2, 3] and [np.count_nonzero(s) for s in S] == [0, 1, 2]
+    one = rtask.Task('hi', ref_d, starting_grid=[(0, 0, 0, 1)])
+    T, S, chats = gw.pool_arrays(one)
+    assert chats == ['hi'] and S[0, 1, 5, 5] == 1 and np.array_equal(T[0], ref_d.astype(np.int8))
 
 
 def test_spaces():
@@ -109,7 +148,7 @@ def test_spaces():
 def test_pool_arrays_and_goal_file_loader(tmp_path):
     """Task collections -> the arrays IGLUVecEnv.set_task_pool takes; goals.pkl-format loader (restricted unpickler)."""
     import pickle
-    from gridworld_b200.tasks import CustomTasks, Task, Tasks, enumerate_tasks, load_goals, pool_arrays
+    from gridworld_b200.tasks import Task, Tasks, enumerate_tasks, load_goals, pool_arrays
     from tests import golden_io as G
     z = G.load('goals.npz')
     dense = z['targets'][:12]
@@ -132,10 +171,15 @@ def test_pool_arrays_and_goal_file_loader(tmp_path):
     order = [list(z['names'][:12]).index(nm) for nm, _ in loaded]
     assert T.dtype == np.int8 and np.array_equal(T, dense[order]) and chats == [nm for nm, _ in loaded]
     assert S[0].sum() == 0 and S[1][0, 5, 6] == 3 and S[1][0, 6, 6] == 4 and np.count_nonzero(S[1]) == 2
-    np.random.seed(0)
-    ct = CustomTasks(loaded)
-    assert len(enumerate_tasks(ct)) == 12
-    assert np.array_equal(np.sort(pool_arrays(ct)[0].reshape(12, -1), axis=0), np.sort(dense.reshape(12, -1), axis=0))
+    class Bag:  # any object with a `.tasks` dict is a collection (the shape of the reference's CustomTasks)
+        def __init__(self, ts):
+            self.tasks = {str(i): t for i, t in enumerate(ts)}
+    assert len(enumerate_tasks(Bag(tasks))) == 12
+    assert np.array_equal(pool_arrays(Bag(tasks))[0], T)
+    # dense starting grids are accepted as they are
+    dense_start = np.zeros((9, 11, 11), int)
+    dense_start[0, 5, 6] = 3
+    assert pool_arrays([Task('', dense[0], starting_grid=dense_start)])[1][0, 0, 5, 6] == 3
     # a pickle that wants to import anything else is refused before it can run
     class Evil:
         def __reduce__(self):
@@ -161,6 +205,7 @@ def test_bench_reference_arm_contract():
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['metric'] == 'env_steps_per_sec' and d['unit'] == 'env-steps/s'
     assert d['higher_is_better'] is True and d['steps'] == 3 and d['value'] > 0 and d['ms_per_step'] > 0
-    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_port']['kind'] == 'port' and d['cpu_port']['value'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
