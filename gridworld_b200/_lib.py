@@ -43,6 +43,12 @@ class TaskPool(C.Structure):
                 ('seed', C.c_uint64), ('env_offset', C.c_int64)]
 
 
+class RandomTaskSpec(C.Structure):
+    """iglu_random_task_spec (include/iglu_b200.h)"""
+    _fields_ = [('max_blocks', C.c_int32), ('height_levels', C.c_int32), ('max_dist', C.c_int32),
+                ('num_colors', C.c_int32)]
+
+
 class EnvSnapshot(C.Structure):
     """iglu_env_snapshot (include/iglu_b200.h)"""
     _fields_ = [('pose', C.c_double * 6), ('reward', C.c_double), ('agent_pos', C.c_float * 5),
@@ -57,7 +63,7 @@ EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_des
            'iglu_reset', 'iglu_step_walking', 'iglu_step_flying', 'iglu_step_walking_dict',
            'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
            'iglu_task_pool_prepare', 'iglu_task_pool_attach', 'iglu_step_walking_host_async', 'iglu_wait',
-           'iglu_fetch_env_host')
+           'iglu_fetch_env_host', 'iglu_max_intersection_strided', 'iglu_sample_tasks')
 
 _lib = None
 
@@ -92,6 +98,10 @@ def load():
     L.iglu_wait.argtypes = [vp]
     L.iglu_fetch_env_host.argtypes = [vp, C.POINTER(State), C.POINTER(Obs), i64, vp, vp, vp]
     L.iglu_max_intersection.argtypes = [vp, vp, vp, i32, vp, vp, i64, vp]
+    if hasattr(L, 'iglu_max_intersection_strided'):  # absent from older A/B builds selected through IGLU_B200_SO
+        L.iglu_max_intersection_strided.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, vp, i64, vp]
+    if hasattr(L, 'iglu_sample_tasks'):
+        L.iglu_sample_tasks.argtypes = [vp, i64, C.POINTER(RandomTaskSpec), C.c_uint64, i64, vp]
     L.iglu_last_launch_count.argtypes = [vp]
     L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]
     L.iglu_task_pool_attach.argtypes = [vp, C.POINTER(TaskPool)]

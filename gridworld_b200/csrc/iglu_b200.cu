@@ -10,7 +10,7 @@
 //   phase B (warp-cooperative, one env at a time): the env's int8 grid and its target block list are brought
 //            into shared memory by TMA bulk copies (cp.async.bulk + mbarrier) through a per-warp ring; the
 //            grid is widened into the int32 obs['grid'] with 16-byte streaming stores and
-//            Task.maximal_intersection is evaluated (iglu_reward.cuh) when required;
+//            Task.maximal_intersection is evaluated (iglu_reward.cuh: shift voting) when required;
 //   phase C (one thread per env): Task.step_intersection bookkeeping, reward, done (task.py:103-119,
 //            env.py:290-296).
 // k_task_prep (Task.__init__), k_reset (GridWorld.reset), k_max_intersection (stateless reward sweep).
@@ -42,8 +42,7 @@ constexpr int WARPS_PER_CTA = IGLU_WARPS_PER_CTA;
 #ifndef IGLU_MI_CTAS
 #define IGLU_MI_CTAS 1
 #endif
-// stateless reward sweep: one 24-warp CTA per SM (198 KB of shared memory). Measured on 1 M pairs, compact rho=0.2:
-// 8x2 warps 2.38 ms, 10x2 2.24, 12x2 2.10, 24x1 1.97, 27x1 1.97 (profiles/r01_mi_occupancy_variants.log)
+// stateless reward sweep: one 24-warp CTA per SM (216 KB of shared memory)
 constexpr int MI_WARPS = IGLU_MI_WARPS;
 constexpr int MI_CTAS = IGLU_MI_CTAS;
 constexpr int CTAS_PER_SM = 2;   // 16 warps / SM: measured faster than 20 / 24 / 32 warps with fewer registers (profiles/)
@@ -56,7 +55,7 @@ struct __align__(16) Slot {
     uint16_t trow[TL_HDR + TL_PRE];    // rectangle header + first target blocks
 };
 
-constexpr size_t TABLE_BYTES = SPREAD_N * sizeof(unsigned long long);
+constexpr size_t TABLE_BYTES = (CELL_LUT_N * sizeof(uint16_t) + 15) & ~(size_t)15;  // cell -> (y, 22 x + z) table per CTA
 
 struct StepParams {
     iglu_state st;
@@ -222,13 +221,14 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     constexpr int NBUF = StepCfg<PHASES>::NBUF;
     constexpr bool HAS_A = PHASES != 2, HAS_B = PHASES != 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
     WarpScratchT<NBUF> *scratch = reinterpret_cast<WarpScratchT<NBUF> *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     WarpScratchT<NBUF> &ws = scratch[HAS_B ? wid : 0];
     if (PHASES == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the observe launch get resident early
     if (HAS_B) {
-        build_spread_table(tbl, threadIdx.x, WPC * 32);
+        build_cell_lut(lut, threadIdx.x, WPC * 32);
+        for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;  // invariant of eval_max_intersection
         if (lane == 0) {
 #pragma unroll
             for (int s = 0; s < NBUF; s++) mbar_init(&ws.bar[s], 1);
@@ -264,13 +264,15 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
     // The observe launch hands groups out dynamically (one atomic per group on a counter the physics launch
     // zeroed; the next index is fetched while the current group is processed): per-env cost varies with the
     // evaluation, and a static deal leaves the SMs unevenly loaded in the single wave.
+    // Every warp's FIRST group is its static index (thousands of warps asking one counter at kernel start would
+    // serialise in the L2: 22 % of round 1's stall samples); the counter only deals the groups after those.
     const bool dynamic = PHASES == 2 && p.dynamic;
     if (PHASES == 1 && p.st.sched != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.st.sched[0] = 0;
+    const int total_warps = (int)gridDim.x * WPC;
     int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x;
-    if (dynamic) grp = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(p.st.sched, 1) : 0, 0);
     while (grp < ngroups) {
         int grp_next = 0;
-        if (dynamic && lane == 0) grp_next = atomicAdd(p.st.sched, 1);
+        if (dynamic && lane == 0) grp_next = total_warps + atomicAdd(p.st.sched, 1);
         auto env_of = [&](int j) -> int64_t { return grp * GS + j; };
         const int64_t i = env_of(lane);
         const bool valid = lane < GS && i < n;
@@ -279,9 +281,9 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
         // ------------------------------------------------------------- phase A
         int w[8], tm[6];
 #pragma unroll
-        for (int c = 0; c < 8; c++) w[c] = p.st.istate[c * n + ii];
+        for (int c = 0; c < 8; c++) w[c] = (HAS_A || c >= 3) ? p.st.istate[c * n + ii] : 0;  // w0..w2: inventory, physics only
 #pragma unroll
-        for (int c = 0; c < 6; c++) tm[c] = p.st.tmeta[c * n + ii];
+        for (int c = 0; c < 6; c++) tm[c] = (HAS_A || c < 2 || c == 5) ? p.st.tmeta[c * n + ii] : 0;
         Agent a;
         if (HAS_A) {
             a.x = p.st.pose[0 * n + ii]; a.y = p.st.pose[1 * n + ii]; a.z = p.st.pose[2 * n + ii];
@@ -456,11 +458,17 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                     const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
                     int r;
                     if (single_shift_rects(rc, 4)) {  // zone-spanning target: one shift per rotation, compare bytes
+                        auto each = [&](auto f) {
+                            for (int b = lane; b < nb; b += 32) {
+                                const uint32_t e = tl[b];
+                                f(e & 15, (e >> 4) & 15, (e >> 8) & 15, e >> 12);
+                            }
+                        };
                         r = eval_single_shift<false>(reinterpret_cast<const int8_t *>(sl.grid),
-                                                     hs ? p.st.init + ej * GSTRIDE : nullptr, tl, nb, rc, 4, lane, nullptr);
+                                                     hs ? p.st.init + ej * GSTRIDE : nullptr, each, rc, 4, nullptr);
                     } else {
-                        build_rows(ws.es, sl.grid, p.st.init + ej * GSTRIDE, hs, lane);
-                        r = eval_max_intersection<false, false>(ws.es, tbl, tl, nb, rc, 4, lane, nullptr);
+                        r = eval_max_intersection<false>(ws.es, sl.grid, hs ? p.st.init + ej * GSTRIDE : nullptr, lut, tl,
+                                                         nb, rc, 4, lane, nullptr);
                     }
                     if (keep && lane == j) mi_eval = r;
                     if (keep) evals_done++;
@@ -624,6 +632,46 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
     }
 }
 
+// ------------------------------------------------------------------ random task structures on the device
+// RandomTasks.sample_task (task_set.py:135-157), one thread per task, with the counter-based stream documented in
+// include/iglu_b200.h (iglu_sample_tasks). Writes dense int8 [m][1089] targets: the input format of iglu_set_tasks /
+// iglu_task_pool_prepare, so a task pool can be (re)filled without the host.
+__device__ __forceinline__ uint32_t sample_draw(uint64_t seed, int64_t task, uint32_t &counter, uint32_t range) {
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(task + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(counter++);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (uint32_t)(((x >> 32) * (uint64_t)range) >> 32);
+}
+
+__global__ void __launch_bounds__(128) k_sample_tasks(int8_t *__restrict__ out, int64_t m, iglu_random_task_spec spec,
+                                                      uint64_t seed, int64_t first_task) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m) return;
+    int8_t *g = out + t * CELLS;
+    for (int c = 0; c < CELLS; c++) g[c] = 0;
+    uint32_t ctr = 0;
+    const uint32_t span = (uint32_t)(2 * spec.max_dist + 1);
+    for (int h = 0; h < spec.height_levels && h < 9; h++) {
+        const int bx = (int)sample_draw(seed, first_task + t, ctr, 11u);
+        const int bz = (int)sample_draw(seed, first_task + t, ctr, 11u);
+        int color = (int)sample_draw(seed, first_task + t, ctr, (uint32_t)spec.num_colors) + 1;
+        g[h * 121 + bx * 11 + bz] = (int8_t)color;
+        for (int b = 1; b < spec.max_blocks; b++) {
+            int x = 0, z = 0;
+            bool ok = false;
+            for (int tries = 0; tries < 4096 && !ok; tries++) {   // the reference redraws without a bound
+                const int ddx = (int)sample_draw(seed, first_task + t, ctr, span) - spec.max_dist;
+                const int ddz = (int)sample_draw(seed, first_task + t, ctr, span) - spec.max_dist;
+                color = (int)sample_draw(seed, first_task + t, ctr, (uint32_t)spec.num_colors) + 1;
+                x = bx + ddx; z = bz + ddz;
+                ok = !(ddx == 0 && ddz == 0) && x < 11 && z < 11 && x >= 0 && z >= 0 && g[h * 121 + x * 11 + z] == 0;
+            }
+            if (ok) g[h * 121 + x * 11 + z] = (int8_t)color;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ reset
 // GridWorld.reset (env.py:206-261). One warp per env.
 __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, const uint8_t *__restrict__ mask,
@@ -680,118 +728,123 @@ __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, cons
 }
 
 // ------------------------------------------------------------------ stateless reward sweep
-// Task(target, full_grid, invariant).maximal_intersection(grid) per pair (BASELINE config 4).
+// Task(target, full_grid, invariant).maximal_intersection(grid) per pair (BASELINE config 4). One warp per pair.
+// The rows of the dense [count][stride] arrays are brought into shared memory by TMA bulk copies of the 16-byte
+// aligned window around each row (a granule that holds a valid byte lies in the same page: nothing outside the
+// caller's pages is touched), double buffered per warp so that pair i + 1 arrives while pair i is evaluated; the
+// consumers read the cells at their byte offset inside the window (Staged<false>), or directly when the caller's
+// rows are 16-byte aligned (stride 1104, the env state layout: Staged<true>). No block list is built: the target's
+// blocks register for the vote straight from the staged target grid.
+constexpr int PBUF = GSTRIDE + 32;   // window: <= 15 bytes before the row + 1089 cells, rounded to 16, + over-read word
 struct __align__(16) PairScratch {
-    uint32_t grid[GSTRIDE / 4];
-    uint32_t tgt[GSTRIDE / 4];
-    uint16_t list[IGLU_TLIST_MAX];
+    uint32_t grid[2][PBUF / 4];
+    uint32_t tgt[2][PBUF / 4];
     EvalScratch es;
+    uint16_t tkey[32];               // key of the target block registered in slot t of the current pass
+    unsigned long long bar[2];
 };
 
-// Copies the 1089 cells at `src` (any alignment) into a 16-byte aligned shared-memory buffer of GSTRIDE
-// bytes (pad zeroed) with coalesced 4-byte global loads + funnel shifts. `last_word` is the aligned word
-// holding the last byte of the whole source array; nothing beyond it is read.
-__device__ __forceinline__ void load_cells_smem(uint32_t *dst, const int8_t *src, const uint32_t *last_word, int lane) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    const int sh = (int)(a & 3) * 8;
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    uint32_t lo[9], hi[9];
-#pragma unroll
-    for (int it = 0; it < 9; it++) {
-        const int i = lane + 32 * it;
-        lo[it] = (i <= 272 && w + i <= last_word) ? __ldg(w + i) : 0u;
-        hi[it] = (i <= 272 && w + i + 1 <= last_word) ? __ldg(w + i + 1) : 0u;
-    }
-#pragma unroll
-    for (int it = 0; it < 9; it++) {
-        const int i = lane + 32 * it;
-        uint32_t v = __funnelshift_r(lo[it], hi[it], sh);
-        if (i == 272) v &= 0xFFu;       // cells 1088 | pad
-        if (i > 272) v = 0u;
-        if (i < GSTRIDE / 4) dst[i] = v;
-    }
-}
-
-// Bounding box (x_min, x_max, z_min, z_max) of the non-zero cells of a staged grid; empty = (10, 0, 10, 0).
-__device__ __forceinline__ void bbox_smem(const uint32_t *g, int lane, int &xmin, int &xmax, int &zmin, int &zmax) {
-    int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
-    for_each_nonzero_cell(g, nullptr, lane, [&](int c, int, int) {
-        const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-    });
-    xmin = __reduce_min_sync(0xffffffffu, x0); xmax = __reduce_max_sync(0xffffffffu, x1);
-    zmin = __reduce_min_sync(0xffffffffu, z0); zmax = __reduce_max_sync(0xffffffffu, z1);
-}
-
-// Ordered (ascending cell index) list of the non-zero cells of a staged target grid + their bounding box.
-// Lane L owns the 36 cells [36 L, 36 L + 36): count, exclusive scan over lanes, emit. Returns the count.
-__device__ __forceinline__ int compact_target(const uint32_t *t, uint16_t *list, int lane, int &xmin, int &xmax,
-                                              int &zmin, int &zmax) {
-    const int cnt = count_nonzero_cells(t, lane);
-    int pos = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, pos, d);
-        if (lane >= d) pos += o;
-    }
-    const int total = __shfl_sync(0xffffffffu, pos, 31);
-    pos -= cnt;
-    int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
-    for_each_nonzero_cell(t, nullptr, lane, [&](int c, int tv, int) {
-        const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-        list[pos++] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(tv) << 12));
-        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-    });
-    xmin = __reduce_min_sync(0xffffffffu, x0); xmax = __reduce_max_sync(0xffffffffu, x1);
-    zmin = __reduce_min_sync(0xffffffffu, z0); zmax = __reduce_max_sync(0xffffffffu, z1);
-    return total;
-}
-
-template <bool CLIP, bool WANT_KEY>
+template <bool WANT_KEY, bool ALIGNED>
 __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
                                                                      const int8_t *__restrict__ fulls,
+                                                                     int64_t gstride, int64_t tstride, int64_t fstride,
                                                                      int invariant, int32_t *__restrict__ out,
                                                                      int32_t *__restrict__ argmax, int64_t count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned long long *tbl = reinterpret_cast<unsigned long long *>(smem_raw);
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
     PairScratch *scratch = reinterpret_cast<PairScratch *>(smem_raw + TABLE_BYTES);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     PairScratch &ps = scratch[wid];
-    build_spread_table(tbl, threadIdx.x, MI_WARPS * 32);
+    build_cell_lut(lut, threadIdx.x, MI_WARPS * 32);
+    for (int q = lane; q < NKEY; q += 32) ps.es.kmask[q] = 0u;
+    if (lane == 0) {
+        mbar_init(&ps.bar[0], 1);
+        mbar_init(&ps.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    const int64_t total_bytes = count * CELLS;
-    auto last_word_of = [&](const int8_t *base) {
-        return reinterpret_cast<const uint32_t *>((reinterpret_cast<uintptr_t>(base) + total_bytes - 1) & ~(uintptr_t)3);
+    const int64_t step = (int64_t)gridDim.x * MI_WARPS;
+    auto issue = [&](int64_t pr, int b) {   // lane 0: both rows of pair `pr` -> buffer b
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(grids + pr * gstride);
+        const uintptr_t ta = reinterpret_cast<uintptr_t>(targets + pr * tstride);
+        const uint32_t gbytes = ALIGNED ? (uint32_t)GSTRIDE : (uint32_t)(((ga & 15) + CELLS + 15) & ~(uintptr_t)15);
+        const uint32_t tbytes = ALIGNED ? (uint32_t)GSTRIDE : (uint32_t)(((ta & 15) + CELLS + 15) & ~(uintptr_t)15);
+        mbar_expect_tx(&ps.bar[b], gbytes + tbytes);
+        tma_load(ps.grid[b], reinterpret_cast<const void *>(ga & ~(uintptr_t)15), gbytes, &ps.bar[b]);
+        tma_load(ps.tgt[b], reinterpret_cast<const void *>(ta & ~(uintptr_t)15), tbytes, &ps.bar[b]);
     };
-    const uint32_t *glast = last_word_of(grids), *tlast = last_word_of(targets);
-    const uint32_t *flast = fulls ? last_word_of(fulls) : nullptr;
-    for (int64_t pr = (int64_t)blockIdx.x * MI_WARPS + wid; pr < count; pr += (int64_t)gridDim.x * MI_WARPS) {
-        load_cells_smem(ps.grid, grids + pr * CELLS, glast, lane);
-        load_cells_smem(ps.tgt, targets + pr * CELLS, tlast, lane);
-        __syncwarp();
-        int xmin, xmax, zmin, zmax;
-        const int nout = compact_target(ps.tgt, ps.list, lane, xmin, xmax, zmin, zmax);
+    int64_t pr = (int64_t)blockIdx.x * MI_WARPS + wid;
+    if (pr < count && lane == 0) issue(pr, 0);
+    for (uint32_t it = 0; pr < count; pr += step, it++) {
+        const int b = it & 1;
+        if (pr + step < count && lane == 0) issue(pr + step, b ^ 1);   // its last readers finished an iteration ago
+        mbar_wait(&ps.bar[b], (it >> 1) & 1u);
+        const int goff = ALIGNED ? 0 : (int)(reinterpret_cast<uintptr_t>(grids + pr * gstride) & 15);
+        const int toff = ALIGNED ? 0 : (int)(reinterpret_cast<uintptr_t>(targets + pr * tstride) & 15);
+        const Staged<ALIGNED> G{ps.grid[b] + (goff >> 2), 8 * (goff & 3)};
+        const Staged<ALIGNED> T{ps.tgt[b] + (toff >> 2), 8 * (toff & 3)};
+        // ---- target: block count per lane (slots for the vote passes) and bounding box ----
+        int cnt = 0, x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+        for_each_nonzero_cell(T, nullptr, lane, [&](int c, int, int) {
+            const int xz = lut[c] & 0xFFF, x = (xz * 2979) >> 16, z = xz - HROW * x;   // x = xz / 22 for xz <= 230
+            x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+            cnt++;
+        });
+        int pos = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, pos, d);
+            if (lane >= d) pos += o;
+        }
+        const int nout = __shfl_sync(0xffffffffu, pos, 31);
+        pos -= cnt;   // first slot of this lane's blocks
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
         if (invariant) {
-            if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid
-                __syncwarp();
-                load_cells_smem(ps.tgt, fulls + pr * CELLS, flast, lane);
-                __syncwarp();
-                bbox_smem(ps.tgt, lane, xmin, xmax, zmin, zmax);
+            if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid (rare: read straight from global)
+                x0 = 10; x1 = 0; z0 = 10; z1 = 0;
+                const int8_t *f = fulls + pr * fstride;
+                for (int c = lane; c < CELLS; c += 32)
+                    if (f[c] != 0) {
+                        const int xz = lut[c] & 0xFFF, x = (xz * 2979) >> 16, z = xz - HROW * x;
+                        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+                    }
             }
-            rc = rects_from_bbox(xmin, xmax, zmin, zmax);
+            x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+            z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+            rc = rects_from_bbox(x0, x1, z0, z1);
             n_rot = 4;
         }
-        __syncwarp();
         int key = -1, best;
-        if (!CLIP && single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
-            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(ps.grid), nullptr, ps.list, nout, rc,
-                                               n_rot, lane, &key);
+        if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
+            auto each = [&](auto f) {
+                for_each_nonzero_cell(T, nullptr, lane, [&](int c, int tv, int) {
+                    const int l = lut[c], xz = l & 0xFFF, x = (xz * 2979) >> 16;
+                    f(l >> 12, x, xz - HROW * x, code_of(tv));
+                });
+            };
+            best = eval_single_shift<WANT_KEY>(G.bytes(), nullptr, each, rc, n_rot, &key);
         } else {
-            build_rows(ps.es, ps.grid, nullptr, false, lane);
-            best = eval_max_intersection<CLIP, WANT_KEY>(ps.es, tbl, ps.list, nout, rc, n_rot, lane, &key);
+            auto reg = [&](int c0) {      // this lane's blocks whose slot falls into [c0, c0 + 32)
+                if (pos < c0 + 32 && pos + cnt > c0) {
+                    int slot = pos;
+                    for_each_nonzero_cell(T, nullptr, lane, [&](int c, int tv, int) {
+                        const int t = slot++ - c0;
+                        if ((unsigned)t < 32u) {
+                            const int l = lut[c], xz = l & 0xFFF, x = (xz * 2979) >> 16;
+                            ps.tkey[t] = (uint16_t)register_target(ps.es, t, l >> 12, x, xz - HROW * x, code_of(tv));
+                        }
+                    });
+                }
+            };
+            auto unreg = [&](int c0) {
+                if (c0 + lane < nout) {
+                    const uint16_t k = ps.tkey[lane];
+                    if (k != 0xFFFFu) ps.es.kmask[k] = 0u;
+                }
+            };
+            best = eval_votes<WANT_KEY, ALIGNED>(ps.es, G, nullptr, lut, nout, reg, unreg, rc, n_rot, lane, &key);
         }
         if (lane == 0) {
             out[pr] = best;
@@ -801,7 +854,7 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
                 argmax[3 * pr + 0] = dx; argmax[3 * pr + 1] = dz; argmax[3 * pr + 2] = k;
             }
         }
-        __syncwarp();
+        __syncwarp();  // every lane is done with buffer b before the next iteration refills it
     }
 }
 
@@ -921,6 +974,16 @@ extern "C" int iglu_task_pool_prepare(iglu_ctx *ctx, const iglu_task_pool *pool,
     k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(st, obs, ctx->cfg, target, start, nullptr,
                                                                          nullptr, pool->m);
     ctx->last_launches = 1;
+    return check(cudaPeekAtLastError());
+}
+
+extern "C" int iglu_sample_tasks(int8_t *targets, int64_t m, const iglu_random_task_spec *spec, uint64_t seed,
+                                 int64_t first_task, void *stream) {
+    if (!targets || m <= 0 || !spec) return IGLU_ERR_INVALID_ARG;
+    if (spec->max_blocks < 1 || spec->height_levels < 1 || spec->height_levels > 9 || spec->max_dist < 0 ||
+        spec->max_dist > 10 || spec->num_colors < 1 || spec->num_colors > 6)
+        return IGLU_ERR_INVALID_ARG;
+    k_sample_tasks<<<(unsigned)((m + 127) / 128), 128, 0, (cudaStream_t)stream>>>(targets, m, *spec, seed, first_task);
     return check(cudaPeekAtLastError());
 }
 
@@ -1135,21 +1198,24 @@ extern "C" int iglu_fetch_env_host(iglu_ctx *ctx, const iglu_state *st, const ig
     return check(cudaStreamSynchronize(s));
 }
 
-template <bool CLIP, bool WANT_KEY>
-static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int invariant, int32_t *out,
-                     int32_t *argmax, int64_t count, unsigned grid, size_t smem, cudaStream_t s) {
-    int rc = check(cudaFuncSetAttribute(k_max_intersection<CLIP, WANT_KEY>,
+template <bool WANT_KEY, bool ALIGNED>
+static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int64_t gs, int64_t ts, int64_t fs,
+                     int invariant, int32_t *out, int32_t *argmax, int64_t count, unsigned grid, size_t smem,
+                     cudaStream_t s) {
+    int rc = check(cudaFuncSetAttribute(k_max_intersection<WANT_KEY, ALIGNED>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (rc) return rc;
-    k_max_intersection<CLIP, WANT_KEY><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, invariant, out,
-                                                                        argmax, count);
+    k_max_intersection<WANT_KEY, ALIGNED><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, gs, ts, fs, invariant,
+                                                                           out, argmax, count);
     return check(cudaPeekAtLastError());
 }
 
-extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls,
-                                     int invariant, int32_t *out, int32_t *argmax, int64_t count,
-                                     void *stream) {
+extern "C" int iglu_max_intersection_strided(const int8_t *grids, int64_t grid_stride, const int8_t *targets,
+                                             int64_t target_stride, const int8_t *fulls, int64_t full_stride,
+                                             int invariant, int32_t *out, int32_t *argmax, int64_t count,
+                                             void *stream) {
     if (!grids || !targets || !out || count <= 0) return IGLU_ERR_INVALID_ARG;
+    if (grid_stride < CELLS || target_stride < CELLS || (fulls && full_stride < CELLS)) return IGLU_ERR_INVALID_ARG;
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return IGLU_ERR_CUDA;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return IGLU_ERR_CUDA;
@@ -1158,11 +1224,23 @@ extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets,
     const int64_t resident = (int64_t)sms * MI_CTAS;
     const unsigned grid = (unsigned)(ctas < resident ? ctas : resident);
     cudaStream_t s = (cudaStream_t)stream;
-    const bool clip = fulls && invariant;
-    if (clip) {
-        return argmax ? launch_mi<true, true>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s)
-                      : launch_mi<true, false>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s);
-    }
-    return argmax ? launch_mi<false, true>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s)
-                  : launch_mi<false, false>(grids, targets, fulls, invariant, out, argmax, count, grid, smem, s);
+    // rows that are 16-byte aligned and at least GSTRIDE long (the env state layout) are copied as they are
+    auto al = [](const int8_t *p, int64_t st) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (st & 15) == 0 && st >= GSTRIDE; };
+    const bool aligned = al(grids, grid_stride) && al(targets, target_stride);
+    if (aligned)
+        return argmax ? launch_mi<true, true>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
+                                              out, argmax, count, grid, smem, s)
+                      : launch_mi<false, true>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
+                                               out, argmax, count, grid, smem, s);
+    return argmax ? launch_mi<true, false>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
+                                           out, argmax, count, grid, smem, s)
+                  : launch_mi<false, false>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
+                                            out, argmax, count, grid, smem, s);
+}
+
+extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls,
+                                     int invariant, int32_t *out, int32_t *argmax, int64_t count,
+                                     void *stream) {
+    return iglu_max_intersection_strided(grids, CELLS, targets, CELLS, fulls, CELLS, invariant, out, argmax, count,
+                                         stream);
 }

@@ -104,19 +104,22 @@ __device__ __forceinline__ bool world_has(int cell_value, int x, int y, int z) {
     return floor_hit || cell_value != 0;  // cell_value is 0 for keys outside the zone
 }
 
-// `self.world[key]` for a key known to be present: WHITE (-1) / GREY (0) floor or the block colour.
-__device__ __forceinline__ int world_tex(const int8_t *__restrict__ g, int x, int y, int z) {
-    if (y == -2) return (abs(x) <= 5 && abs(z) <= 5) ? -1 : 0;
-    return (int)g[(y + 1) * 121 + (x + 5) * 11 + (z + 5)];
-}
-
 __device__ __forceinline__ bool build_zone_i(int x, int y, int z) {
     return -5 <= x && x <= 5 && -5 <= z && z <= 5 && -1 <= y && y < 8;
 }
 
+// Neighbour cells already fetched around one centre voxel. The grid does not change between the sub-steps of one
+// update() (the step's edit happens before it), so a sub-step that stays in the centre cell of the one before only
+// fetches the neighbours it still lacks -- usually none: one memory round trip per step instead of one per sub-step.
+struct CollideCache {
+    uint32_t key;     // packed centre voxel (0 = nothing cached: real keys have bit 9 of every field set or more)
+    unsigned have;    // bit c: neighbour cell c (of the 12) was fetched
+    unsigned filled;  // bit c: ... and holds a block
+};
+
 // world.py:264-310 collide (FACES order utils.py:156-163: +y, -y, -x, +x, +z, -z)
 __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px, double &py, double &pz,
-                                        double &agent_dy) {
+                                        double &agent_dy, CollideCache &cc) {
     const double pad = 0.25;
     const int nx = (int)rint(px), ny = (int)rint(py), nz = (int)rint(pz);
     // A face can only act when the overlap along its axis is >= pad, and the two faces of one axis
@@ -135,24 +138,34 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
     const bool zf[3] = {(unsigned)(nz + 17) <= 36u, (unsigned)(nz + 18) <= 36u, (unsigned)(nz + 19) <= 36u};
     const bool yf[4] = {ny == 0, ny == -1, ny == -2, ny == -3};                                          // y == -2
     const int c0 = cell_of(nx, ny, nz);
+    const uint32_t ckey = (uint32_t)(nx + 512) + ((uint32_t)(ny + 512) << 10) + ((uint32_t)(nz + 512) << 20);
+    if (ckey != cc.key) { cc.key = ckey; cc.have = 0u; cc.filled = 0u; }
     // per (face, height): index into the x / y / z coordinate tables and the cell offset
     //                      +y        -y        -x        +x        +z        -z
     constexpr int XI[12] = {1, 1,     1, 1,     0, 0,     2, 2,     1, 1,     1, 1};
     constexpr int YI[12] = {3, 2,     1, 0,     2, 1,     2, 1,     2, 1,     2, 1};
     constexpr int ZI[12] = {1, 1,     1, 1,     1, 1,     1, 1,     2, 2,     0, 0};
     int cv[12];
+    unsigned fetched = 0u;
 #pragma unroll
     for (int c = 0; c < 12; c++) {
-        const bool need = on[c >> 1] && xz[XI[c]] && yz[YI[c]] && zz[ZI[c]];
+        const bool need = on[c >> 1] && xz[XI[c]] && yz[YI[c]] && zz[ZI[c]] && !((cc.have >> c) & 1u);
         const int off = (XI[c] - 1) * 11 + (YI[c] - 2) * 121 + (ZI[c] - 1);
         cv[c] = ld_s8_if(g + (need ? c0 + off : 0), need);
+        fetched |= (unsigned)need << c;
     }
     unsigned solid = 0;
 #pragma unroll
     for (int c = 0; c < 12; c++) {
         const bool floor_hit = yf[YI[c]] && xf[XI[c]] && zf[ZI[c]];
-        solid |= (unsigned)(floor_hit || cv[c] != 0) << c;
+        solid |= (unsigned)floor_hit << c;
     }
+    if (fetched) {  // nothing to wait for when every neighbour this sub-step needs is cached
+#pragma unroll
+        for (int c = 0; c < 12; c++) cc.filled |= (unsigned)(cv[c] != 0) << c;
+        cc.have |= fetched;
+    }
+    solid |= cc.filled;  // cells never fetched are outside the zone (empty) or belong to faces that cannot act
 #pragma unroll
     for (int f = 0; f < 6; f++) {
         const int axis = (f < 2) ? 1 : (f < 4 ? 0 : 2);
@@ -170,7 +183,7 @@ __device__ __forceinline__ void collide(const int8_t *__restrict__ g, double &px
 
 // world.py:222-262 _update
 __device__ __forceinline__ void update_sub(const int8_t *__restrict__ g, Agent &a, bool flying, double mvx,
-                                           double mvy, double mvz, double dt) {
+                                           double mvy, double mvz, double dt, CollideCache &cc) {
     const double speed = flying ? 15.0 : 5.0;
     const double d = dt * speed;
     double dx = mvx * d, dy = mvy * d, dz = mvz * d;
@@ -187,7 +200,7 @@ __device__ __forceinline__ void update_sub(const int8_t *__restrict__ g, Agent &
     const bool inside = -7.0 <= cx && cx <= 7.0 && -7.0 <= cz && cz <= 7.0 && -3.0 <= cy && cy < 10.0;
     if (inside || !flying) {  // world.py:258-261: collide(cand) or, when walking, collide((x, y + dy, z))
         double ux = inside ? cx : a.x, uy = inside ? cy : a.y + dy, uz = inside ? cz : a.z;
-        collide(g, ux, uy, uz, a.dy);
+        collide(g, ux, uy, uz, a.dy, cc);
         a.x = ux; a.y = uy; a.z = uz;
     }
 }
@@ -231,6 +244,7 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         // (which lie in the zone or on the floor) and of the sample before it are unpacked.
         // `previous` (world.py:97) is always the key of the sample before, so "key != previous" is `fresh`.
         uint32_t kkey = 0, qkey = 0, last = 0;
+        int hit_val = 0;  // grid byte of the hit cell (0 for floor hits): self.world[block] without a second load
         bool has_prev = false, hit = false, lvalid = false;
         for (int i0 = 0; i0 < 40 && !hit; i0 += 8) {
             uint32_t key[8];
@@ -259,15 +273,15 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
             if (hm) {  // first fresh sample whose key is in the world: (block, previous) = (its key, the key before)
                 hit = true;
                 const int jh = __ffs(hm) - 1;
-                kkey = key[0]; qkey = last_in; has_prev = lvalid_in;
+                kkey = key[0]; qkey = last_in; has_prev = lvalid_in; hit_val = cv[0];
 #pragma unroll
                 for (int j = 1; j < 8; j++)
-                    if (jh == j) { kkey = key[j]; qkey = key[j - 1]; has_prev = true; }
+                    if (jh == j) { kkey = key[j]; qkey = key[j - 1]; has_prev = true; hit_val = cv[j]; }
             }
         }
         const int kx = (int)(kkey & 1023u) - 512, ky = (int)((kkey >> 10) & 1023u) - 512, kz = (int)(kkey >> 20) - 512;
         const int qx = (int)(qkey & 1023u) - 512, qy = (int)((qkey >> 10) & 1023u) - 512, qz = (int)(qkey >> 20) - 512;
-        int cell = -1, newv = 0;
+        int cell = -1, newv = 0, oldv = 0;
         if (act.add) {
             if (hit && has_prev) {
                 if (inv_get(a, a.active - 1) > 0 && build_zone_i(qx, qy, qz)) {
@@ -283,15 +297,18 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
                 }
             }
         } else if (hit) {
-            const int tex = world_tex(g, kx, ky, kz);
+            // self.world[block]: the floor's WHITE / GREY or the byte the hit test already fetched
+            const int tex = ky == -2 ? ((abs(kx) <= 5 && abs(kz) <= 5) ? -1 : 0) : hit_val;
             if (tex != 0 && tex != -1) {  // not GREY / WHITE floor
                 cell = (ky + 1) * 121 + (kx + 5) * 11 + (kz + 5);
                 newv = 0;
+                oldv = tex;
                 if (tex >= 1 && tex <= 6) inv_add(a, tex - 1, 1);
             }
         }
         if (cell >= 0) {
-            int oldv = g[cell];
+            // old value of the edited cell: a removed block's colour; 0 for a placed one (`previous` is a sample
+            // whose key was looked up and found absent, world.py:95-97, and build_zone puts it inside the grid)
             int iv = has_start ? (int)init[cell] : 0;
             dsize += (int)(newv != iv) - (int)(oldv != iv);
             g[cell] = (int8_t)newv;
@@ -318,7 +335,8 @@ __device__ __forceinline__ void world_step(int8_t *__restrict__ g, const int8_t 
         }
         const int m = a.tis;
         const double dt = 0.05 / (double)m;
-        for (int i = 0; i < m; i++) update_sub(g, a, flying, mvx, mvy, mvz, dt);
+        CollideCache cc = {0u, 0u, 0u};
+        for (int i = 0; i < m; i++) update_sub(g, a, flying, mvx, mvy, mvz, dt, cc);
         if (flying) a.dy = 0.0;
     }
     // world.py:451-456. The iteration cap only matters for |yaw| so large that +-360 no longer

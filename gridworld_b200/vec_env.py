@@ -287,7 +287,16 @@ class IGLUVecEnv:
         self._was_reset = False
         return self.reset() if reset else None
 
-    def set_task_generator(self, tasks, seed=0, env_offset=0, next_task=None, reset=True):
+    def set_random_task_pool(self, m, max_blocks=4, height_levels=1, max_dist=2, num_colors=1, task_seed=0,
+                             first_task=0, **pool_kwargs):
+        """A pool of m RandomTasks.sample_task structures (reference task_set.py:135-157) generated ON THE DEVICE
+        (iglu_sample_tasks) and attached as the task generator: neither filling nor refreshing the pool involves the
+        host -- call again with another task_seed / first_task to refresh it. pool_kwargs go to set_task_pool."""
+        targets = sample_tasks(m, max_blocks, height_levels, max_dist, num_colors, seed=task_seed,
+                               first_task=first_task, device=self.device)
+        return self.set_task_pool(targets, None, **pool_kwargs)
+
+    def set_task_generator(self, tasks, seed=0, env_offset=0, next_task=None, reset=True, samples=4096):
         """env.set_task_generator (reference env.py:166-172) for a task COLLECTION (Task, CustomTasks, RandomTasks
         with max_cache > 0, Subtasks, or any iterable of Tasks): its tasks are enumerated once into the
         device-resident pool (set_task_pool) and every reset draws one of them on the device.
@@ -296,6 +305,14 @@ class IGLUVecEnv:
         if tasks is None:
             self.dialogs = None
             return self.set_task_pool(None)
+        hp = [getattr(tasks, k, None) for k in ('max_blocks', 'height_levels', 'max_dist', 'num_colors')]
+        if (all(isinstance(v, int) for v in hp) and not getattr(tasks, '__dict__', {}).get('tasks')
+                and not getattr(tasks, 'max_cache', 0)):
+            # a RandomTasks(max_cache=0)-shaped generator (fresh sample_task at every reset, task_set.py:120-127):
+            # its structures are sampled on the device from its hyper-parameters, `samples` of them per pool
+            self.dialogs = None
+            return self.set_random_task_pool(samples, *hp, task_seed=seed, seed=seed, env_offset=env_offset,
+                                             next_task=next_task, reset=reset)
         targets, starts, chats = pool_arrays(tasks)
         self.dialogs = chats
         return self.set_task_pool(targets, starts, seed=seed, env_offset=env_offset, next_task=next_task, reset=reset)
@@ -576,13 +593,42 @@ def make_vec(num_envs, device='cuda', **kwargs):
     return IGLUVecEnv(num_envs, device=device, **kwargs)
 
 
+def sample_tasks(m, max_blocks=4, height_levels=1, max_dist=2, num_colors=1, seed=0, first_task=0, device='cuda'):
+    """m random target structures with the semantics of RandomTasks.sample_task (reference task_set.py:135-157),
+    generated on the GPU by iglu_sample_tasks; int8 device tensor [m, 9, 11, 11]. The random stream is the
+    counter-based one documented in include/iglu_b200.h (task `first_task + i`, so shards can split a pool)."""
+    dev = _require_cuda(device)
+    L = _lib.load()
+    out = torch.empty(int(m), 9, 11, 11, dtype=torch.int8, device=dev)
+    spec = _lib.RandomTaskSpec(int(max_blocks), int(height_levels), int(max_dist), int(num_colors))
+    with torch.cuda.device(dev):
+        _lib.check(L.iglu_sample_tasks(out.data_ptr(), int(m), C.byref(spec), int(seed) & (2 ** 64 - 1),
+                                       int(first_task), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out
+
+
 def max_intersection(grids, targets, full_grids=None, invariant=True, return_argmax=False, device='cuda'):
     """Task(target, full_grid=full, invariant=invariant).maximal_intersection(grid) for a batch of pairs
     (reference gridworld/tasks/task.py:9-72, 147-161), on the GPU. Inputs: int8-convertible
-    [k, 9, 11, 11]. Returns int32 [k] (and int32 [k, 3] = (dx, dz, rot) like argmax_intersection)."""
+    [k, 9, 11, 11]. Returns int32 [k] (and int32 [k, 3] = (dx, dz, rot) like argmax_intersection).
+    Device int8 tensors of shape [k, 1104] -- rows in the env state layout, e.g. IGLUVecEnv._grid / ._target --
+    are evaluated where they lie (iglu_max_intersection_strided), without a repack."""
     dev = _require_cuda(device)
     L = _lib.load()
     g = torch.as_tensor(grids)
+    t = torch.as_tensor(targets)
+    rows = lambda x: (x.dim() == 2 and x.shape[1] == _lib.GRID_STRIDE and x.dtype == torch.int8  # noqa: E731
+                      and x.is_cuda and x.is_contiguous())
+    if rows(g) and rows(t) and full_grids is None:
+        k = g.shape[0]
+        out = torch.zeros(k, dtype=torch.int32, device=g.device)
+        arg = torch.zeros(k, 3, dtype=torch.int32, device=g.device) if return_argmax else None
+        with torch.cuda.device(g.device):
+            _lib.check(L.iglu_max_intersection_strided(
+                g.data_ptr(), _lib.GRID_STRIDE, t.data_ptr(), _lib.GRID_STRIDE, None, 0, int(bool(invariant)),
+                out.data_ptr(), None if arg is None else arg.data_ptr(), k,
+                C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
+        return (out, arg) if return_argmax else out
     k = g.shape[0] if g.dim() == 4 else 1
 
     def prep(x):

@@ -179,6 +179,26 @@ typedef struct iglu_task_pool {
 int iglu_task_pool_prepare(iglu_ctx *ctx, const iglu_task_pool *pool, const int8_t *target, const int8_t *start,
                            void *stream);
 
+/* RandomTasks.sample_task (task_set.py:135-157) on the device: m random target structures, dense int8 [m][1089] in
+ * `targets` (device) -- the input format of iglu_set_tasks / iglu_task_pool_prepare, so a pool can be refilled without
+ * the host. Per height level one uniformly placed first block, then max_blocks - 1 more, each at an offset in
+ * [-max_dist, max_dist]^2 from the FIRST block of the level, redrawn together with its colour until it is not (0, 0),
+ * inside the zone and free -- the reference's control flow. Its random numbers come from numpy's global Mersenne
+ * Twister; here the i-th draw (i = 0, 1, ...) of task t (global index first_task + row) with range r is
+ *     x = seed + 0x9E3779B97F4A7C15 * (t + 1) + 0xD1B54A32D192ED03 * i   (mod 2^64), the finaliser of the pool draw,
+ *     value = ((x >> 32) * r) >> 32
+ * in the order block_x, block_z, colour, then (ddx, ddz, colour) per attempt; a block that finds no free cell
+ * within 4096 attempts is skipped (the reference would loop forever). */
+typedef struct iglu_random_task_spec {
+    int32_t max_blocks;     /* blocks per height level (task_set.py:75) */
+    int32_t height_levels;  /* 1..9 */
+    int32_t max_dist;       /* Chebyshev distance from the level's first block */
+    int32_t num_colors;     /* 1..6 */
+} iglu_random_task_spec;
+
+int iglu_sample_tasks(int8_t *targets, int64_t m, const iglu_random_task_spec *spec, uint64_t seed,
+                      int64_t first_task, void *stream);
+
 /* Attach (pool != NULL, m > 0) or detach (NULL) the generator. The ctx keeps a COPY of the struct, i.e. it
  * retains the device pointers until detached or destroyed; the caller keeps the buffers alive. */
 int iglu_task_pool_attach(iglu_ctx *ctx, const iglu_task_pool *pool);
@@ -251,6 +271,14 @@ int iglu_fetch_env_host(iglu_ctx *ctx, const iglu_state *st, const iglu_obs *obs
  *   argmax                : device int32 [count][3] = (dx, dz, rot) of task.py:121-136, or NULL */
 int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int invariant,
                           int32_t *out, int32_t *argmax, int64_t count, void *stream);
+
+/* The same for rows that are not densely packed: row i of `grids` starts at grids + i * grid_stride bytes (stride >=
+ * 1089), likewise targets / fulls. Rows that are 16-byte aligned with a stride that is a multiple of 16 and >= 1104 --
+ * the layout of iglu_state.grid / target / init -- are staged as they are (no repack of env state is needed to
+ * evaluate it); bytes of a row past cell 1088 are ignored. iglu_max_intersection == strides of 1089. */
+int iglu_max_intersection_strided(const int8_t *grids, int64_t grid_stride, const int8_t *targets,
+                                  int64_t target_stride, const int8_t *fulls, int64_t full_stride, int invariant,
+                                  int32_t *out, int32_t *argmax, int64_t count, void *stream);
 
 /* Number of kernels the last step call on this ctx launched (bench.py's gpu_launches claim). */
 int iglu_last_launch_count(const iglu_ctx *ctx);

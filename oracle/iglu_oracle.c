@@ -812,3 +812,49 @@ void orc_tasks_eval(const orc_task *ts, const int8_t *grids, int32_t *out, int64
     orc_parallel_for(tasks_eval_range, &m, n, threads);
 }
 void orc_tasks_free(orc_task *ts) { free(ts); }
+
+/* tasks/task_set.py:135-157 RandomTasks.sample_task for a batch of tasks. The control flow is the reference's:
+ * per height level one uniformly placed first block, then max_blocks - 1 more, each at an offset
+ * (ddx, ddz) in [-max_dist, max_dist]^2 from the FIRST block of the level (block_x / block_z never move), redrawn
+ * -- together with a colour -- until it is not (0, 0), inside the zone and free. The reference draws from numpy's
+ * global Mersenne Twister, which has no batched meaning; like the task-pool draw above, the batched build defines
+ * a counter-based stream instead (include/iglu_b200.h iglu_sample_tasks): the i-th draw of task t with range r is
+ *     x = seed + 0x9E3779B97F4A7C15 * (t + 1) + 0xD1B54A32D192ED03 * i   (then the splitmix64 finaliser)
+ *     value = ((x >> 32) * r) >> 32
+ * and a block that finds no free cell within 4096 redraws is skipped (the reference would loop forever). */
+static uint32_t sample_draw(uint64_t seed, int64_t task, uint32_t *counter, uint32_t range) {
+    uint64_t x = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(task + 1) + 0xD1B54A32D192ED03ull * (uint64_t)(*counter)++;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (uint32_t)(((x >> 32) * (uint64_t)range) >> 32);
+}
+
+void orc_sample_tasks(int8_t *out, int64_t m, int max_blocks, int height_levels, int max_dist, int num_colors,
+                      uint64_t seed, int64_t first_task) {
+    for (int64_t t = 0; t < m; t++) {
+        int8_t *g = out + t * CELLS;
+        memset(g, 0, CELLS);
+        uint32_t ctr = 0;
+        for (int h = 0; h < height_levels && h < GY; h++) {
+            const int bx = (int)sample_draw(seed, first_task + t, &ctr, GX);
+            const int bz = (int)sample_draw(seed, first_task + t, &ctr, GZ);
+            int color = (int)sample_draw(seed, first_task + t, &ctr, (uint32_t)num_colors) + 1;
+            g[h * GX * GZ + bx * GZ + bz] = (int8_t)color;
+            for (int b = 1; b < max_blocks; b++) {
+                int ddx = 0, ddz = 0, tries = 0, ok = 0;
+                while (tries++ < 4096) {
+                    ddx = (int)sample_draw(seed, first_task + t, &ctr, (uint32_t)(2 * max_dist + 1)) - max_dist;
+                    ddz = (int)sample_draw(seed, first_task + t, &ctr, (uint32_t)(2 * max_dist + 1)) - max_dist;
+                    color = (int)sample_draw(seed, first_task + t, &ctr, (uint32_t)num_colors) + 1;
+                    const int x = bx + ddx, z = bz + ddz;
+                    if ((ddx == 0 && ddz == 0) || x >= GX || z >= GZ || x < 0 || z < 0) continue;
+                    if (g[h * GX * GZ + x * GZ + z] != 0) continue;
+                    ok = 1;
+                    break;
+                }
+                if (ok) g[h * GX * GZ + (bx + ddx) * GZ + (bz + ddz)] = (int8_t)color;
+            }
+        }
+    }
+}

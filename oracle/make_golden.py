@@ -19,6 +19,7 @@ Files written (all small, committed):
   traces_flying.npz  flying Dict traces (float32 actions, widened to fp64 for the reference)
   traces_dict.npz    walking Dict (discretize=False) traces
   misc.npz           Task.get_intersection and Subtasks (reset / progressive step_intersection) known answers
+  surface.npz        N = 1 gym surface: SizeReward, initialize_world / deinitialize_world, host set_task_generator
 """
 import os
 import pickle
@@ -631,12 +632,141 @@ def gen_generator(gym, Task, Tasks):
     print('traces_generator.npz', idx, 'traces')
 
 
+def gen_surface(gym, Task, Tasks):
+    """The N = 1 gym surface beyond set_task / reset / step, recorded from the reference:
+    the SizeReward wrapper (env.py:316-331; its reward only ever sees GridWorld.max_int / .wrong_placement as reset
+    left them), initialize_world / deinitialize_world (env.py:177-193) and a host-side set_task_generator
+    (env.py:168-175, 213-216) whose generator hands its tasks out in a fixed cycle."""
+    rng = np.random.RandomState(77)
+    out = {}
+    T = np.zeros((9, 11, 11), np.int8)
+    T[0, 5, 6] = 1
+    T[0, 6, 6] = 3
+    T[0, 4, 6] = 2
+    T[1, 5, 6] = 1
+    S = np.zeros((9, 11, 11), np.int8)
+    S[0, 6, 6] = 3            # one target block is there from the start: max_int at reset = 1
+    S[0, 2, 2] = 4            # ... and one that is not part of the target
+
+    def state(env):
+        u = env.unwrapped
+        return ([float(v) for v in u.agent.position] + [float(v) for v in u.agent.rotation],
+                [int(v) for v in u.agent.inventory], u.grid.astype(np.int8).reshape(-1).copy())
+
+    # ---- A: SizeReward ----
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=True, action_space='walking',
+                   max_steps=40)
+    env.set_task(Task('size', T.astype(np.int32), starting_grid=dense_to_sparse_world(S)))
+    acts = walking_action_mix(rng, 150, 'builder')
+    acts[:11] = [6] + [14] * 9 + [17]   # the scripted placement of gen_generator: puts BLUE at dense (0, 5, 6)
+    rew, dn, pose, inv, grids, resets = [], [], [], [], [], []
+    done = False
+    for t, a in enumerate(acts):
+        if done:
+            env.reset()
+        resets.append(done)
+        obs, r, done, _ = env.step(int(a))
+        p, i, g = state(env)
+        rew.append(float(r)); dn.append(bool(done)); pose.append(p); inv.append(i); grids.append(g)
+    out['size_target'], out['size_start'], out['size_actions'] = T, S, acts
+    out['size_reward'], out['size_done'] = np.array(rew, np.float64), np.array(dn, bool)
+    out['size_pose'], out['size_inv'] = np.array(pose, np.float64), np.array(inv, np.int32)
+    out['size_grid'], out['size_resets'] = np.array(grids, np.int8), np.array(resets, bool)
+    out['size_max_int_attr'] = np.array(int(env.unwrapped.max_int), np.int32)
+    print('  SizeReward rewards seen:', sorted(set(rew)), 'dones', int(np.sum(dn)))
+
+    # ---- B: initialize_world / deinitialize_world ----
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking',
+                   max_steps=60)
+    env.set_task(Task('init', T.astype(np.int32), starting_grid=dense_to_sparse_world(S)))
+    W = np.zeros((9, 11, 11), np.int8)
+    W[0, 7, 7] = 5
+    W[0, 5, 6] = 1            # a target block in the overwritten world
+    W[1, 3, 3] = 6
+    segs = []
+    acts = walking_action_mix(rng, 120, 'builder')
+    rew, dn, pose, inv, grids, apos, ogrid = [], [], [], [], [], [], []
+    events = []               # (step index, kind): 1 = initialize_world before this step, 2 = deinitialize_world, 3 = reset
+    done = False
+    for t, a in enumerate(acts):
+        if t == 20:
+            env.initialize_world(dense_to_sparse_world(W), (1.5, 0.25, -2.0, 45.0, -10.0))
+            events.append((t, 1)); done = False
+        elif t == 75:
+            env.deinitialize_world()
+            events.append((t, 2)); done = False
+        elif done:
+            env.reset(); events.append((t, 3))
+        obs, r, done, _ = env.step(int(a))
+        p, i, g = state(env)
+        rew.append(float(r)); dn.append(bool(done)); pose.append(p); inv.append(i); grids.append(g)
+        apos.append(np.asarray(obs['agentPos'], np.float32)); ogrid.append(np.asarray(obs['grid'], np.int32).reshape(-1))
+    out['iw_target'], out['iw_start'], out['iw_world'], out['iw_actions'] = T, S, W, acts
+    out['iw_pose0'] = np.array([1.5, 0.25, -2.0, 45.0, -10.0])
+    out['iw_events'] = np.array(events, np.int32)
+    out['iw_reward'], out['iw_done'] = np.array(rew, np.float64), np.array(dn, bool)
+    out['iw_pose'], out['iw_inv'] = np.array(pose, np.float64), np.array(inv, np.int32)
+    out['iw_grid'], out['iw_agentPos'] = np.array(grids, np.int8), np.array(apos, np.float32)
+    print('  initialize_world events', events, 'reward sum', float(np.sum(rew)))
+
+    # ---- C: set_task_generator with a host-side generator that cycles through its tasks ----
+    class Cycle(Tasks):
+        def __init__(self, tasks):
+            self.tasks, self.i, self.current = tasks, 0, None
+
+        def reset(self):
+            self.current = self.tasks[self.i % len(self.tasks)]
+            self.i += 1
+            return self.current
+
+    pool_t, pool_s = [], []
+    for j in range(4):
+        t = synth_target(rng, 0.08, 'compact')
+        t[0, 5, 6] = 1 + j
+        s = synth_target(rng, 0.04, 'compact') if j % 2 else np.zeros((9, 11, 11), np.int8)
+        s[:, 5, 5] = 0
+        s[2:] = 0
+        pool_t.append(t); pool_s.append(s)
+    one = np.zeros((9, 11, 11), np.int8)
+    one[0, 5, 6] = 1          # finished by the scripted placement -> an early done
+    pool_t[0], pool_s[0] = one, np.zeros((9, 11, 11), np.int8)
+    tasks = [Task(f'task {j}', pool_t[j].astype(np.int32), starting_grid=dense_to_sparse_world(pool_s[j]))
+             for j in range(4)]
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking',
+                   max_steps=25, target_in_obs=True)
+    env.set_task_generator(Cycle(tasks))
+    acts = walking_action_mix(rng, 160, 'builder')
+    rew, dn, pose, inv, grids, dialog, tsum, resets = [], [], [], [], [], [], [], []
+    done, ep_t = False, 0
+    SCRIPT = [6] + [14] * 9 + [17]
+    for t in range(len(acts)):
+        if done:
+            env.reset(); ep_t = 0
+        resets.append(done)
+        if ep_t < len(SCRIPT):
+            acts[t] = SCRIPT[ep_t]
+        ep_t += 1
+        obs, r, done, _ = env.step(int(acts[t]))
+        p, i, g = state(env)
+        rew.append(float(r)); dn.append(bool(done)); pose.append(p); inv.append(i); grids.append(g)
+        dialog.append(obs['dialog']); tsum.append(np.asarray(obs['target_grid'], np.int32).reshape(-1))
+    out['gen_targets'], out['gen_starts'], out['gen_actions'] = np.array(pool_t), np.array(pool_s), acts
+    out['gen_reward'], out['gen_done'] = np.array(rew, np.float64), np.array(dn, bool)
+    out['gen_pose'], out['gen_inv'] = np.array(pose, np.float64), np.array(inv, np.int32)
+    out['gen_grid'], out['gen_dialog'] = np.array(grids, np.int8), np.array(dialog)
+    out['gen_target_obs'], out['gen_resets'] = np.array(tsum, np.int32), np.array(resets, bool)
+    print('  host generator: dones', int(np.sum(dn)), 'early', int(np.sum(np.array(dn) & (np.arange(len(dn)) % 25 != 24))),
+          'dialogs', sorted(set(dialog)))
+    np.savez_compressed(os.path.join(OUT, 'surface.npz'), **out)
+    print('surface.npz')
+
+
 def main():
     load_reference.load()
     import gym
     from gridworld.tasks import Task, Tasks
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator']
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator', 'surface']
     if 'goals' in which:
         gen_goals(Task, Tasks)
     if 'pairs' in which:
@@ -651,6 +781,8 @@ def main():
         gen_misc(Task, Tasks)
     if 'generator' in which:
         gen_generator(gym, Task, Tasks)
+    if 'surface' in which:
+        gen_surface(gym, Task, Tasks)
 
 
 if __name__ == '__main__':

@@ -52,6 +52,7 @@ def lib():
         L.orc_tasks_prepare.argtypes = [vp, i64, i32]
         L.orc_tasks_eval.argtypes = [vp, vp, vp, i64, i32]
         L.orc_tasks_free.argtypes = [vp]
+        L.orc_sample_tasks.argtypes = [vp, i64, i32, i32, i32, i32, C.c_uint64, i64]
         _lib = L
     return _lib
 
@@ -205,3 +206,11 @@ class PreparedTasks:
         if getattr(self, '_h', None) and _lib is not None:
             _lib.orc_tasks_free(self._h)
             self._h = None
+
+
+def sample_tasks(m, max_blocks=4, height_levels=1, max_dist=2, num_colors=1, seed=0, first_task=0):
+    """RandomTasks.sample_task (task_set.py:135-157) for m tasks with the batched build's counter-based stream."""
+    out = np.zeros((int(m), 9, 11, 11), np.int8)
+    lib().orc_sample_tasks(_p(out), int(m), int(max_blocks), int(height_levels), int(max_dist), int(num_colors),
+                           int(seed) & (2 ** 64 - 1), int(first_task))
+    return out

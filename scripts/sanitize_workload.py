@@ -40,6 +40,24 @@ for pin in (True, False):
     for t in range(5):
         a.copy_(torch.randint(0, 18, (n,), dtype=torch.int32))
         env.step_host(a, r, d)
+# the async form on its own stream + wait, the single-env snapshot, pre-built worlds, env rows evaluated in place
+st = torch.cuda.Stream()
+for t in range(4):
+    a.copy_(torch.randint(0, 18, (n,), dtype=torch.int32))
+    with torch.cuda.stream(st):
+        env.step_host(a, r, d, wait=False)
+    env.wait()
+env.fetch_env(3)
+env2 = gw.make_vec(n, max_steps=50, reward_mode='every_step')
+env2.set_tasks(T, S)
+env2.set_grids(np.where(rng.random_sample(T.shape) < 0.5, T, S).astype(np.int8))
+for t in range(6):
+    env2.step(acts())
+gw.max_intersection(env2._grid, env2._target, return_argmax=True)
+one = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=True)
+one.set_task(gw.Task('', T[1].astype(np.int32), starting_grid=[(1, -1, 1, 3)]))
+for t in range(4):
+    one.step(17 if t % 2 else 6)
 G = rnd(0.2)
 gw.max_intersection(G, T, return_argmax=True)
 gw.max_intersection(G, T, T)

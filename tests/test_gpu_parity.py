@@ -780,3 +780,202 @@ def test_new_host_surface_async_snapshot_set_grids_restore():
         assert bool((((g == c).flatten(1).sum(1)) + env.inventory[:, c - 1] == 20).all())
     assert torch.equal(gw.max_intersection(g, T).to(torch.int32), env.max_int)
     assert torch.equal(obs['grid'], g.to(torch.int32))
+    # the env's own rows (stride 1104, 16-byte aligned) evaluated where they lie == the dense repack
+    v1, a1 = gw.max_intersection(env._grid, env._target, return_argmax=True)
+    v2, a2 = gw.max_intersection(g, T, return_argmax=True)
+    assert torch.equal(v1, v2) and torch.equal(a1, a2)
+
+
+def _sparse(d):
+    ys, xs, zs = np.nonzero(d)
+    return [(int(x) - 5, int(y) - 1, int(z) - 5, int(d[y, x, z])) for y, x, z in zip(ys, xs, zs)]
+
+
+def test_surface_golden_size_reward_initialize_world_host_generator():
+    """SURVEY rows a20 / a23 at N = 1 against traces recorded from the executed reference (tests/golden/surface.npz):
+    the SizeReward wrapper's (degenerate) reward, initialize_world / deinitialize_world, and set_task_generator with
+    a host-side generator object."""
+    import gridworld_b200 as gw
+    z = G.load('surface.npz')
+
+    def check(env, t, pre, r, done):
+        u = env.unwrapped
+        assert r == z[pre + 'reward'][t] and done == bool(z[pre + 'done'][t]), (pre, t, r, z[pre + 'reward'][t])
+        assert list(u.agent.position) + list(u.agent.rotation) == z[pre + 'pose'][t].tolist(), (pre, t)
+        assert u.agent.inventory == z[pre + 'inv'][t].tolist(), (pre, t)
+        assert np.array_equal(u.grid.reshape(-1), z[pre + 'grid'][t].astype(np.int32)), (pre, t)
+
+    # ---- SizeReward (env.py:316-331) ----
+    env = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=True, action_space='walking',
+                  max_steps=40)
+    env.set_task(gw.Task('size', z['size_target'].astype(np.int32), starting_grid=_sparse(z['size_start'])))
+    done = False
+    for t, a in enumerate(z['size_actions']):
+        if done:
+            env.reset()
+        assert done == bool(z['size_resets'][t])
+        obs, r, done, _ = env.step(int(a))
+        check(env, t, 'size_', r, done)
+    assert env.unwrapped.max_int == int(z['size_max_int_attr'])
+    assert 1.0 in z['size_reward'] and set(z['size_reward'].tolist()) <= {0.0, 1.0}
+
+    # ---- initialize_world / deinitialize_world (env.py:177-193) ----
+    env = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking',
+                  max_steps=60)
+    env.set_task(gw.Task('init', z['iw_target'].astype(np.int32), starting_grid=_sparse(z['iw_start'])))
+    events = {int(t): int(k) for t, k in z['iw_events']}
+    done = False
+    for t, a in enumerate(z['iw_actions']):
+        ev = events.get(t, 0)
+        if ev == 1:
+            with pytest.warns(UserWarning):
+                env.initialize_world(_sparse(z['iw_world']), tuple(z['iw_pose0'].tolist()))
+            done = False
+        elif ev == 2:
+            env.deinitialize_world()
+            done = False
+        elif done:
+            env.reset()
+        obs, r, done, _ = env.step(int(a))
+        check(env, t, 'iw_', r, done)
+        assert np.array_equal(obs['agentPos'], z['iw_agentPos'][t])
+
+    # ---- set_task_generator with a host-side generator (env.py:168-175, 213-216) ----
+    class Cycle:
+        def __init__(self, tasks):
+            self.tasks, self.i = tasks, 0
+
+        def reset(self):
+            self.i += 1
+            return self.tasks[(self.i - 1) % len(self.tasks)]
+
+    tasks = [gw.Task(f'task {j}', z['gen_targets'][j].astype(np.int32), starting_grid=_sparse(z['gen_starts'][j]))
+             for j in range(len(z['gen_targets']))]
+    env = gw.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking',
+                  max_steps=25, target_in_obs=True)
+    env.set_task_generator(Cycle(tasks))
+    done = False
+    for t, a in enumerate(z['gen_actions']):
+        if done:
+            env.reset()
+        assert done == bool(z['gen_resets'][t])
+        obs, r, done, _ = env.step(int(a))
+        check(env, t, 'gen_', r, done)
+        assert obs['dialog'] == str(z['gen_dialog'][t])
+        assert np.array_equal(obs['target_grid'].reshape(-1), z['gen_target_obs'][t])
+    with pytest.warns(UserWarning):
+        env.set_task(tasks[0])   # env.py:162-164: no effect on the generator, but warns
+
+
+@pytest.mark.parametrize('support', ['compact', 'full'])
+@pytest.mark.parametrize('rho', [0.05, 0.20, 0.50])
+def test_reward_config4_subset_vs_oracle(rho, support):
+    """BASELINE config 4 as SURVEY 8(d) states it: the 1 M-pair sweep (half of the grids independent draws, half a
+    rotated, shifted, 10 % re-randomised copy of the target), of which a seeded 10,000-pair subset is checked
+    bit-exact against the oracle -- per density and per support."""
+    import gridworld_b200 as gw
+    from bench import synth_targets
+    n = 1_000_000
+    T = synth_targets(n, rho, support, 1237, device='cuda')
+    Gd = synth_targets(n, rho, support, 1238, device='cuda')
+    h = n // 2
+    g = torch.Generator('cuda').manual_seed(99)
+    k = int(torch.randint(1, 4, (1,)).item())
+    rel = torch.rot90(T[:h], k=k, dims=(2, 3))
+    if support == 'compact':   # an admissible translation: the 5 x 5 support stays inside the zone
+        rel = torch.roll(rel, shifts=(2, -3), dims=(2, 3))
+    noise = torch.rand(rel.shape, device='cuda', generator=g) < 0.1
+    rnd = synth_targets(h, 0.3, support, 1239, device='cuda')
+    Gd[:h] = torch.where(noise, rnd, rel)
+    out, arg = gw.max_intersection(Gd, T, return_argmax=True)
+    idx = np.sort(np.random.RandomState(0).choice(n, 10_000, replace=False))
+    it = torch.as_tensor(idx, device='cuda')
+    Gs, Ts = Gd[it].cpu().numpy(), T[it].cpu().numpy()
+    ref, ref_arg = O.max_intersection(Gs, Ts, threads=8, return_argmax=True)
+    got, got_arg = out[it].cpu().numpy(), arg[it].cpu().numpy()
+    assert np.array_equal(got, ref), np.nonzero(got != ref)[0][:10]
+    pos = ref > 0
+    assert np.array_equal(got_arg[pos], ref_arg[pos])
+    assert (ref[:5000] > ref[5000:].mean()).mean() > 0.5   # the related half really scores higher
+    # the sweep without argmax gives the same values
+    assert torch.equal(gw.max_intersection(Gd, T), out)
+
+
+def test_flying_batch_config3_size_vs_oracle():
+    """Flying Dict + target_in_obs at config-3 scale per launch (65,536 envs here, the oracle's budget) against the
+    oracle: every launch geometry of the big configuration (persistent observe grid, dynamic hand-out) is used."""
+    import gridworld_b200 as gw
+    n, steps = 65536, 60
+    rng = np.random.RandomState(15)
+    T, S, poses = _tasks(rng, n)
+    env = gw.make_vec(n, action_space='flying', max_steps=40, auto_reset=True, target_in_obs=True,
+                      reward_mode='every_step')
+    env.set_tasks(T, S, poses)
+    orc = O.OracleBatch(n, 'flying', max_steps=40, threads=8)
+    orc.set_tasks(T, S, poses)
+    bad_envs = np.zeros(n, bool)
+    for t in range(steps):
+        mv = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+        mv[rng.random_sample((n, 3)) < 0.3] = 0
+        cam = rng.uniform(-5, 5, (n, 2)).astype(np.float32)
+        inv = rng.randint(0, 7, n).astype(np.int32)
+        pl = rng.randint(0, 3, n).astype(np.int32)
+        obs, r, d, _ = env.step({'movement': mv, 'camera': cam, 'inventory': inv, 'placement': pl})
+        ro, do = orc.step_flying(mv, cam, inv, pl, auto_reset=True)
+        if t % 10 == 9 or t == steps - 1:
+            s = orc.state()
+            pos_err = np.abs(env.position.cpu().numpy() - s['pos']).max(axis=1)
+            grid_bad = (env.grid.cpu().numpy() != s['grid']).reshape(n, -1).any(axis=1)
+            bad_envs |= (pos_err > POSE_TOL) | grid_bad
+        # between state checks an env can only be excused after it was seen diverging
+        mism = (r.cpu().numpy() != ro) | (d.cpu().numpy() != do)
+        bad_envs |= mism
+    assert bad_envs.mean() <= 0.002, bad_envs.sum()
+    ok = ~bad_envs
+    s = orc.state()
+    assert np.array_equal(env.grid.cpu().numpy()[ok], s['grid'][ok])
+    assert np.array_equal(env.inventory.cpu().numpy()[ok], s['inventory'][ok])
+    assert np.array_equal(env.max_int.cpu().numpy()[ok], s['max_int'][ok])
+    assert np.array_equal(obs['target_grid'].cpu().numpy(), T.astype(np.int32))
+    assert np.array_equal(obs['grid'].cpu().numpy()[ok], s['grid'][ok].astype(np.int32))
+
+
+def test_sample_tasks_device_vs_oracle():
+    """RandomTasks.sample_task on the device (iglu_sample_tasks) against the oracle's restatement (itself checked
+    against the executed reference's distribution): bit-exact structures, shard-splittable stream, and an env whose
+    task generator is a device-sampled pool stepping exactly like the oracle on the same pool."""
+    import gridworld_b200 as gw
+    for spec in (dict(max_blocks=4, height_levels=1, max_dist=2, num_colors=1),
+                 dict(max_blocks=6, height_levels=3, max_dist=2, num_colors=4),
+                 dict(max_blocks=9, height_levels=2, max_dist=1, num_colors=6),     # blocks that find no free cell
+                 dict(max_blocks=1, height_levels=9, max_dist=0, num_colors=2)):
+        got = gw.sample_tasks(5000, seed=21, **spec).cpu().numpy()
+        assert np.array_equal(got, O.sample_tasks(5000, seed=21, **spec)), spec
+    a = gw.sample_tasks(100, max_blocks=5, height_levels=2, num_colors=3, seed=4, first_task=1000).cpu().numpy()
+    b = gw.sample_tasks(1100, max_blocks=5, height_levels=2, num_colors=3, seed=4).cpu().numpy()
+    assert np.array_equal(a, b[1000:])
+    with pytest.raises(RuntimeError):
+        gw.sample_tasks(4, num_colors=7)
+    n, m, steps = 1024, 300, 120
+    env = gw.make_vec(n, max_steps=20, reward_mode='every_step', target_in_obs=True)
+    env.set_random_task_pool(m, max_blocks=5, height_levels=2, max_dist=2, num_colors=3, task_seed=8, seed=3)
+    pool = O.sample_tasks(m, max_blocks=5, height_levels=2, max_dist=2, num_colors=3, seed=8)
+    orc = O.OracleBatch(n, 'walking', max_steps=20, threads=8)
+    orc.set_pool(pool, None, seed=3)
+    orc.reset()
+    assert np.array_equal(env.task_ids.cpu().numpy(), orc.task_ids)
+    rng = np.random.RandomState(2)
+    p = np.array([1, 5, 2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+    for t in range(steps):
+        a = rng.choice(18, n, p=p / p.sum()).astype(np.int32)
+        obs, r, d, _ = env.step(a)
+        ro, do = orc.step_walking(a, auto_reset=True)
+        assert np.array_equal(r.cpu().numpy(), ro) and np.array_equal(d.cpu().numpy(), do), t
+    assert np.array_equal(env.grid.cpu().numpy(), orc.state()['grid'])
+    assert np.array_equal(obs['target_grid'].cpu().numpy(), orc.target_grids())
+
+    class NoCache:   # the shape of the reference's RandomTasks(max_cache=0): hyper-parameters, no cached tasks
+        max_blocks, height_levels, max_dist, num_colors, max_cache, tasks = 3, 1, 2, 2, 0, {}
+    env.set_task_generator(NoCache(), seed=6, samples=64)
+    assert np.array_equal(env._pool['target'][:, :1089].cpu().numpy().reshape(64, 9, 11, 11),
+                          O.sample_tasks(64, max_blocks=3, height_levels=1, max_dist=2, num_colors=2, seed=6))

@@ -1,11 +1,15 @@
 """Pins the C oracle (oracle/iglu_oracle.c) against the EXECUTED reference: every golden trace
 and reward known answer recorded by oracle/make_golden.py must be reproduced bit-for-bit
 (fp64 pose compared with ==, not a tolerance: same libm, same operation order)."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import oracle as O
 from tests import golden_io as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _replay(tr, kind):
@@ -173,3 +177,45 @@ def test_reward_pairs():
         n_adm, rect, ts = O.task_describe(z['targets'][i], None if full is None else full[0], bool(z['invariant'][i]))
         assert n_adm.tolist() == z['n_adm'][i].tolist(), i
         assert ts == z['target_size'][i]
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/gridworld'), reason='needs the reference tree (build container)')
+def test_sample_tasks_matches_reference_distribution():
+    """The oracle's sample_task restatement (counter-based stream) against the executed RandomTasks.sample_task
+    (task_set.py:135-157, numpy's Mersenne Twister): same structure invariants, same distributions."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'oracle', 'refharness'))
+    import load_reference
+    load_reference.load()
+    from gridworld.tasks.task_set import RandomTasks
+    n = 1500
+    for spec in (dict(max_blocks=4, height_levels=1, max_dist=2, num_colors=1),
+                 dict(max_blocks=6, height_levels=3, max_dist=2, num_colors=4)):
+        np.random.seed(11)
+        gen = RandomTasks(max_cache=0, **spec)
+        ref = np.stack([np.asarray(gen.sample_task().target_grid) for _ in range(n)]).astype(np.int8)
+        got = O.sample_tasks(n, seed=5, **spec)
+
+        def stats(T):
+            lv = T[:, :spec['height_levels']]
+            assert (T[:, spec['height_levels']:] == 0).all()
+            cnt = (lv != 0).reshape(len(T), spec['height_levels'], -1).sum(2)
+            assert (cnt == spec['max_blocks']).all()          # every level gets exactly max_blocks blocks
+            assert T.max() <= spec['num_colors'] and T.min() >= 0
+            ext = []
+            for t in lv.reshape(-1, 11, 11):
+                xs, zs = np.nonzero(t)
+                ext.append((xs.max() - xs.min(), zs.max() - zs.min()))
+            ext = np.array(ext)
+            assert ext.max() <= 2 * spec['max_dist']           # all blocks within max_dist of the level's first block
+            occ = (lv != 0).reshape(-1, 11, 11).mean(0)         # where blocks land
+            col = np.bincount(lv[lv != 0].ravel(), minlength=7)[1:] / np.count_nonzero(lv)
+            hx = np.bincount(ext[:, 0], minlength=5) / len(ext)
+            hz = np.bincount(ext[:, 1], minlength=5) / len(ext)
+            return occ, col, hx, hz
+        for a, b in zip(stats(ref), stats(got)):
+            assert np.abs(a - b).max() < 0.05, (spec, np.abs(a - b).max())
+    # the stream is a function of (seed, task index): shards can split a pool
+    whole = O.sample_tasks(64, max_blocks=5, height_levels=2, num_colors=3, seed=9)
+    part = O.sample_tasks(24, max_blocks=5, height_levels=2, num_colors=3, seed=9, first_task=40)
+    assert np.array_equal(whole[40:], part)
