@@ -211,6 +211,82 @@ def pool_arrays(tasks, samples=0):
     return targets, starts, chats
 
 
+class _Record:
+    """Attribute bag standing in for a pickled reference object (its class is never imported)."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {})
+
+
+class _StagedRecord(_Record):
+    """A pickled reference Subtasks: dialog, structure_seq (block lists after every turn), ..."""
+
+
+class _TaskRecord(_Record):
+    """A pickled reference Task: target_grid, starting_grid, chat, ..."""
+
+
+class _DatasetUnpickler(pickle.Unpickler):
+    """IGLUDataset.dump_tasks_dataset (reference data/iglu_dataset.py:204-216) pickles {task id: [Subtasks, ...]}.
+    The two task classes are mapped to attribute bags and apart from them only numpy array / scalar reconstruction
+    and builtin containers are allowed, so that loading a file cannot run arbitrary code."""
+    _ALLOWED = {('numpy.core.multiarray', 'scalar'), ('numpy._core.multiarray', 'scalar'), ('numpy', 'dtype'),
+                ('numpy.core.multiarray', '_reconstruct'), ('numpy._core.multiarray', '_reconstruct'),
+                ('numpy', 'ndarray'), ('builtins', 'tuple'), ('builtins', 'list'), ('builtins', 'dict'),
+                ('builtins', 'set'), ('collections', 'OrderedDict'), ('collections', 'defaultdict'),
+                ('copyreg', '_reconstructor'), ('builtins', 'object')}
+    _CLASSES = {('gridworld.tasks.task', 'Subtasks'): _StagedRecord, ('gridworld.tasks.task', 'Task'): _TaskRecord,
+                ('gridworld.tasks', 'Subtasks'): _StagedRecord, ('gridworld.tasks', 'Task'): _TaskRecord}
+
+    def find_class(self, module, name):
+        if (module, name) in self._CLASSES:
+            return self._CLASSES[(module, name)]
+        if (module, name) in self._ALLOWED:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f'task dataset refers to {module}.{name}: not allowed')
+
+
+def _staged_tasks(rec):
+    """The single-turn tasks of one staged (multi-turn) structure, as the reference enumerates them (Subtasks.__iter__
+    / create_task, task.py:251-285): turn i starts from the blocks after turn i - 1 (nothing for i = 0), its target is
+    the blocks after turn i, and its chat is every utterance up to and including turn i, one per line."""
+    seq, dialog = rec.structure_seq, rec.dialog
+    lines, out = [], []
+    for i, blocks in enumerate(seq):
+        if i < len(dialog):
+            turn = dialog[i]
+            lines.append('\n'.join(turn) if isinstance(turn, list) else turn)
+        out.append(Task('\n'.join(lines), _dense_int8(list(blocks)).astype(np.int32),
+                        starting_grid=[tuple(int(v) for v in b) for b in (seq[i - 1] if i else [])],
+                        full_grid=_dense_int8(list(seq[-1])).astype(np.int32)))
+    return out
+
+
+def load_tasks_dataset(path):
+    """Reads a parsed-task cache in the format of the reference's IGLUDataset.dump_tasks_dataset (bz2-compressed
+    pickle of {task id: [Subtasks, ...]}, data/iglu_dataset.py:204-216) without importing the reference, and returns
+    [(task id, session index, [Task per turn])]. Feed the tasks to IGLUVecEnv.set_task_generator / pool_arrays."""
+    import bz2
+    with open(path, 'rb') as f:
+        raw = bz2.decompress(f.read())
+    data = _DatasetUnpickler(io.BytesIO(raw)).load()
+    if not isinstance(data, dict):
+        raise ValueError('task dataset must hold a dict task id -> list of staged tasks')
+    out = []
+    for tid in sorted(data, key=str):
+        sessions = data[tid] if isinstance(data[tid], (list, tuple)) else [data[tid]]
+        for k, rec in enumerate(sessions):
+            if isinstance(rec, _StagedRecord):
+                out.append((str(tid), k, _staged_tasks(rec)))
+            elif isinstance(rec, _TaskRecord):
+                out.append((str(tid), k, [Task(rec.chat, np.asarray(rec.target_grid),
+                                               starting_grid=getattr(rec, 'starting_grid', None),
+                                               full_grid=getattr(rec, 'full_grid', None))]))
+            else:
+                raise ValueError(f'task dataset entry {tid!r} holds {type(rec).__name__}, not a task')
+    return out
+
+
 class _GoalsUnpickler(pickle.Unpickler):
     """goals.pkl holds {name: [(x, y, z, colour), ...]} with numpy integer scalars: only
     what is needed to rebuild those is allowed, so that loading a file cannot run arbitrary code."""

@@ -20,6 +20,8 @@ Files written (all small, committed):
   traces_dict.npz    walking Dict (discretize=False) traces
   misc.npz           Task.get_intersection and Subtasks (reset / progressive step_intersection) known answers
   surface.npz        N = 1 gym surface: SizeReward, initialize_world / deinitialize_world, host set_task_generator
+  tasks_dataset.pkl.bz2 + tasks_dataset_expected.npz   a parsed-task cache in IGLUDataset's format and the single-turn
+                     tasks the reference derives from it
 """
 import os
 import pickle
@@ -761,12 +763,52 @@ def gen_surface(gym, Task, Tasks):
     print('surface.npz')
 
 
+def gen_dataset(Tasks):
+    """A parsed-task cache as IGLUDataset.dump_tasks_dataset writes it (data/iglu_dataset.py:204-209: bz2-compressed
+    pickle of {task id: [Subtasks, ...]}) with the single-turn tasks the reference's Subtasks.__iter__ derives from
+    it, for gridworld_b200.tasks.load_tasks_dataset."""
+    import bz2
+    from gridworld.tasks.task import Subtasks
+    rng = np.random.RandomState(31)
+    np.random.seed(3)
+    data = {}
+    for name, turns in (('c17', 4), ('c3', 1), ('c101', 3)):
+        sessions = []
+        for s_i in range(2 if turns > 1 else 1):
+            blocks, seq, dialog = [], [], []
+            for t in range(turns):
+                for _ in range(rng.randint(1, 4)):
+                    cell = (int(rng.randint(-5, 6)), int(rng.randint(-1, 4)), int(rng.randint(-5, 6)))
+                    if all(b[:3] != cell for b in blocks):
+                        blocks.append(cell + (int(rng.randint(1, 7)),))
+                if t == 2 and blocks:
+                    blocks.pop(0)      # a turn that also removes a block
+                seq.append(list(blocks))
+                dialog.append([f'<A> turn {t} of {name}', '<B> ok'] if t % 2 else f'<A> turn {t} of {name}')
+            sessions.append(Subtasks(dialog, seq, invariant=False, progressive=True))
+        data[name] = sessions
+    with open(os.path.join(OUT, 'tasks_dataset.pkl.bz2'), 'wb') as f:
+        f.write(bz2.compress(pickle.dumps(data)))
+    rows = []
+    for name in sorted(data):
+        for k, st in enumerate(data[name]):
+            for task in st:
+                rows.append((name, k, np.asarray(task.target_grid).astype(np.int8),
+                             np.asarray(Tasks.to_dense(task.starting_grid)).astype(np.int8),
+                             np.asarray(task.full_grid).astype(np.int8), task.chat))
+    np.savez_compressed(os.path.join(OUT, 'tasks_dataset_expected.npz'),
+                        names=np.array([r[0] for r in rows]), session=np.array([r[1] for r in rows], np.int32),
+                        targets=np.array([r[2] for r in rows]), starts=np.array([r[3] for r in rows]),
+                        fulls=np.array([r[4] for r in rows]), chats=np.array([r[5] for r in rows]))
+    print('tasks_dataset.pkl.bz2', len(rows), 'single-turn tasks')
+
+
 def main():
     load_reference.load()
     import gym
     from gridworld.tasks import Task, Tasks
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator', 'surface']
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator', 'surface', 'dataset']
     if 'goals' in which:
         gen_goals(Task, Tasks)
     if 'pairs' in which:
@@ -783,6 +825,8 @@ def main():
         gen_generator(gym, Task, Tasks)
     if 'surface' in which:
         gen_surface(gym, Task, Tasks)
+    if 'dataset' in which:
+        gen_dataset(Tasks)
 
 
 if __name__ == '__main__':

@@ -191,6 +191,33 @@ def test_pool_arrays_and_goal_file_loader(tmp_path):
         load_goals(str(bad))
 
 
+def test_tasks_dataset_loader(tmp_path):
+    """IGLUDataset-format parsed-task cache (bz2-pickled {task id: [Subtasks]}, reference data/iglu_dataset.py:204-216)
+    read without the reference: the single-turn tasks equal the ones the reference's Subtasks.__iter__ produced."""
+    import bz2
+    import pickle
+    from gridworld_b200.tasks import Tasks, load_tasks_dataset, pool_arrays
+    z = G.load('tasks_dataset_expected.npz')
+    loaded = load_tasks_dataset(os.path.join(G.GOLDEN, 'tasks_dataset.pkl.bz2'))
+    tasks = [(nm, k, t) for nm, k, ts in loaded for t in ts]
+    assert [t[0] for t in tasks] == z['names'].tolist() and [t[1] for t in tasks] == z['session'].tolist()
+    for i, (_, _, t) in enumerate(tasks):
+        assert np.array_equal(t.target_grid, z['targets'][i]) and t.chat == str(z['chats'][i])
+        assert np.array_equal(np.asarray(Tasks.to_dense(t.starting_grid)), z['starts'][i])
+        assert np.array_equal(t.full_grid, z['fulls'][i])
+    T, S, chats = pool_arrays([t for _, _, t in tasks])
+    assert np.array_equal(T, z['targets']) and np.array_equal(S, z['starts']) and chats == z['chats'].tolist()
+
+    class Evil:
+        def __reduce__(self):
+            import os as _os
+            return (_os.system, ('echo pwned',))
+    bad = tmp_path / 'bad.pkl.bz2'
+    bad.write_bytes(bz2.compress(pickle.dumps({'c1': [Evil()]})))
+    with pytest.raises(pickle.UnpicklingError):
+        load_tasks_dataset(str(bad))
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints ONE JSON line with the
     contract's keys; it never touches CUDA."""
