@@ -49,6 +49,13 @@ class RandomTaskSpec(C.Structure):
                 ('num_colors', C.c_int32)]
 
 
+class StagedTasks(C.Structure):
+    """iglu_staged_tasks (include/iglu_b200.h)"""
+    _fields_ = [('m', C.c_int64), ('tlist', C.c_void_p), ('tmeta', C.c_void_p), ('next_stage', C.c_void_p),
+                ('stage_of', C.c_void_p), ('progressive', C.c_int32), ('reserved', C.c_int32),
+                ('state', C.c_void_p), ('out', C.c_void_p)]
+
+
 class EnvSnapshot(C.Structure):
     """iglu_env_snapshot (include/iglu_b200.h)"""
     _fields_ = [('pose', C.c_double * 6), ('reward', C.c_double), ('agent_pos', C.c_float * 5),
@@ -63,7 +70,8 @@ EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_des
            'iglu_reset', 'iglu_step_walking', 'iglu_step_flying', 'iglu_step_walking_dict',
            'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
            'iglu_task_pool_prepare', 'iglu_task_pool_attach', 'iglu_step_walking_host_async', 'iglu_wait',
-           'iglu_fetch_env_host', 'iglu_max_intersection_strided', 'iglu_sample_tasks')
+           'iglu_fetch_env_host', 'iglu_max_intersection_strided', 'iglu_sample_tasks',
+           'iglu_staged_prepare', 'iglu_staged_step')
 
 _lib = None
 
@@ -102,6 +110,9 @@ def load():
         L.iglu_max_intersection_strided.argtypes = [vp, i64, vp, i64, vp, i64, i32, vp, vp, i64, vp]
     if hasattr(L, 'iglu_sample_tasks'):
         L.iglu_sample_tasks.argtypes = [vp, i64, C.POINTER(RandomTaskSpec), C.c_uint64, i64, vp]
+    if hasattr(L, 'iglu_staged_step'):
+        L.iglu_staged_prepare.argtypes = [vp, C.POINTER(StagedTasks), vp, vp, vp]
+        L.iglu_staged_step.argtypes = [vp, C.POINTER(State), C.POINTER(StagedTasks), vp, vp]
     L.iglu_last_launch_count.argtypes = [vp]
     L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]
     L.iglu_task_pool_attach.argtypes = [vp, C.POINTER(TaskPool)]

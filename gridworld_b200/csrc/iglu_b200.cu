@@ -578,6 +578,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
 __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, iglu_config cfg,
                                                    const int8_t *__restrict__ target,
                                                    const int8_t *__restrict__ start,
+                                                   const int8_t *__restrict__ full,
                                                    const double *__restrict__ init_pose,
                                                    const int32_t *__restrict__ env_idx, int64_t count) {
     const int lane = threadIdx.x & 31;
@@ -588,7 +589,8 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
     const int64_t n = st.n;
     const int8_t *t = target + row * CELLS;
     const int8_t *s = start ? start + row * CELLS : nullptr;
-    int8_t *gt = st.target + e * GSTRIDE, *gi = st.init + e * GSTRIDE;
+    const int8_t *fg = full ? full + row * CELLS : nullptr;   // task.py:63-64: admissible shifts from full_grid
+    int8_t *gt = st.target ? st.target + e * GSTRIDE : nullptr, *gi = st.init ? st.init + e * GSTRIDE : nullptr;
     uint16_t *tl = st.tlist + e * cfg.tlist_cap;
     const int room = cfg.tlist_cap - TL_HDR;
     int nout = 0, xmin = 10, xmax = 0, zmin = 10, zmax = 0, any_start = 0;
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
             tv = t[c];
             sv = s ? (int)s[c] : 0;
         }
-        if (c < GSTRIDE) { gt[c] = (int8_t)tv; gi[c] = (int8_t)sv; }
+        if (c < GSTRIDE && gt) { gt[c] = (int8_t)tv; gi[c] = (int8_t)sv; }
         if (c < CELLS && obs.target_grid) obs.target_grid[e * CELLS + c] = tv;
         const int d = tv - sv;  // env.py:230
         const unsigned m = __ballot_sync(0xffffffffu, d != 0);
@@ -611,6 +613,10 @@ __global__ void __launch_bounds__(256) k_task_prep(iglu_state st, iglu_obs obs, 
             const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
             const int pos = nout + __popc(m & ((1u << lane) - 1u));
             if (pos < room) tl[TL_HDR + pos] = (uint16_t)(y | (x << 4) | (z << 8) | (code_of(d) << 12));
+            if (!fg) { xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z); }
+        }
+        if (fg && c < CELLS && fg[c] != 0) {
+            const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
             xmin = min(xmin, x); xmax = max(xmax, x); zmin = min(zmin, z); zmax = max(zmax, z);
         }
         nout += __popc(m);
@@ -644,12 +650,11 @@ __device__ __forceinline__ uint32_t sample_draw(uint64_t seed, int64_t task, uin
     return (uint32_t)(((x >> 32) * (uint64_t)range) >> 32);
 }
 
-__global__ void __launch_bounds__(128) k_sample_tasks(int8_t *__restrict__ out, int64_t m, iglu_random_task_spec spec,
+__global__ void __launch_bounds__(128) k_sample_tasks(int8_t *out, int64_t m, iglu_random_task_spec spec,
                                                       uint64_t seed, int64_t first_task) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m) return;
-    int8_t *g = out + t * CELLS;
-    for (int c = 0; c < CELLS; c++) g[c] = 0;
+    int8_t *g = out + t * CELLS;   // zeroed by the cudaMemsetAsync that iglu_sample_tasks enqueues before this kernel
     uint32_t ctr = 0;
     const uint32_t span = (uint32_t)(2 * spec.max_dist + 1);
     for (int h = 0; h < spec.height_levels && h < 9; h++) {
@@ -724,6 +729,81 @@ __global__ void __launch_bounds__(256) k_reset(iglu_state st, iglu_obs obs, cons
         }
         obs.reward[e] = 0.0;
         obs.done[e] = 0;
+    }
+}
+
+// ------------------------------------------------------------------ multi-turn structures with progressive goals
+// Subtasks.step_intersection (tasks/task.py:288-298) for every env, on the env's RAW grid: the score of the current
+// turn's Task (target = the structure after that turn, admissible shifts from the FULL structure, task.py:63-64), and
+// when that task is complete the goal moves on to the next turn (create_task + reset + a second step_intersection
+// with prev_grid_size = 0). One warp per env; runs after the step kernels when staged tasks are attached.
+struct __align__(16) StagedScratch {
+    uint32_t grid[GSTRIDE / 4];
+    uint32_t init[GSTRIDE / 4];
+    EvalScratch es;
+};
+constexpr int STAGED_WARPS = 4;
+
+__global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st, iglu_staged_tasks sg,
+                                                                  const int32_t *__restrict__ task_row, int cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
+    StagedScratch *scratch = reinterpret_cast<StagedScratch *>(smem_raw + TABLE_BYTES);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    StagedScratch &ws = scratch[wid];
+    build_cell_lut(lut, threadIdx.x, STAGED_WARPS * 32);
+    for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
+    __syncthreads();
+    const int64_t n = st.n;
+    const int64_t e = (int64_t)blockIdx.x * STAGED_WARPS + wid;
+    if (e >= n) return;
+    {   // stage the env's grid and starting grid
+        const int4 *g4 = reinterpret_cast<const int4 *>(st.grid + e * GSTRIDE);
+        const int4 *i4 = reinterpret_cast<const int4 *>(st.init + e * GSTRIDE);
+        for (int q = lane; q < GSTRIDE / 16; q += 32) {
+            reinterpret_cast<int4 *>(ws.grid)[q] = g4[q];
+            reinterpret_cast<int4 *>(ws.init)[q] = i4[q];
+        }
+    }
+    __syncwarp();
+    const Staged<true> G{ws.grid, 0}, I{ws.init, 0};
+    const int size = __reduce_add_sync(0xffffffffu, count_nonzero_cells(G, lane));
+    int goal = sg.state[0 * n + e], prev = sg.state[1 * n + e], max_int = sg.state[2 * n + e];
+    auto eval = [&](const uint32_t *x, int row) {   // Task(stage `row`).maximal_intersection(x)
+        const uint16_t *tl = sg.tlist + (int64_t)row * cap;
+        const int4 rc = *reinterpret_cast<const int4 *>(tl);
+        return eval_max_intersection<false>(ws.es, x, nullptr, lut, tl + TL_HDR, sg.tmeta[row], rc, 4, lane, nullptr);
+    };
+    auto create_task = [&](int row, int nstart) {   // create_task(...) + task.reset(): task.py:256-285, 74-86
+        max_int = nstart ? eval(ws.init, row) : 0;
+        prev = nstart;
+    };
+    const bool fresh = st.istate[4 * n + e] == 1;   // first step of an episode: Subtasks.reset() happened in env.reset()
+    const int nstart = (fresh || sg.progressive) ? __reduce_add_sync(0xffffffffu, count_nonzero_cells(I, lane)) : 0;
+    if (fresh) {
+        const int64_t r = task_row ? task_row[e] : e;
+        goal = sg.stage_of ? sg.stage_of[r] : (int)r;
+        create_task(goal, nstart);
+    }
+    // task.py:103-119 on the raw grid
+    const int wrong = prev - size;
+    int mi = wrong != 0 ? eval(ws.grid, goal) : max_int;
+    bool done = mi == sg.tmeta[sg.m + goal];
+    const int right = mi - max_int;
+    max_int = mi;
+    prev = size;
+    const int nxt = sg.next_stage[goal];
+    if (done && sg.progressive && nxt >= 0) {   // task.py:290-297
+        goal = nxt;
+        create_task(goal, nstart);
+        mi = size != 0 ? eval(ws.grid, goal) : max_int;   // prev_grid_size = 0: wrong_placement = -size
+        done = mi == sg.tmeta[sg.m + goal];
+        max_int = mi;
+        prev = size;
+    }
+    if (lane == 0) {
+        sg.state[0 * n + e] = goal; sg.state[1 * n + e] = prev; sg.state[2 * n + e] = max_int;
+        sg.out[0 * n + e] = right; sg.out[1 * n + e] = wrong; sg.out[2 * n + e] = (int)done; sg.out[3 * n + e] = goal;
     }
 }
 
@@ -948,7 +1028,7 @@ extern "C" int iglu_set_tasks(iglu_ctx *ctx, const iglu_state *st, const iglu_ob
     if (!ctx || !state_ok(st, obs) || !target || count <= 0) return IGLU_ERR_INVALID_ARG;
     const int threads = 256;
     const int64_t blocks = (count * 32 + threads - 1) / threads;
-    k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*st, *obs, ctx->cfg, target, start,
+    k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*st, *obs, ctx->cfg, target, start, nullptr,
                                                                          init_pose, env_idx, count);
     ctx->last_launches = 1;
     return check(cudaPeekAtLastError());
@@ -972,7 +1052,38 @@ extern "C" int iglu_task_pool_prepare(iglu_ctx *ctx, const iglu_task_pool *pool,
     const int threads = 256;
     const int64_t blocks = (pool->m * 32 + threads - 1) / threads;
     k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(st, obs, ctx->cfg, target, start, nullptr,
-                                                                         nullptr, pool->m);
+                                                                         nullptr, nullptr, pool->m);
+    ctx->last_launches = 1;
+    return check(cudaPeekAtLastError());
+}
+
+static bool staged_ok(const iglu_staged_tasks *sg) {
+    return sg && sg->m > 0 && sg->m < (int64_t)1 << 31 && sg->tlist && sg->tmeta && sg->next_stage && sg->state && sg->out;
+}
+
+extern "C" int iglu_staged_prepare(iglu_ctx *ctx, const iglu_staged_tasks *sg, const int8_t *target,
+                                   const int8_t *full, void *stream) {
+    if (!ctx || !staged_ok(sg) || !target || !full) return IGLU_ERR_INVALID_ARG;
+    iglu_state st;
+    iglu_obs obs;
+    memset(&st, 0, sizeof(st));
+    memset(&obs, 0, sizeof(obs));
+    st.n = sg->m;
+    st.tlist = sg->tlist; st.tmeta = sg->tmeta;
+    const int threads = 256;
+    const int64_t blocks = (sg->m * 32 + threads - 1) / threads;
+    k_task_prep<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(st, obs, ctx->cfg, target, nullptr, full, nullptr,
+                                                                         nullptr, sg->m);
+    ctx->last_launches = 1;
+    return check(cudaPeekAtLastError());
+}
+
+extern "C" int iglu_staged_step(iglu_ctx *ctx, const iglu_state *st, const iglu_staged_tasks *sg,
+                                const int32_t *task_row, void *stream) {
+    if (!ctx || !st || st->n <= 0 || !st->grid || !st->init || !st->istate || !staged_ok(sg)) return IGLU_ERR_INVALID_ARG;
+    const size_t smem = TABLE_BYTES + STAGED_WARPS * sizeof(StagedScratch);
+    k_staged_step<<<(unsigned)((st->n + STAGED_WARPS - 1) / STAGED_WARPS), STAGED_WARPS * 32, smem,
+                    (cudaStream_t)stream>>>(*st, *sg, task_row, ctx->cfg.tlist_cap);
     ctx->last_launches = 1;
     return check(cudaPeekAtLastError());
 }
@@ -983,6 +1094,8 @@ extern "C" int iglu_sample_tasks(int8_t *targets, int64_t m, const iglu_random_t
     if (spec->max_blocks < 1 || spec->height_levels < 1 || spec->height_levels > 9 || spec->max_dist < 0 ||
         spec->max_dist > 10 || spec->num_colors < 1 || spec->num_colors > 6)
         return IGLU_ERR_INVALID_ARG;
+    int rc = check(cudaMemsetAsync(targets, 0, (size_t)m * CELLS, (cudaStream_t)stream));
+    if (rc) return rc;
     k_sample_tasks<<<(unsigned)((m + 127) / 128), 128, 0, (cudaStream_t)stream>>>(targets, m, *spec, seed, first_task);
     return check(cudaPeekAtLastError());
 }

@@ -211,6 +211,47 @@ def pool_arrays(tasks, samples=0):
     return targets, starts, chats
 
 
+def staged_arrays(structures):
+    """Arrays for IGLUVecEnv.set_staged_tasks from multi-turn structures -- objects with a `.structure_seq` (the shape
+    of the reference's Subtasks, tasks/task.py:208-308; `.dialog` is used for the chats when present) or plain lists
+    [blocks after turn 0, blocks after turn 1, ...] of (x, y, z, colour) rows.
+
+    Task pool (what an episode can be): for a structure with L turns the rows turn = -1 .. L - 2, i.e. "start from the
+    structure after turn `turn` (nothing for -1), build the one after turn + 1" -- the tasks Subtasks.reset() creates.
+    Stage rows (what the goal can become): turns 0 .. L - 1 plus one repeat of the last turn (see
+    include/iglu_b200.h iglu_staged_tasks), each scored against the FULL structure's admissible shifts."""
+    pool_t, pool_s, chats, rows = [], [], [], []
+    stage_t, stage_f, next_stage, stage_of, base = [], [], [], [], []
+    for si, st in enumerate(structures):
+        seq = getattr(st, 'structure_seq', st)
+        dialog = getattr(st, 'dialog', None) or [''] * len(seq)
+        dense = [_dense_int8([tuple(int(v) for v in b) for b in blocks]) for blocks in seq]
+        L = len(dense)
+        if L == 0:
+            raise ValueError('a structure needs at least one turn')
+        b0 = len(stage_t)
+        base.append(b0)
+        for j in range(L + 1):
+            stage_t.append(dense[min(j, L - 1)])
+            stage_f.append(dense[L - 1])
+            next_stage.append(b0 + j + 1 if j < L else -1)
+        lines = []
+        for turn in range(-1, L - 1):
+            goal = turn + 1
+            if goal < len(dialog):
+                utt = dialog[goal]
+                lines.append('\n'.join(utt) if isinstance(utt, list) else utt)
+            pool_t.append(dense[goal])
+            pool_s.append(dense[turn] if turn >= 0 else np.zeros(BUILD_ZONE_SIZE, np.int8))
+            chats.append('\n'.join(lines))
+            rows.append((si, turn))
+            stage_of.append(b0 + goal)
+    return dict(pool_targets=np.stack(pool_t), pool_starts=np.stack(pool_s), chats=chats, rows=rows,
+                stage_targets=np.stack(stage_t), stage_fulls=np.stack(stage_f),
+                next_stage=np.array(next_stage, np.int32), stage_of=np.array(stage_of, np.int32),
+                stage_base=np.array(base, np.int32))
+
+
 class _Record:
     """Attribute bag standing in for a pickled reference object (its class is never imported)."""
 

@@ -122,6 +122,7 @@ class IGLUVecEnv:
         self._was_reset = False   # every env has been reset since its task rows were (re)written
         self._reset_seen = None
         self._pool = None
+        self._staged = None
         self.dialogs = None
 
         dev = self.device
@@ -317,6 +318,49 @@ class IGLUVecEnv:
         self.dialogs = chats
         return self.set_task_pool(targets, starts, seed=seed, env_offset=env_offset, next_task=next_task, reset=reset)
 
+    def set_staged_tasks(self, structures, progressive=True, seed=0, env_offset=0, next_task=None, reset=True):
+        """Multi-turn structures with progressive goals on the device (reference Subtasks, tasks/task.py:208-308).
+
+        structures : list of objects with `.structure_seq` (+ `.dialog`), e.g. the reference's own Subtasks, or plain
+                     lists of per-turn block lists (see tasks.staged_arrays).
+        Every reset draws one (structure, starting turn) task from the device-resident pool (as set_task_pool does;
+        next_task imposes the row -- rows are listed in self.staged_rows as (structure index, turn)). After every
+        step() the staged score of Subtasks.step_intersection(env.grid) -- right / wrong placement and done of the
+        CURRENT turn's task, which moves on to the next turn when complete -- is in self.staged (device tensors)."""
+        from .tasks import staged_arrays
+        a = staged_arrays(structures)
+        self.dialogs = a['chats']
+        self.staged_rows = a['rows']
+        self.set_task_pool(a['pool_targets'], a['pool_starts'], seed=seed, env_offset=env_offset, next_task=next_task,
+                           reset=False)
+        dev, n, ms = self.device, self.num_envs, a['stage_targets'].shape[0]
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.int32, device=dev)  # noqa: E731
+        bufs = dict(tlist=torch.zeros(ms, self._tlist.shape[1], dtype=torch.int16, device=dev), tmeta=z(8, ms),
+                    next_stage=torch.as_tensor(a['next_stage'], device=dev),
+                    stage_of=torch.as_tensor(a['stage_of'], device=dev), state=z(4, n), out=z(4, n),
+                    base=torch.as_tensor(a['stage_base'], device=dev))
+        sg = _lib.StagedTasks(ms, bufs['tlist'].data_ptr(), bufs['tmeta'].data_ptr(), bufs['next_stage'].data_ptr(),
+                              bufs['stage_of'].data_ptr(), int(bool(progressive)), 0, bufs['state'].data_ptr(),
+                              bufs['out'].data_ptr())
+        t = self._dev(a['stage_targets'], torch.int8, (ms, _lib.CELLS))
+        f = self._dev(a['stage_fulls'], torch.int8, (ms, _lib.CELLS))
+        self._check_block_capacity(t, None)
+        with self._guard():
+            _lib.check(self._L.iglu_staged_prepare(self._ctx, C.byref(sg), t.data_ptr(), f.data_ptr(), self._stream()))
+            self._count()
+        bufs['struct'] = sg
+        self._staged = bufs
+        return self.reset() if reset else None
+
+    @property
+    def staged(self):
+        """Staged score of the last step (Subtasks.step_intersection on each env's grid): int32 device tensors
+        right, wrong, goal (stage row; minus self._staged['base'][structure] = the turn) and bool done."""
+        if self._staged is None:
+            raise ValueError('no staged tasks attached (set_staged_tasks)')
+        o = self._staged['out']
+        return {'right': o[0], 'wrong': o[1], 'done': o[2].bool(), 'goal': o[3]}
+
     @property
     def task_ids(self):
         """int32 [num_envs]: pool index of each env's current task (-1 before its first draw); the host
@@ -406,6 +450,10 @@ class IGLUVecEnv:
                 _lib.check(L.iglu_step_walking_dict(self._ctx, st, b.data_ptr(), cam.data_ptr(), ob,
                                                     self._stream()))
             self._count()
+            if self._staged is not None:   # Subtasks.step_intersection(env.grid) for every env, as one more launch
+                _lib.check(L.iglu_staged_step(self._ctx, st, C.byref(self._staged['struct']),
+                                              self._pool['cursor'].data_ptr(), self._stream()))
+                self._count()
         return self.observation(), self._reward, self._done.view(torch.bool), {}
 
     def step_host(self, actions_host, reward_host, done_host, wait=True):
@@ -629,7 +677,7 @@ def max_intersection(grids, targets, full_grids=None, invariant=True, return_arg
                 out.data_ptr(), None if arg is None else arg.data_ptr(), k,
                 C.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)))
         return (out, arg) if return_argmax else out
-    k = g.shape[0] if g.dim() == 4 else 1
+    k = g.shape[0] if g.dim() in (2, 4) else 1   # [k, 9, 11, 11] or [k, 1089]; a single grid otherwise
 
     def prep(x):
         if x is None:

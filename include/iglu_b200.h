@@ -199,6 +199,38 @@ typedef struct iglu_random_task_spec {
 int iglu_sample_tasks(int8_t *targets, int64_t m, const iglu_random_task_spec *spec, uint64_t seed,
                       int64_t first_task, void *stream);
 
+/* Multi-turn structures with progressive goals -- reference Subtasks (tasks/task.py:208-308): structure_seq[i] is the
+ * structure after turn i; a task (turn_start, turn_goal) starts from structure_seq[turn_start] and has target
+ * structure_seq[min(turn_goal, L - 1)] with full_grid = structure_seq[L - 1] (create_task, 256-285). GridWorld.step
+ * only ever scores the episode's synthetic task (env.py:291); Subtasks.step_intersection (288-298) is what a
+ * training loop calls on the env's grid to get the staged (right, wrong, done), and when the current task is
+ * complete it moves the goal on to the next turn. iglu_staged_step does that for all n envs after a step call.
+ * Stage rows: one per turn of every structure plus, per structure, one more row that repeats the last turn (the
+ * reference advances once past the end, len(structure_seq) > task_goal, and min() then repeats the last target). */
+typedef struct iglu_staged_tasks {
+    int64_t m;            /* stage rows */
+    uint16_t *tlist;      /* [m][tlist_cap]  same row format as iglu_state.tlist: rectangles from the FULL structure,
+                                             then the non-zero cells of the stage's target */
+    int32_t *tmeta;       /* [8][m]          w0: list entries, w1: target_size */
+    int32_t *next_stage;  /* [m]             row of the next turn of the same structure, -1 after the repeated row */
+    int32_t *stage_of;    /* [rows of the task pool] goal stage row of task row r (its turn_goal), or NULL = identity */
+    int32_t progressive;  /* Subtasks(progressive=...) */
+    int32_t reserved;
+    int32_t *state;       /* [4][n] per env: goal stage row, prev_grid_size, max_int (of the current staged task), - */
+    int32_t *out;         /* [4][n] per env and step: right_placement, wrong_placement, done, goal stage row */
+} iglu_staged_tasks;
+
+/* Task.__init__ of every stage row (task.py:9-72 with full_grid): target, full device int8 [m][1089] dense. */
+int iglu_staged_prepare(iglu_ctx *ctx, const iglu_staged_tasks *staged, const int8_t *target, const int8_t *full,
+                        void *stream);
+
+/* Subtasks.step_intersection(env.grid) for all n envs; call after a step call. An env whose step_no is 1 starts a new
+ * episode: its staged task is (re)created first -- Subtasks.reset() inside GridWorld.reset (env.py:219) -- with goal
+ * stage_of[task_row[e]] (task_row NULL = e; with a task pool pass iglu_task_pool.cursor, whose first n words are the
+ * pool row of each env's current task). */
+int iglu_staged_step(iglu_ctx *ctx, const iglu_state *st, const iglu_staged_tasks *staged, const int32_t *task_row,
+                     void *stream);
+
 /* Attach (pool != NULL, m > 0) or detach (NULL) the generator. The ctx keeps a COPY of the struct, i.e. it
  * retains the device pointers until detached or destroyed; the caller keeps the buffers alive. */
 int iglu_task_pool_attach(iglu_ctx *ctx, const iglu_task_pool *pool);

@@ -858,3 +858,58 @@ void orc_sample_tasks(int8_t *out, int64_t m, int max_blocks, int height_levels,
         }
     }
 }
+
+/* tasks/task.py:208-308 Subtasks: a multi-turn structure whose goal moves on to the next turn's target when the
+ * current one is complete (step_intersection, 288-298). One handle = one structure + its current task. */
+typedef struct {
+    int L, progressive;
+    int32_t *seq;         /* [L][CELLS] dense structure after every turn (Tasks.to_dense of structure_seq[i]) */
+    int task_start, task_goal;
+    int32_t start[CELLS]; /* dense starting grid of the current task */
+    orc_task cur;
+} orc_staged;
+
+orc_staged *orc_staged_create(const int8_t *stages, int L, int progressive) {
+    orc_staged *s = (orc_staged *)calloc(1, sizeof(orc_staged));
+    s->L = L;
+    s->progressive = progressive;
+    s->seq = (int32_t *)malloc(sizeof(int32_t) * (size_t)L * CELLS);
+    for (int64_t i = 0; i < (int64_t)L * CELLS; i++) s->seq[i] = stages[i];
+    return s;
+}
+void orc_staged_destroy(orc_staged *s) { free(s->seq); free(s); }
+
+/* task.py:256-285 create_task(turn_start, turn_goal) + the task.reset() at its end (74-86) */
+static void staged_create_task(orc_staged *s, int turn_start, int turn_goal) {
+    const int tid = turn_goal < s->L - 1 ? turn_goal : s->L - 1;   /* min(turn_goal, len - 1); self.full is never set */
+    for (int k = 0; k < CELLS; k++) s->start[k] = turn_start == -1 ? 0 : s->seq[(int64_t)turn_start * CELLS + k];
+    orc_task_init(&s->cur, s->seq + (int64_t)tid * CELLS, s->seq + (int64_t)(s->L - 1) * CELLS, 1);
+    int nstart = 0;
+    for (int k = 0; k < CELLS; k++) nstart += s->start[k] != 0;
+    s->cur.max_int = orc_task_max_intersection(&s->cur, s->start, NULL);  /* starting_grid is a list, never None */
+    s->cur.prev_grid_size = nstart;
+    s->cur.right_placement = s->cur.wrong_placement = 0;
+}
+
+/* task.py:225-243 reset with self.next = turn */
+void orc_staged_reset(orc_staged *s, int turn) {
+    s->task_start = turn;
+    s->task_goal = turn + 1;
+    staged_create_task(s, s->task_start, s->task_goal);
+}
+
+/* task.py:288-298 */
+void orc_staged_step(orc_staged *s, const int8_t *grid, int32_t *out /* right, wrong, done, task_goal, max_int */) {
+    int32_t g[CELLS];
+    for (int k = 0; k < CELLS; k++) g[k] = grid[k];
+    int right, wrong, done;
+    task_step_intersection(&s->cur, g, &right, &wrong, &done);
+    if (done && s->L > s->task_goal && s->progressive) {
+        s->task_goal += 1;
+        staged_create_task(s, s->task_start, s->task_goal);
+        s->cur.prev_grid_size = 0;
+        int r2, w2;
+        task_step_intersection(&s->cur, g, &r2, &w2, &done);
+    }
+    out[0] = right; out[1] = wrong; out[2] = done; out[3] = s->task_goal; out[4] = s->cur.max_int;
+}

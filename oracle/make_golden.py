@@ -763,6 +763,60 @@ def gen_surface(gym, Task, Tasks):
     print('surface.npz')
 
 
+def gen_staged(gym, Task, Tasks):
+    """Multi-turn structures with progressive goals (reference tasks/task.py:208-308). GridWorld.step itself only ever
+    scores the single synthetic task of the episode (env.py:291); Subtasks.step_intersection -- which moves on to the
+    next turn's target when the current one is complete -- is the call a training loop makes on the env's grid. The
+    harness does exactly that after every env.step and records what the reference's Subtasks returned."""
+    from gridworld.tasks.task import Subtasks
+    A = [[(0, -1, -1, 1)],
+         [(0, -1, -1, 1), (1, -1, -1, 2)],
+         [(0, -1, -1, 1), (1, -1, -1, 2), (1, -1, 0, 3)]]
+    B = [[(0, -1, -1, 1)]]
+    dlgA = ['<A> a blue one', ['<A> a green one next to it', '<B> ok'], '<A> and a red one']
+    np.random.seed(0)
+    stA = Subtasks(dlgA, A)
+    stB = Subtasks(['<A> just one'], B)
+    rng = np.random.RandomState(41)
+    S1, S2, S3 = [6] + [14] * 9 + [17], [13] * 9 + [7], [13] * 9 + [8]
+    episodes = [
+        (0, -1, S1 + S2 + [0, 16] + S3 + [12] * 18 + [16] + list(walking_action_mix(rng, 15, 'builder'))),
+        (0, 0, [14] * 9 + S2 + S3 + list(walking_action_mix(rng, 25, 'builder'))),
+        (1, -1, S1 + list(walking_action_mix(rng, 12, 'builder'))),
+        (0, 1, list(walking_action_mix(rng, 45, 'builder'))),
+    ]
+    env = gym.make('IGLUGridworld-v0', render=False, vector_state=True, size_reward=False, action_space='walking',
+                   max_steps=1000)
+    rows = []
+    first = True
+    for ep, (which, turn, acts) in enumerate(episodes):
+        st = (stA, stB)[which]
+        st.next = turn
+        if first or env.unwrapped._task is not st:
+            env.set_task(st)          # resets: Subtasks.reset() -> create_task(turn, turn + 1)
+            first = False
+        else:
+            env.reset()
+        assert (st.task_start, st.task_goal) == (turn, turn + 1)
+        for a in acts:
+            obs, r, done, _ = env.step(int(a))
+            g = env.unwrapped.grid.copy()
+            sr, sw, sd = st.step_intersection(g)
+            rows.append((ep, which, turn, int(a), int(sr), int(sw), int(bool(sd)), int(st.task_goal),
+                         int(st.current.max_int), float(r), g.astype(np.int8).reshape(-1)))
+    out = dict(ep=np.array([r[0] for r in rows], np.int32), structure=np.array([r[1] for r in rows], np.int32),
+               turn=np.array([r[2] for r in rows], np.int32), actions=np.array([r[3] for r in rows], np.int32),
+               right=np.array([r[4] for r in rows], np.int32), wrong=np.array([r[5] for r in rows], np.int32),
+               done=np.array([r[6] for r in rows], np.int32), goal=np.array([r[7] for r in rows], np.int32),
+               max_int=np.array([r[8] for r in rows], np.int32), env_reward=np.array([r[9] for r in rows]),
+               grid=np.array([r[10] for r in rows], np.int8))
+    for name, seq in (('A', A), ('B', B)):
+        out['seq' + name] = np.array([np.asarray(Tasks.to_dense(list(b))).astype(np.int8) for b in seq])
+    np.savez_compressed(os.path.join(OUT, 'staged.npz'), **out)
+    print('staged.npz', len(rows), 'steps; goals reached', sorted(set(out['goal'].tolist())), 'dones',
+          int(out['done'].sum()), 'rights', int((out['right'] != 0).sum()), 'wrongs', int((out['wrong'] != 0).sum()))
+
+
 def gen_dataset(Tasks):
     """A parsed-task cache as IGLUDataset.dump_tasks_dataset writes it (data/iglu_dataset.py:204-209: bz2-compressed
     pickle of {task id: [Subtasks, ...]}) with the single-turn tasks the reference's Subtasks.__iter__ derives from
@@ -808,7 +862,7 @@ def main():
     import gym
     from gridworld.tasks import Task, Tasks
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator', 'surface', 'dataset']
+    which = sys.argv[1:] or ['goals', 'pairs', 'walking', 'flying', 'dict', 'misc', 'generator', 'surface', 'dataset', 'staged']
     if 'goals' in which:
         gen_goals(Task, Tasks)
     if 'pairs' in which:
@@ -827,6 +881,8 @@ def main():
         gen_surface(gym, Task, Tasks)
     if 'dataset' in which:
         gen_dataset(Tasks)
+    if 'staged' in which:
+        gen_staged(gym, Task, Tasks)
 
 
 if __name__ == '__main__':

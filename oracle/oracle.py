@@ -52,6 +52,11 @@ def lib():
         L.orc_tasks_prepare.argtypes = [vp, i64, i32]
         L.orc_tasks_eval.argtypes = [vp, vp, vp, i64, i32]
         L.orc_tasks_free.argtypes = [vp]
+        L.orc_staged_create.restype = vp
+        L.orc_staged_create.argtypes = [vp, i32, i32]
+        L.orc_staged_destroy.argtypes = [vp]
+        L.orc_staged_reset.argtypes = [vp, i32]
+        L.orc_staged_step.argtypes = [vp, vp, vp]
         L.orc_sample_tasks.argtypes = [vp, i64, i32, i32, i32, i32, C.c_uint64, i64]
         _lib = L
     return _lib
@@ -214,3 +219,26 @@ def sample_tasks(m, max_blocks=4, height_levels=1, max_dist=2, num_colors=1, see
     lib().orc_sample_tasks(_p(out), int(m), int(max_blocks), int(height_levels), int(max_dist), int(num_colors),
                            int(seed) & (2 ** 64 - 1), int(first_task))
     return out
+
+
+class Staged:
+    """Subtasks (reference tasks/task.py:208-308) for one multi-turn structure: reset(turn) = Subtasks.reset with
+    self.next = turn; step(grid) = Subtasks.step_intersection(grid) -> (right, wrong, done, task_goal, max_int)."""
+
+    def __init__(self, stages, progressive=True):
+        st = _i8(stages).reshape(-1, CELLS)
+        self._h = lib().orc_staged_create(_p(st), st.shape[0], int(bool(progressive)))
+
+    def reset(self, turn):
+        lib().orc_staged_reset(self._h, int(turn))
+
+    def step(self, grid):
+        g = _i8(grid, (CELLS,))
+        out = np.zeros(5, np.int32)
+        lib().orc_staged_step(self._h, _p(g), _p(out))
+        return tuple(int(v) for v in out)
+
+    def __del__(self):
+        if getattr(self, '_h', None) and _lib is not None:
+            _lib.orc_staged_destroy(self._h)
+            self._h = None

@@ -218,6 +218,32 @@ def test_tasks_dataset_loader(tmp_path):
         load_tasks_dataset(str(bad))
 
 
+def test_staged_arrays_follow_subtasks_enumeration():
+    """tasks.staged_arrays (the inputs of IGLUVecEnv.set_staged_tasks): episode tasks = what Subtasks.reset() can
+    create, stage rows = the per-turn targets + one repeat of the last, all scored against the full structure."""
+    from gridworld_b200.tasks import Tasks, staged_arrays
+    z = G.load('staged.npz')
+
+    def blocks(dense):
+        return [(int(x) - 5, int(y) - 1, int(zz) - 5, int(dense[y, x, zz])) for y, x, zz in np.argwhere(dense)]
+    A, B = [blocks(d) for d in z['seqA']], [blocks(d) for d in z['seqB']]
+
+    class Sub:   # the shape of the reference's Subtasks
+        def __init__(self, seq, dialog):
+            self.structure_seq, self.dialog = seq, dialog
+    a = staged_arrays([Sub(A, ['one', ['two', 'ok'], 'three']), B])
+    assert a['rows'] == [(0, -1), (0, 0), (0, 1), (1, -1)]
+    assert np.array_equal(a['pool_targets'], np.stack([z['seqA'][0], z['seqA'][1], z['seqA'][2], z['seqB'][0]]))
+    assert a['pool_starts'][0].sum() == 0 and np.array_equal(a['pool_starts'][1], z['seqA'][0])
+    assert np.array_equal(a['pool_starts'][2], z['seqA'][1]) and a['pool_starts'][3].sum() == 0
+    assert a['chats'] == ['one', 'one\ntwo\nok', 'one\ntwo\nok\nthree', '']
+    assert a['next_stage'].tolist() == [1, 2, 3, -1, 5, -1] and a['stage_of'].tolist() == [0, 1, 2, 4]
+    assert np.array_equal(a['stage_targets'][3], z['seqA'][2]) and np.array_equal(a['stage_targets'][5], z['seqB'][0])
+    assert all(np.array_equal(f, z['seqA'][2]) for f in a['stage_fulls'][:4])
+    assert a['stage_base'].tolist() == [0, 4]
+    assert np.array_equal(Tasks.to_dense(A[2]), z['seqA'][2])
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs next to the GPU arm) prints ONE JSON line with the
     contract's keys; it never touches CUDA."""

@@ -219,3 +219,20 @@ def test_sample_tasks_matches_reference_distribution():
     whole = O.sample_tasks(64, max_blocks=5, height_levels=2, num_colors=3, seed=9)
     part = O.sample_tasks(24, max_blocks=5, height_levels=2, num_colors=3, seed=9, first_task=40)
     assert np.array_equal(whole[40:], part)
+
+
+def test_staged_tasks_golden():
+    """Subtasks.step_intersection with progressive goals (task.py:288-298) as recorded from the reference on the
+    grids of an env trace (tests/golden/staged.npz) vs the oracle's restatement."""
+    z = G.load('staged.npz')
+    objs = [O.Staged(z['seqA']), O.Staged(z['seqB'])]
+    last_ep = -1
+    for i in range(len(z['ep'])):
+        st = objs[int(z['structure'][i])]
+        if z['ep'][i] != last_ep:
+            st.reset(int(z['turn'][i]))
+            last_ep = int(z['ep'][i])
+        got = st.step(z['grid'][i])
+        want = (int(z['right'][i]), int(z['wrong'][i]), int(z['done'][i]), int(z['goal'][i]), int(z['max_int'][i]))
+        assert got == want, (i, got, want)
+    assert set(z['goal'].tolist()) == {0, 1, 2, 3}   # every turn incl. the one past the last was reached
