@@ -48,11 +48,9 @@ constexpr int MI_CTAS = IGLU_MI_CTAS;
 constexpr int CTAS_PER_SM = 2;   // 16 warps / SM: measured faster than 20 / 24 / 32 warps with fewer registers (profiles/)
 constexpr int NB = IGLU_RING;    // TMA ring depth per warp
 constexpr int TL_HDR = 8;    // uint16 slots holding the 16-byte rectangle header of a tlist row
-constexpr int TL_PRE = 64;   // target blocks prefetched with the header (longer lists are read from global)
 
 struct __align__(16) Slot {
     uint32_t grid[GSTRIDE / 4];        // int8 grid of one env (1089 cells + zero pad)
-    uint16_t trow[TL_HDR + TL_PRE];    // rectangle header + first target blocks
 };
 
 constexpr size_t TABLE_BYTES = (CELL_LUT_N * sizeof(uint16_t) + 15) & ~(size_t)15;  // cell -> (y, 22 x + z) table per CTA
@@ -146,7 +144,7 @@ __device__ __forceinline__ int pool_draw(uint64_t seed, int64_t env, uint32_t ep
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
     x ^= x >> 31;
-    return (int)(((x >> 32) * (uint64_t)m) >> 32);
+    return (int)__umulhi((uint32_t)(x >> 32), (uint32_t)m);   // ((x >> 32) * m) >> 32, m < 2^31
 }
 
 // Per-env part of a draw (one thread): choose the index, advance the cursor, copy the tmeta column.
@@ -199,6 +197,9 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #ifndef IGLU_OBS_RING
 #define IGLU_OBS_RING 2
 #endif
+#ifndef IGLU_OBS_CTAS
+#define IGLU_OBS_CTAS 2        // resident CTAs per SM of the observe launch
+#endif
 #ifndef IGLU_OBS_DYN_GROUP
 #define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
 #endif
@@ -216,7 +217,7 @@ template <int PHASES> constexpr size_t step_smem_bytes() {
 }
 
 template <int KIND, int PHASES>
-__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : CTAS_PER_SM) k_step(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (PHASES == 2 ? IGLU_OBS_CTAS : CTAS_PER_SM)) k_step(const __grid_constant__ StepParams p) {
     constexpr int WPC = StepCfg<PHASES>::WPC;
     constexpr int NBUF = StepCfg<PHASES>::NBUF;
     constexpr bool HAS_A = PHASES != 2, HAS_B = PHASES != 1;
@@ -340,22 +341,16 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
             }
         }
 
-        // ring producer: lane 0 issues the bulk copies of env j of this group into the next slot
-        const uint32_t my_tbytes = (uint32_t)((2 * (TL_HDR + min(nblk, TL_PRE)) + 15) & ~15);
-        unsigned need_tlist = 0xffffffffu;  // envs whose target list is needed (the ones that get evaluated)
+        // ring producer: lane 0 issues the bulk copy of env j's grid row into the next slot
         auto issue = [&](int j) {
-            const uint32_t tbytes = ((need_tlist >> j) & 1u) ? __shfl_sync(0xffffffffu, my_tbytes, j) : 0u;
             if (lane == 0) {
                 const int64_t ej = env_of(j);
                 uint32_t sa = slot_addr[0], ba = bar_addr[0];
 #pragma unroll
                 for (int s = 1; s < NBUF; s++) if ((int)(seq_issue % NBUF) == s) { sa = slot_addr[s]; ba = bar_addr[s]; }
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t)GSTRIDE + tbytes) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"((uint32_t)GSTRIDE) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(sa), "l"(p.st.grid + ej * GSTRIDE), "r"((uint32_t)GSTRIDE), "r"(ba) : "memory");
-                if (tbytes)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(sa + (uint32_t)GSTRIDE), "l"(p.st.tlist + ej * cap), "r"(tbytes), "r"(ba) : "memory");
             }
             seq_issue++;
         };
@@ -444,6 +439,11 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 const int64_t ej = env_of(j);
                 const bool ev = (em >> j) & 1u, hs = (hm >> j) & 1u;
                 Slot &sl = ws.slot[seq_cons % NBUF];
+                // the task's rectangles (16-byte header of its block list, one broadcast load): asked for before the
+                // wait so that the latency hides behind the grid copy and the observation write
+                const uint16_t *trow = p.st.tlist + ej * cap;
+                int4 rc = make_int4(0, 0, 0, 0);
+                if (ev) rc = __ldg(reinterpret_cast<const int4 *>(trow));
                 mbar_wait(&ws.bar[seq_cons % NBUF], (seq_cons / NBUF) & 1u);
                 if (patch) {  // the copy may have raced with this step's edit of the same env
                     const int ec = __shfl_sync(0xffffffffu, edit_cell, j);
@@ -454,8 +454,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
                 if (obs_on) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
                 if (ev) {
                     const int nb = __shfl_sync(0xffffffffu, nblk, j);
-                    const int4 rc = *reinterpret_cast<const int4 *>(sl.trow);
-                    const uint16_t *tl = nb <= TL_PRE ? sl.trow + TL_HDR : p.st.tlist + ej * cap + TL_HDR;
+                    const uint16_t *tl = trow + TL_HDR;
                     int r;
                     if (single_shift_rects(rc, 4)) {  // zone-spanning target: one shift per rotation, compare bytes
                         auto each = [&](auto f) {
@@ -489,7 +488,6 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : C
             // state was advanced by the physics launch: wrong_placement (task.py:111) is in w7
             // an all-zero difference grid (dsize == 0) scores 0 without looking: no target cell can equal 0
             const unsigned em = __ballot_sync(0xffffffffu, valid && nblk > 0 && dsize != 0 && (every_step || w[7] != 0));
-            need_tlist = em;
             ring_start(em | (grid_obs ? __ballot_sync(0xffffffffu, valid) : 0u));
             ring_drain(grid_obs, em, false, true);
         } else {
@@ -647,7 +645,9 @@ __device__ __forceinline__ uint32_t sample_draw(uint64_t seed, int64_t task, uin
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
     x ^= x >> 31;
-    return (uint32_t)(((x >> 32) * (uint64_t)range) >> 32);
+    // ((x >> 32) * range) >> 32 as a 32-bit multiply-high. (Written as a 64-bit product, ptxas 12.9 drops the whole
+    // hash chain of block_x in the max_blocks == 1 loop -- every level then lands at x = 0; caught by the oracle.)
+    return __umulhi((uint32_t)(x >> 32), range);
 }
 
 __global__ void __launch_bounds__(128) k_sample_tasks(int8_t *out, int64_t m, iglu_random_task_spec spec,
@@ -766,8 +766,8 @@ __global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st
         }
     }
     __syncwarp();
-    const Staged<true> G{ws.grid, 0}, I{ws.init, 0};
-    const int size = __reduce_add_sync(0xffffffffu, count_nonzero_cells(G, lane));
+    uint32_t nzs[12];
+    const int size = row_scan(ws.grid, 0, nullptr, lane, nzs).total;
     int goal = sg.state[0 * n + e], prev = sg.state[1 * n + e], max_int = sg.state[2 * n + e];
     auto eval = [&](const uint32_t *x, int row) {   // Task(stage `row`).maximal_intersection(x)
         const uint16_t *tl = sg.tlist + (int64_t)row * cap;
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st
         prev = nstart;
     };
     const bool fresh = st.istate[4 * n + e] == 1;   // first step of an episode: Subtasks.reset() happened in env.reset()
-    const int nstart = (fresh || sg.progressive) ? __reduce_add_sync(0xffffffffu, count_nonzero_cells(I, lane)) : 0;
+    const int nstart = (fresh || sg.progressive) ? row_scan(ws.init, 0, nullptr, lane, nzs).total : 0;
     if (fresh) {
         const int64_t r = task_row ? task_row[e] : e;
         goal = sg.stage_of ? sg.stage_of[r] : (int)r;
@@ -809,22 +809,20 @@ __global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st
 
 // ------------------------------------------------------------------ stateless reward sweep
 // Task(target, full_grid, invariant).maximal_intersection(grid) per pair (BASELINE config 4). One warp per pair.
-// The rows of the dense [count][stride] arrays are brought into shared memory by TMA bulk copies of the 16-byte
-// aligned window around each row (a granule that holds a valid byte lies in the same page: nothing outside the
-// caller's pages is touched), double buffered per warp so that pair i + 1 arrives while pair i is evaluated; the
-// consumers read the cells at their byte offset inside the window (Staged<false>), or directly when the caller's
-// rows are 16-byte aligned (stride 1104, the env state layout: Staged<true>). No block list is built: the target's
-// blocks register for the vote straight from the staged target grid.
-constexpr int PBUF = GSTRIDE + 32;   // window: <= 15 bytes before the row + 1089 cells, rounded to 16, + over-read word
+// The rows of the [count][stride] arrays are brought into shared memory by TMA bulk copies of the 16-byte aligned
+// window around each row (a granule that holds a valid byte lies in the same page: nothing outside the caller's
+// pages is touched), double buffered per warp so that pair i + 1 arrives while pair i is evaluated. The consumers
+// take the byte offset of cell 0 inside the window (iglu_reward.cuh, compaction), so neither a realignment pass nor
+// funnel shifts are needed; rows in the env state layout (stride 1104, 16-byte aligned) have offset 0.
 struct __align__(16) PairScratch {
-    uint32_t grid[2][PBUF / 4];
-    uint32_t tgt[2][PBUF / 4];
+    uint32_t grid[2][GSTRIDE / 4];
+    uint32_t tgt[2][GSTRIDE / 4];
     EvalScratch es;
-    uint16_t tkey[32];               // key of the target block registered in slot t of the current pass
+    uint16_t tl[32];                 // target blocks of the current pass: cell | code << 11
     unsigned long long bar[2];
 };
 
-template <bool WANT_KEY, bool ALIGNED>
+template <bool WANT_KEY>
 __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
                                                                      const int8_t *__restrict__ fulls,
@@ -845,14 +843,12 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
     }
     __syncthreads();
     const int64_t step = (int64_t)gridDim.x * MI_WARPS;
-    auto issue = [&](int64_t pr, int b) {   // lane 0: both rows of pair `pr` -> buffer b
-        const uintptr_t ga = reinterpret_cast<uintptr_t>(grids + pr * gstride);
-        const uintptr_t ta = reinterpret_cast<uintptr_t>(targets + pr * tstride);
-        const uint32_t gbytes = ALIGNED ? (uint32_t)GSTRIDE : (uint32_t)(((ga & 15) + CELLS + 15) & ~(uintptr_t)15);
-        const uint32_t tbytes = ALIGNED ? (uint32_t)GSTRIDE : (uint32_t)(((ta & 15) + CELLS + 15) & ~(uintptr_t)15);
-        mbar_expect_tx(&ps.bar[b], gbytes + tbytes);
-        tma_load(ps.grid[b], reinterpret_cast<const void *>(ga & ~(uintptr_t)15), gbytes, &ps.bar[b]);
-        tma_load(ps.tgt[b], reinterpret_cast<const void *>(ta & ~(uintptr_t)15), tbytes, &ps.bar[b]);
+    auto issue = [&](int64_t pr, int b) {   // lane 0: the aligned windows around both rows of pair `pr` -> buffer b
+        const uintptr_t ga = reinterpret_cast<uintptr_t>(grids + pr * gstride) & ~(uintptr_t)15;
+        const uintptr_t ta = reinterpret_cast<uintptr_t>(targets + pr * tstride) & ~(uintptr_t)15;
+        mbar_expect_tx(&ps.bar[b], 2u * GSTRIDE);
+        tma_load(ps.grid[b], reinterpret_cast<const void *>(ga), GSTRIDE, &ps.bar[b]);
+        tma_load(ps.tgt[b], reinterpret_cast<const void *>(ta), GSTRIDE, &ps.bar[b]);
     };
     int64_t pr = (int64_t)blockIdx.x * MI_WARPS + wid;
     if (pr < count && lane == 0) issue(pr, 0);
@@ -860,71 +856,78 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         const int b = it & 1;
         if (pr + step < count && lane == 0) issue(pr + step, b ^ 1);   // its last readers finished an iteration ago
         mbar_wait(&ps.bar[b], (it >> 1) & 1u);
-        const int goff = ALIGNED ? 0 : (int)(reinterpret_cast<uintptr_t>(grids + pr * gstride) & 15);
-        const int toff = ALIGNED ? 0 : (int)(reinterpret_cast<uintptr_t>(targets + pr * tstride) & 15);
-        const Staged<ALIGNED> G{ps.grid[b] + (goff >> 2), 8 * (goff & 3)};
-        const Staged<ALIGNED> T{ps.tgt[b] + (toff >> 2), 8 * (toff & 3)};
-        // ---- target: block count per lane (slots for the vote passes) and bounding box ----
-        int cnt = 0, x0 = 10, x1 = 0, z0 = 10, z1 = 0;
-        for_each_nonzero_cell(T, nullptr, lane, [&](int c, int, int) {
-            const int xz = lut[c] & 0xFFF, x = (xz * 2979) >> 16, z = xz - HROW * x;   // x = xz / 22 for xz <= 230
+        const int goff = (int)(reinterpret_cast<uintptr_t>(grids + pr * gstride) & 15);
+        const int toff = (int)(reinterpret_cast<uintptr_t>(targets + pr * tstride) & 15);
+        const uint32_t *G = ps.grid[b], *T = ps.tgt[b];
+        // ---- target: compact its blocks (the first 32 stay in ps.tl), bounding box ----
+        uint32_t tnz[12];
+        const RowScan ts = row_scan(T, toff, nullptr, lane, tnz);
+        const int nout = ts.total;
+        row_emit(T, toff, nullptr, lane, tnz, ts, 0, 32, ps.tl);
+        __syncwarp();
+        int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+        auto grow = [&](int cell) {
+            const int l = lut[cell], x = lut_x(l), z = (l & 0xFF) - HROW * x;
             x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-            cnt++;
-        });
-        int pos = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, pos, d);
-            if (lane >= d) pos += o;
-        }
-        const int nout = __shfl_sync(0xffffffffu, pos, 31);
-        pos -= cnt;   // first slot of this lane's blocks
+        };
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
         if (invariant) {
             if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid (rare: read straight from global)
-                x0 = 10; x1 = 0; z0 = 10; z1 = 0;
                 const int8_t *f = fulls + pr * fstride;
                 for (int c = lane; c < CELLS; c += 32)
-                    if (f[c] != 0) {
-                        const int xz = lut[c] & 0xFFF, x = (xz * 2979) >> 16, z = xz - HROW * x;
-                        x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-                    }
+                    if (f[c] != 0) grow(c);
+            } else {
+                if (lane < min(nout, 32)) grow(ps.tl[lane] & 0x7FF);
+                for (int c0 = 32; c0 < nout; c0 += 32) {   // more than 32 blocks: walk the rest once for the box
+                    __syncwarp();
+                    uint32_t nz2[12];
+                    row_masks(T, toff, nullptr, lane, nz2);
+                    row_emit(T, toff, nullptr, lane, nz2, ts, c0, 32, ps.tl);
+                    __syncwarp();
+                    if (c0 + lane < nout) grow(ps.tl[lane] & 0x7FF);
+                }
             }
             x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
             z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
             rc = rects_from_bbox(x0, x1, z0, z1);
             n_rot = 4;
         }
+        int tl_at = nout > 32 && invariant && !fulls ? ((nout - 1) & ~31) : 0;   // which pass ps.tl holds right now
+        auto load_pass = [&](int c0) {   // target blocks [c0, c0 + 32) -> ps.tl
+            if (tl_at != c0) {
+                __syncwarp();
+                uint32_t nz2[12];
+                row_masks(T, toff, nullptr, lane, nz2);
+                row_emit(T, toff, nullptr, lane, nz2, ts, c0, 32, ps.tl);
+                tl_at = c0;
+            }
+            __syncwarp();
+        };
         int key = -1, best;
         if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
             auto each = [&](auto f) {
-                for_each_nonzero_cell(T, nullptr, lane, [&](int c, int tv, int) {
-                    const int l = lut[c], xz = l & 0xFFF, x = (xz * 2979) >> 16;
-                    f(l >> 12, x, xz - HROW * x, code_of(tv));
-                });
+                for (int c0 = 0; c0 < nout; c0 += 32) {
+                    load_pass(c0);
+                    if (c0 + lane < nout) {
+                        const int e = ps.tl[lane], l = lut[e & 0x7FF], x = lut_x(l);
+                        f((l >> 8) / NCLS, x, (l & 0xFF) - HROW * x, e >> 11);
+                    }
+                }
             };
-            best = eval_single_shift<WANT_KEY>(G.bytes(), nullptr, each, rc, n_rot, &key);
+            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(G) + goff, nullptr, each, rc, n_rot, &key);
         } else {
-            auto reg = [&](int c0) {      // this lane's blocks whose slot falls into [c0, c0 + 32)
-                if (pos < c0 + 32 && pos + cnt > c0) {
-                    int slot = pos;
-                    for_each_nonzero_cell(T, nullptr, lane, [&](int c, int tv, int) {
-                        const int t = slot++ - c0;
-                        if ((unsigned)t < 32u) {
-                            const int l = lut[c], xz = l & 0xFFF, x = (xz * 2979) >> 16;
-                            ps.tkey[t] = (uint16_t)register_target(ps.es, t, l >> 12, x, xz - HROW * x, code_of(tv));
-                        }
-                    });
-                }
-            };
-            auto unreg = [&](int c0) {
+            int mykey = -1;
+            auto reg = [&](int c0) {
+                load_pass(c0);
+                mykey = -1;
                 if (c0 + lane < nout) {
-                    const uint16_t k = ps.tkey[lane];
-                    if (k != 0xFFFFu) ps.es.kmask[k] = 0u;
+                    const int e = ps.tl[lane], l = lut[e & 0x7FF], x = lut_x(l);
+                    mykey = register_target(ps.es, lane, l >> 8, x, (l & 0xFF) - HROW * x, e >> 11);
                 }
             };
-            best = eval_votes<WANT_KEY, ALIGNED>(ps.es, G, nullptr, lut, nout, reg, unreg, rc, n_rot, lane, &key);
+            auto unreg = [&](int) { if (mykey >= 0) ps.es.kmask[mykey] = 0u; };
+            best = eval_votes<WANT_KEY>(ps.es, G, goff, nullptr, lut, nout, reg, unreg, rc, n_rot, lane, &key);
         }
         if (lane == 0) {
             out[pr] = best;
@@ -971,7 +974,7 @@ extern "C" const char *iglu_strerror(int status) {
 extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!cfg || !out) return IGLU_ERR_INVALID_ARG;
     if (cfg->action_space < 0 || cfg->action_space > 2) return IGLU_ERR_INVALID_ARG;
-    if (cfg->tlist_cap < TL_HDR + TL_PRE || cfg->tlist_cap > IGLU_TLIST_ROW_MAX || (cfg->tlist_cap & 7))
+    if (cfg->tlist_cap < TL_HDR + 64 || cfg->tlist_cap > IGLU_TLIST_ROW_MAX || (cfg->tlist_cap & 7))
         return IGLU_ERR_INVALID_ARG;
     iglu_ctx *c = new iglu_ctx();
     c->cfg = *cfg;
@@ -1146,7 +1149,7 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     const int64_t groups_a = (n + 31) / 32;
     k_step<KIND, 1><<<(unsigned)((groups_a + StepCfg<1>::WPC - 1) / StepCfg<1>::WPC), StepCfg<1>::WPC * 32, 0, s>>>(p);
     // launch 2: observe, persistent, chunk = ceil(n / resident warps) envs per warp (<= 32)
-    const int64_t resident_ctas = (int64_t)ctx->num_sms * CTAS_PER_SM;
+    const int64_t resident_ctas = (int64_t)ctx->num_sms * IGLU_OBS_CTAS;
     const int64_t warp_slots = resident_ctas * StepCfg<2>::WPC;
     int64_t chunk = (n + warp_slots - 1) / warp_slots;
     // dynamic hand-out pays when every env has ring work in this launch (measured: profiles/r01_launch_policy.txt);
@@ -1311,15 +1314,15 @@ extern "C" int iglu_fetch_env_host(iglu_ctx *ctx, const iglu_state *st, const ig
     return check(cudaStreamSynchronize(s));
 }
 
-template <bool WANT_KEY, bool ALIGNED>
+template <bool WANT_KEY>
 static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *fulls, int64_t gs, int64_t ts, int64_t fs,
                      int invariant, int32_t *out, int32_t *argmax, int64_t count, unsigned grid, size_t smem,
                      cudaStream_t s) {
-    int rc = check(cudaFuncSetAttribute(k_max_intersection<WANT_KEY, ALIGNED>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = check(cudaFuncSetAttribute(k_max_intersection<WANT_KEY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
     if (rc) return rc;
-    k_max_intersection<WANT_KEY, ALIGNED><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, gs, ts, fs, invariant,
-                                                                           out, argmax, count);
+    k_max_intersection<WANT_KEY><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, gs, ts, fs, invariant, out,
+                                                                  argmax, count);
     return check(cudaPeekAtLastError());
 }
 
@@ -1337,18 +1340,10 @@ extern "C" int iglu_max_intersection_strided(const int8_t *grids, int64_t grid_s
     const int64_t resident = (int64_t)sms * MI_CTAS;
     const unsigned grid = (unsigned)(ctas < resident ? ctas : resident);
     cudaStream_t s = (cudaStream_t)stream;
-    // rows that are 16-byte aligned and at least GSTRIDE long (the env state layout) are copied as they are
-    auto al = [](const int8_t *p, int64_t st) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (st & 15) == 0 && st >= GSTRIDE; };
-    const bool aligned = al(grids, grid_stride) && al(targets, target_stride);
-    if (aligned)
-        return argmax ? launch_mi<true, true>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
-                                              out, argmax, count, grid, smem, s)
-                      : launch_mi<false, true>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
-                                               out, argmax, count, grid, smem, s);
-    return argmax ? launch_mi<true, false>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
-                                           out, argmax, count, grid, smem, s)
-                  : launch_mi<false, false>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant,
-                                            out, argmax, count, grid, smem, s);
+    return argmax ? launch_mi<true>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant, out,
+                                    argmax, count, grid, smem, s)
+                  : launch_mi<false>(grids, targets, fulls, grid_stride, target_stride, full_stride, invariant, out,
+                                     argmax, count, grid, smem, s);
 }
 
 extern "C" int iglu_max_intersection(const int8_t *grids, const int8_t *targets, const int8_t *fulls,

@@ -16,12 +16,14 @@
 // answer is the maximum of the table over the admissible rectangles. Work is proportional to the number of
 // same-(level, class) block pairs -- a few dozen for real structures -- and it needs no clipping case: a target
 // cell that a shift moves outside the zone simply has no grid partner.
+//   * the staged int8 row is COMPACTED first: every lane reads its share with 16-byte shared-memory loads, finds
+//     its non-zero bytes with three logic operations per word, a shuffle scan gives it its slots, and the blocks
+//     land in a short list (cell | class << 11) -- everything after that runs in lock step over list entries
+//     instead of diverging over bytes;
 //   * matching pairs are found through a per-(level, class) bit mask over the (<= 32 per pass) target blocks:
-//     lane t registers its block with one shared-memory atomicOr; a lane that holds a grid block reads the mask
-//     of its key and walks the set bits;
-//   * the grid is traversed sparsely: lane L owns the words L, L + 32, ... of the staged int8 grid and only
-//     visits non-zero words / bytes; (y, 22 xg + zg) of a cell comes from a 1089-entry table in shared memory;
-//   * votes are shared-memory atomic adds of 1 << 16 (idx & 1) on word idx >> 1; the table is cleared with
+//     lane t registers target block t with one shared-memory atomicOr; the lane that holds a grid block reads the
+//     mask of its key and walks the set bits;
+//   * votes are shared-memory reductions of 1 << 16 (idx & 1) on word idx >> 1; the table is cleared with
 //     16-byte stores before every evaluation; the scan runs over (rotation, dx) rows with __reduce_max_sync at
 //     the end (and the reference's first-max tie-break encoded in the key when argmax is wanted).
 // Tasks whose every rotation admits exactly ONE shift (zone-spanning targets, invariant=False) keep the direct
@@ -34,90 +36,118 @@ namespace iglu {
 constexpr int HROW = 22;                         // 16-bit counters per (rotation, dx) row: 21 dz values + 1 pad
 constexpr int HROT = 21 * HROW;                  // counters per rotation (462)
 constexpr int HIST_WORDS = 4 * HROT / 2;         // 924 words = 3696 bytes
-constexpr int NKEY = 144;                        // (level y) * 16 + class code
+constexpr int NCLS = 13;                         // class of a code: 1..6 colours, 7..12 the values -6..-1 (0 unused)
+constexpr int NKEY = 120;                        // 9 levels x 13 classes = 117 key masks, padded to 16 bytes
 constexpr int CELL_LUT_N = 1092;                 // 1089 cells (+ pad to a multiple of 4)
+constexpr int GL_CAP = 64;                       // grid blocks per voting round
+constexpr int ROW_CHUNKS = GSTRIDE / 16;         // a staged row / window is 69 sixteen-byte chunks
 
 // Grid / target values are differences of colour ids, i.e. -6..6 (env.py:230, 290). code_of() maps a value
-// to a 4-bit code (value & 15; 8 = "not a valid value", never matches).
+// to a 4-bit code (value & 15; 8 = "not a valid value", never matches), class_of() a valid code to 1..12.
 __device__ __forceinline__ int code_of(int v) { return (v >= -6 && v <= 6) ? (v & 15) : 8; }
+__device__ __forceinline__ int class_of(int code) { return code < 7 ? code : code - 3; }
 
 // Per-warp scratch for one evaluation.
 struct __align__(16) EvalScratch {
     uint32_t hist[HIST_WORDS];   // vote counters, idx16 = k * HROT + (dx + 10) * HROW + (dz + 10)
-    uint32_t kmask[NKEY];        // per (y, class): bit t set when target block t of the current pass has that key
+    uint32_t kmask[NKEY];        // per (level, class): bit t set when target block t of the current pass has that key
                                  // (all zero between evaluations: every pass clears what it set)
     uint2 tb[32];                // per target block of the pass: the four vote bases (16 bits each)
+    uint16_t glist[GL_CAP];      // grid blocks of the current round: cell | code << 11
 };
 
-// cell index -> y << 12 | (HROW * x + z); built once per CTA
+// cell index -> (13 * y) << 8 | (HROW * x + z); built once per CTA
 __device__ __forceinline__ void build_cell_lut(uint16_t *lut, int tid, int nthreads) {
     for (int c = tid; c < CELL_LUT_N; c += nthreads) {
         const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
-        lut[c] = (uint16_t)(c < 1089 ? ((y << 12) | (HROW * x + z)) : 0);
+        lut[c] = (uint16_t)(c < 1089 ? ((NCLS * y) << 8 | (HROW * x + z)) : 0);
     }
 }
+__device__ __forceinline__ int lut_x(int l) { return ((l & 0xFF) * 2979) >> 16; }   // (22 x + z) / 22 for values <= 230
 
-// A staged int8 grid in shared memory. ALIGNED: 16-byte aligned copy of a GSTRIDE-byte row (the env state layout).
-// Otherwise the 1089 cells start at an arbitrary byte offset of a 16-byte aligned window (the stateless sweep brings
-// the unaligned rows of a dense [count][1089] array in with aligned TMA bulk copies): a logical word is then two
-// aligned shared-memory words and a funnel shift, and bytes past cell 1088 are masked to zero.
-template <bool ALIGNED>
-struct Staged {
-    const uint32_t *w;   // word holding the first cell
-    int sh;              // 8 * (byte offset of the first cell inside that word)
-    __device__ __forceinline__ uint32_t word(int i, bool last_q) const {
-        uint32_t v = ALIGNED ? w[i] : __funnelshift_r(w[i], w[i + 1], sh);
-        if (last_q && i >= 272) v = i == 272 ? (v & 0xFFu) : 0u;   // cell 1088 | bytes that are not cells
-        return v;
-    }
-    __device__ __forceinline__ const int8_t *bytes() const {
-        return reinterpret_cast<const int8_t *>(w) + (sh >> 3);
-    }
+// ---- compaction of a staged row -----------------------------------------------------------------------------------
+// `win` is a 16-byte aligned shared-memory window of GSTRIDE bytes whose byte `off` (0..15) is cell 0: off = 0 for
+// rows in the env state layout, the source address & 15 for the unaligned rows of a dense [count][1089] array that
+// the stateless sweep brings in with aligned TMA bulk copies. `init` (nullptr, or a 16-byte aligned row in the env
+// layout in global / shared memory; needs off == 0) is subtracted cell-wise: a "block" is a cell whose value differs
+// from init's. Lane L owns the chunks L, L + 32, L + 64; window bytes that are not cells (before `off`, from
+// off + 1089 on) are masked out.
+struct RowScan {
+    int pos;     // slot of this lane's first block
+    int total;   // blocks in the row
 };
 
-// Sparse traversal of a staged grid. Lane L owns the 32-bit words L, L + 32, ..., L + 256 (consecutive lanes read
-// consecutive words: conflict free; a clump of blocks spreads over many lanes). Grids hold a few dozen blocks, so
-// each lane first builds a 9-bit mask of its non-zero words and then loops over the set words / non-zero bytes
-// only:  f(cell, value, sub_value).  `sub` (may be nullptr; 16-byte aligned row, shared or global) is subtracted
-// cell-wise. Pad bytes (cells >= 1089) are zero in both. No ordering guarantee.
-template <bool ALIGNED, class F>
-__device__ __forceinline__ void for_each_nonzero_cell(const Staged<ALIGNED> g, const uint32_t *sub, int lane, F f) {
-    unsigned wm = 0u;
-#pragma unroll
-    for (int q = 0; q < 9; q++) {
-        const int i = lane + 32 * q;
-        uint32_t x = 0u;
-        if (q < 8 || i < GSTRIDE / 4) {
-            x = g.word(i, q == 8);
-            if (sub) x ^= sub[i];
-        }
-        if (x) wm |= 1u << q;
-    }
-    while (wm) {
-        const int q = __ffs(wm) - 1;
-        wm &= wm - 1;
-        const int i = lane + 32 * q;
-        const uint32_t gw = g.word(i, true), sw = sub ? sub[i] : 0u;
-        uint32_t x = gw ^ sw;
-        while (x) {
-            const int j = (__ffs(x) - 1) >> 3;
-            x &= ~(0xFFu << (8 * j));
-            f(4 * i + j, (int)(int8_t)(gw >> (8 * j)), (int)(int8_t)(sw >> (8 * j)));
-        }
-    }
-}
+__device__ __forceinline__ uint32_t keep_from(int n) { return n <= 0 ? 0xFFFFFFFFu : (n >= 4 ? 0u : 0xFFFFFFFFu << (8 * n)); }
+__device__ __forceinline__ uint32_t keep_below(int n) { return n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ~(0xFFFFFFFFu << (8 * n))); }
 
-// number of non-zero cells among the words lane L owns
-template <bool ALIGNED>
-__device__ __forceinline__ int count_nonzero_cells(const Staged<ALIGNED> g, int lane) {
+// The non-zero-byte masks (bit 8 j + 7 <-> byte j) of the twelve words this lane owns; returns their block count.
+__device__ __forceinline__ int row_masks(const uint32_t *win, int off, const int8_t *init, int lane, uint32_t (&nz)[12]) {
+    const int4 *w4 = reinterpret_cast<const int4 *>(win);
+    const int4 *i4 = reinterpret_cast<const int4 *>(init);
     int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 9; q++) {
-        const int i = lane + 32 * q;
-        const uint32_t x = (q < 8 || i < GSTRIDE / 4) ? g.word(i, q == 8) : 0u;
-        cnt += __popc((x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u);
+    for (int q = 0; q < 3; q++) {
+        const int c = lane + 32 * q;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (q < 2 || c < ROW_CHUNKS) {
+            v = w4[c];
+            if (init) {
+                const int4 s = i4[c];
+                v.x ^= s.x; v.y ^= s.y; v.z ^= s.z; v.w ^= s.w;
+            }
+        }
+        uint32_t x[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        const int lo = off - 16 * c, hi = lo + CELLS;   // bytes [lo, hi) of this chunk are cells
+        if (lo > 0 || hi < 16) {                        // first / last chunk of the row only
+#pragma unroll
+            for (int k = 0; k < 4; k++) x[k] &= keep_from(lo - 4 * k) & keep_below(hi - 4 * k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t m = (x[k] | ((x[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+            nz[4 * q + k] = m;
+            cnt += __popc(m);
+        }
     }
     return cnt;
+}
+
+// Masks (left in nz for a first row_emit) + exclusive scan of the per-lane block counts.
+__device__ __forceinline__ RowScan row_scan(const uint32_t *win, int off, const int8_t *init, int lane, uint32_t (&nz)[12]) {
+    const int cnt = row_masks(win, off, init, lane, nz);
+    int pos = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, pos, d);
+        if (lane >= d) pos += o;
+    }
+    RowScan rs;
+    rs.total = __shfl_sync(0xffffffffu, pos, 31);
+    rs.pos = pos - cnt;
+    return rs;
+}
+
+// Writes the blocks with slots [r0, r0 + cap) into list[0 .. cap) as cell | code << 11 (code 8 = value that is no
+// colour difference). The caller synchronises the warp before reading the list.
+__device__ __forceinline__ void row_emit(const uint32_t *win, int off, const int8_t *init, int lane,
+                                         const uint32_t (&nz)[12], RowScan rs, int r0, int cap, uint16_t *list) {
+    if (rs.pos >= r0 + cap) return;   // all of this lane's blocks come after the window
+    const int8_t *w8 = reinterpret_cast<const int8_t *>(win);
+    int slot = rs.pos - r0;
+#pragma unroll
+    for (int q = 0; q < 12; q++) {
+        uint32_t m = nz[q];
+        while (m) {
+            const int j = (__ffs(m) - 1) >> 3;
+            m &= m - 1;
+            if ((unsigned)slot < (unsigned)cap) {
+                const int p = 16 * (lane + 32 * (q >> 2)) + 4 * (q & 3) + j;   // window byte
+                const int d = init ? (int)w8[p] - (int)init[p] : (int)w8[p];
+                list[slot] = (uint16_t)((p - off) | (code_of(d) << 11));
+            }
+            slot++;
+        }
+    }
 }
 
 // Admissible-shift rectangles of the four rotations from the rotation-0 bounding box of the non-zero
@@ -141,9 +171,19 @@ __device__ __forceinline__ int4 rects_identity() { return make_int4(0x01000100, 
 
 __device__ __forceinline__ int rect_byte(int w, int i) { return (int)(int8_t)((unsigned)w >> (8 * i)); }
 
-// One target block of the current pass: slot t (0..31) gets its four vote bases and its (level, class) key mask bit.
-// Returns the key (for un-registering), or -1 for a value that is no colour difference (matches nothing).
-__device__ __forceinline__ int register_target(EvalScratch &es, int t, int y, int x, int z, int code) {
+// ---- the vote ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void hist_clear(EvalScratch &es, int lane) {
+    int4 *hz = reinterpret_cast<int4 *>(es.hist);
+#pragma unroll
+    for (int it = 0; it < (HIST_WORDS / 4 + 31) / 32; it++) {
+        const int q = lane + 32 * it;
+        if (q < HIST_WORDS / 4) hz[q] = make_int4(0, 0, 0, 0);
+    }
+}
+
+// Target block (y13 = 13 * level, x, z, code) becomes slot t (0..31) of the current pass: its four vote bases and
+// its (level, class) key mask bit. Returns the key (for un-registering), or -1 for a code that matches nothing.
+__device__ __forceinline__ int register_target(EvalScratch &es, int t, int y13, int x, int z, int code) {
     if (code == 8) return -1;
     // vote base of rotation k: k * HROT + (x_k + 10) * HROW + (z_k + 10) with the rotations of task.py:52-53
     const uint32_t b0 = 0 * HROT + (x + 10) * HROW + (z + 10);                 // (x, z)
@@ -151,70 +191,45 @@ __device__ __forceinline__ int register_target(EvalScratch &es, int t, int y, in
     const uint32_t b2 = 2 * HROT + (20 - x) * HROW + (20 - z);                 // (10 - x, 10 - z)
     const uint32_t b3 = 3 * HROT + (20 - z) * HROW + (x + 10);                 // (10 - z, x)
     es.tb[t] = make_uint2(b0 | (b1 << 16), b2 | (b3 << 16));
-    const int key = (y << 4) | code;
+    const int key = y13 + class_of(code);
     atomicOr(&es.kmask[key], 1u << t);
     return key;
 }
 
-// Evaluate max intersection of the staged (difference) grid with a set of target blocks.
-//   grid  : staged int8 grid (shared memory)
-//   init  : the env's starting grid (16-byte aligned row, global or shared memory) subtracted cell-wise, or nullptr
-//   lut   : build_cell_lut table (shared memory)
-//   nblk  : number of target blocks; they are handed over in passes of 32: reg(c0) makes every lane register the
-//           blocks it holds among slots [c0, c0 + 32) (register_target with t = slot - c0) and unreg(c0) makes it
-//           clear es.kmask[key] for each of them again
-//   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
-// Returns (warp-uniform) best count; if WANT_KEY also the first (rot, dx, dz) reaching it in the
-// reference's iteration order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if best == 0.
-template <bool WANT_KEY, bool ALIGNED, class RegF, class UnregF>
-__device__ __forceinline__ int eval_votes(EvalScratch &es, const Staged<ALIGNED> grid, const int8_t *init,
-                                          const uint16_t *__restrict__ lut, int nblk, RegF reg, UnregF unreg,
-                                          int4 rc, int n_rot, int lane, int *key_out) {
-    if (WANT_KEY) *key_out = -1;
-    if (nblk == 0) return 0;
-    // ---- clear the vote table ----
-    {
-        int4 *hz = reinterpret_cast<int4 *>(es.hist);
-#pragma unroll
-        for (int it = 0; it < (HIST_WORDS / 4 + 31) / 32; it++) {
-            const int q = lane + 32 * it;
-            if (q < HIST_WORDS / 4) hz[q] = make_int4(0, 0, 0, 0);
+// The blocks glist[0 .. n) (lock step: lane i takes entries i, i + 32, ...) vote once per rotation with every
+// registered target block of their (level, class).
+__device__ __forceinline__ void vote_round(EvalScratch &es, const uint16_t *__restrict__ lut, int n, int n_rot, int lane) {
+    const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(es.hist);
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t it = es.glist[i];
+        const int code = it >> 11;
+        if (code == 8) continue;
+        const uint32_t l = lut[it & 0x7FFu];
+        unsigned m = es.kmask[(l >> 8) + class_of(code)];
+        const uint32_t gb = l & 0xFFu;
+        while (m) {
+            const int t = __ffs(m) - 1;
+            m &= m - 1;
+            const uint2 b = es.tb[t];
+            auto vote = [&](uint32_t v) {
+                asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_base + ((v >> 1) << 2)),
+                             "r"(1u << ((v & 1u) << 4)) : "memory");
+            };
+            vote((b.x & 0xFFFFu) - gb);
+            if (n_rot > 1) {
+                vote((b.x >> 16) - gb);
+                vote((b.y & 0xFFFFu) - gb);
+                vote((b.y >> 16) - gb);
+            }
         }
     }
-    const uint32_t *iw = reinterpret_cast<const uint32_t *>(init);
-    const uint32_t hist_base = (uint32_t)__cvta_generic_to_shared(es.hist);
-    for (int c0 = 0; c0 < nblk; c0 += 32) {
-        reg(c0);
-        __syncwarp();
-        // ---- every grid block votes once per rotation with each target block of its (level, class) ----
-        for_each_nonzero_cell(grid, iw, lane, [&](int cell, int gv, int sv) {
-            const int d = gv - sv;
-            if (d >= -6 && d <= 6) {  // other values are not colour differences and match nothing
-                const uint32_t l = lut[cell];
-                unsigned m = es.kmask[((l >> 12) << 4) | (d & 15)];
-                const uint32_t gb = l & 0xFFFu;
-                while (m) {
-                    const int t = __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint2 b = es.tb[t];
-                    auto vote = [&](uint32_t v) {
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(hist_base + ((v >> 1) << 2)),
-                                     "r"(1u << ((v & 1u) << 4)) : "memory");
-                    };
-                    vote((b.x & 0xFFFFu) - gb);
-                    if (n_rot > 1) {
-                        vote((b.x >> 16) - gb);
-                        vote((b.y & 0xFFFFu) - gb);
-                        vote((b.y >> 16) - gb);
-                    }
-                }
-            }
-        });
-        __syncwarp();
-        unreg(c0);   // leave the key masks all-zero for the next pass / evaluation
-        __syncwarp();
-    }
-    // ---- maximum over the admissible rectangles: one (rotation, dx) row per lane and pass ----
+}
+
+// Maximum of the vote table over the admissible rectangles: one (rotation, dx) row per lane and pass. Returns
+// (warp-uniform) the best count; if WANT_KEY also the first (rot, dx, dz) reaching it in the reference's iteration
+// order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if the best is 0.
+template <bool WANT_KEY>
+__device__ __forceinline__ int hist_max(EvalScratch &es, int4 rc, int n_rot, int lane, int *key_out) {
     const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
     const int n0 = (rw[0] >> 8) & 0x1F, n1 = n_rot > 1 ? (rw[1] >> 8) & 0x1F : 0;
     const int n2 = n_rot > 1 ? (rw[2] >> 8) & 0x1F : 0, n3 = n_rot > 1 ? (rw[3] >> 8) & 0x1F : 0;
@@ -243,30 +258,69 @@ __device__ __forceinline__ int eval_votes(EvalScratch &es, const Staged<ALIGNED>
     return best;
 }
 
+// Evaluate max intersection of a staged (difference) grid with a set of target blocks.
+//   win / off / init : the staged grid (see the compaction above)
+//   nblk  : number of target blocks; they are handed over in passes of 32: reg(c0) makes lane t register block
+//           c0 + t (register_target) and unreg(c0) makes it clear es.kmask[key] again
+//   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
+template <bool WANT_KEY, class RegF, class UnregF>
+__device__ __forceinline__ int eval_votes(EvalScratch &es, const uint32_t *win, int off, const int8_t *init,
+                                          const uint16_t *__restrict__ lut, int nblk, RegF reg, UnregF unreg,
+                                          int4 rc, int n_rot, int lane, int *key_out) {
+    if (WANT_KEY) *key_out = -1;
+    if (nblk == 0) return 0;
+    hist_clear(es, lane);
+    uint32_t nz[12];
+    const RowScan gs = row_scan(win, off, init, lane, nz);
+    if (gs.total == 0) { __syncwarp(); return 0; }
+    const bool one_round = gs.total <= GL_CAP;
+    if (one_round) row_emit(win, off, init, lane, nz, gs, 0, GL_CAP, es.glist);
+    for (int c0 = 0; c0 < nblk; c0 += 32) {
+        reg(c0);
+        __syncwarp();
+        if (one_round) {
+            vote_round(es, lut, gs.total, n_rot, lane);
+        } else {
+            for (int r0 = 0; r0 < gs.total; r0 += GL_CAP) {   // crowded grids: the masks are rebuilt per round
+                uint32_t nz2[12];
+                row_masks(win, off, init, lane, nz2);
+                row_emit(win, off, init, lane, nz2, gs, r0, GL_CAP, es.glist);
+                __syncwarp();
+                vote_round(es, lut, min(GL_CAP, gs.total - r0), n_rot, lane);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        unreg(c0);   // leave the key masks all-zero for the next pass / evaluation
+        __syncwarp();
+    }
+    return hist_max<WANT_KEY>(es, rc, n_rot, lane, key_out);
+}
+
 // The env path: the target blocks are a packed list (y | x<<4 | z<<8 | code<<12; shared or global memory) and lane t
-// registers entry c0 + t.
+// registers entry c0 + t; the grid is a row in the env layout (off = 0).
 template <bool WANT_KEY>
 __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                                      const uint16_t *__restrict__ lut,
                                                      const uint16_t *__restrict__ tlist, int nblk, int4 rc,
                                                      int n_rot, int lane, int *key_out) {
     int mykey = -1;
+    uint32_t e_next = lane < nblk ? tlist[lane] : 0u;   // fetched before the grid is compacted: the latency hides there
     auto reg = [&](int c0) {
         mykey = -1;
-        if (c0 + lane < nblk) {
-            const uint32_t e = tlist[c0 + lane];
-            mykey = register_target(es, lane, e & 15, (e >> 4) & 15, (e >> 8) & 15, e >> 12);
-        }
+        const uint32_t e = e_next;
+        if (c0 + 32 + lane < nblk) e_next = tlist[c0 + 32 + lane];
+        if (c0 + lane < nblk) mykey = register_target(es, lane, NCLS * (e & 15), (e >> 4) & 15, (e >> 8) & 15, e >> 12);
     };
     auto unreg = [&](int) { if (mykey >= 0) es.kmask[mykey] = 0u; };
-    return eval_votes<WANT_KEY, true>(es, Staged<true>{grid, 0}, init, lut, nblk, reg, unreg, rc, n_rot, lane, key_out);
+    return eval_votes<WANT_KEY>(es, grid, 0, init, lut, nblk, reg, unreg, rc, n_rot, lane, key_out);
 }
 
 // Direct evaluation for tasks whose every rotation admits exactly ONE shift (targets spanning the whole zone in
 // x and z, or invariant=False): per target block and rotation one byte of the staged grid is compared -- no
-// vote table. Lane L takes blocks L, L + 32, ...
-//   g8 : staged grid (shared memory, dense 1089 bytes); sub : starting grid to subtract cell-wise (global memory)
-//        or nullptr; rc / n_rot as for eval_votes
+// vote table.
+//   g8 : staged grid (shared memory, cell c at g8[c]); sub : starting grid to subtract cell-wise (global memory)
+//        or nullptr; for_each_target(f) calls f(y, x, z, code) for the target blocks this lane is responsible for
 __device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
     const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
     bool ok = true;
@@ -276,7 +330,6 @@ __device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
     return ok;
 }
 
-// for_each_target(f) calls f(y, x, z, code) for the target blocks this lane is responsible for.
 template <bool WANT_KEY, class ForEachT>
 __device__ __forceinline__ int eval_single_shift(const int8_t *g8, const int8_t *__restrict__ sub,
                                                  ForEachT for_each_target, int4 rc, int n_rot, int *key_out) {
