@@ -766,8 +766,7 @@ __global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st
         }
     }
     __syncwarp();
-    uint32_t nzs[12];
-    const int size = row_scan(ws.grid, 0, nullptr, lane, nzs).total;
+    const int size = count_blocks(ws.grid, 0, nullptr, lane);
     int goal = sg.state[0 * n + e], prev = sg.state[1 * n + e], max_int = sg.state[2 * n + e];
     auto eval = [&](const uint32_t *x, int row) {   // Task(stage `row`).maximal_intersection(x)
         const uint16_t *tl = sg.tlist + (int64_t)row * cap;
@@ -779,7 +778,7 @@ __global__ void __launch_bounds__(STAGED_WARPS * 32) k_staged_step(iglu_state st
         prev = nstart;
     };
     const bool fresh = st.istate[4 * n + e] == 1;   // first step of an episode: Subtasks.reset() happened in env.reset()
-    const int nstart = (fresh || sg.progressive) ? row_scan(ws.init, 0, nullptr, lane, nzs).total : 0;
+    const int nstart = (fresh || sg.progressive) ? count_blocks(ws.init, 0, nullptr, lane) : 0;
     if (fresh) {
         const int64_t r = task_row ? task_row[e] : e;
         goal = sg.stage_of ? sg.stage_of[r] : (int)r;
@@ -818,8 +817,42 @@ struct __align__(16) PairScratch {
     uint32_t grid[2][GSTRIDE / 4];
     uint32_t tgt[2][GSTRIDE / 4];
     EvalScratch es;
-    uint16_t tl[32];                 // target blocks of the current pass: cell | code << 11
+    uint16_t tl[GL_CAP];             // target blocks of the current round: cell | code << 11
+    uint16_t twl[WL_CAP];            // non-zero words of the target's current round
     unsigned long long bar[2];
+};
+
+// The target side of one pair for eval_votes: rounds of <= 32 non-zero words (<= 128 blocks) compacted on demand.
+struct WindowTargets {
+    PairScratch &ps;
+    const uint32_t *T;
+    const uint16_t *lut;
+    int toff, nwords, lane;
+    int twl_round, tl_round, ntl;
+    __device__ __forceinline__ WindowTargets(PairScratch &ps_, const uint32_t *T_, int toff_, const uint16_t *lut_, int nwords_,
+                                             int lane_)
+        : ps(ps_), T(T_), lut(lut_), toff(toff_), nwords(nwords_), lane(lane_), twl_round(0), tl_round(-1), ntl(0) {}
+    __device__ __forceinline__ bool empty() const { return nwords == 0; }
+    __device__ __forceinline__ int rounds() const { return (nwords + WL_CAP - 1) / WL_CAP; }
+    __device__ __forceinline__ int load(int r) {
+        if (tl_round != r) {
+            __syncwarp();   // the readers of ps.tl / ps.twl are done
+            if (twl_round != r) {
+                word_scan<false>(T, toff, nullptr, lane, WL_CAP * r, ps.twl, nullptr);
+                twl_round = r;
+            }
+            __syncwarp();
+            ntl = block_emit(T, toff, nullptr, lane, min(WL_CAP, nwords - WL_CAP * r), ps.twl, ps.tl);
+            tl_round = r;
+            __syncwarp();
+        }
+        return ntl;
+    }
+    __device__ __forceinline__ int reg(EvalScratch &es, int c0, int) const {
+        if (c0 + lane >= ntl) return -1;
+        const int e = ps.tl[c0 + lane], l = lut[e & 0x7FF], x = lut_x(l);
+        return register_target(es, lane, l >> 8, x, (l & 0xFF) - HROW * x, e >> 11);
+    }
 };
 
 template <bool WANT_KEY>
@@ -859,33 +892,24 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         const int goff = (int)(reinterpret_cast<uintptr_t>(grids + pr * gstride) & 15);
         const int toff = (int)(reinterpret_cast<uintptr_t>(targets + pr * tstride) & 15);
         const uint32_t *G = ps.grid[b], *T = ps.tgt[b];
-        // ---- target: compact its blocks (the first 32 stay in ps.tl), bounding box ----
-        uint32_t tnz[12];
-        const RowScan ts = row_scan(T, toff, nullptr, lane, tnz);
-        const int nout = ts.total;
-        row_emit(T, toff, nullptr, lane, tnz, ts, 0, 32, ps.tl);
-        __syncwarp();
-        int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
-        auto grow = [&](int cell) {
-            const int l = lut[cell], x = lut_x(l), z = (l & 0xFF) - HROW * x;
-            x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-        };
+        // ---- target: its non-zero words (first round in ps.twl), then blocks round by round ----
+        WindowTargets tg(ps, T, toff, lut, word_scan<false>(T, toff, nullptr, lane, 0, ps.twl, nullptr), lane);
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
-        if (invariant) {
-            if (fulls) {  // task.py:63-64: the admissible shifts come from full_grid (rare: read straight from global)
+        if (invariant) {  // bounding box of the target (or of full_grid: task.py:63-64) -> admissible rectangles
+            int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+            auto grow = [&](int cell) {
+                const int l = lut[cell], x = lut_x(l), z = (l & 0xFF) - HROW * x;
+                x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+            };
+            if (fulls) {  // rare: read straight from global memory
                 const int8_t *f = fulls + pr * fstride;
                 for (int c = lane; c < CELLS; c += 32)
                     if (f[c] != 0) grow(c);
             } else {
-                if (lane < min(nout, 32)) grow(ps.tl[lane] & 0x7FF);
-                for (int c0 = 32; c0 < nout; c0 += 32) {   // more than 32 blocks: walk the rest once for the box
-                    __syncwarp();
-                    uint32_t nz2[12];
-                    row_masks(T, toff, nullptr, lane, nz2);
-                    row_emit(T, toff, nullptr, lane, nz2, ts, c0, 32, ps.tl);
-                    __syncwarp();
-                    if (c0 + lane < nout) grow(ps.tl[lane] & 0x7FF);
+                for (int r = tg.rounds() - 1; r >= 0; r--) {   // backwards: round 0 stays loaded for the evaluation
+                    const int nt = tg.load(r);
+                    for (int i = lane; i < nt; i += 32) grow(ps.tl[i] & 0x7FF);
                 }
             }
             x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
@@ -893,41 +917,20 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             rc = rects_from_bbox(x0, x1, z0, z1);
             n_rot = 4;
         }
-        int tl_at = nout > 32 && invariant && !fulls ? ((nout - 1) & ~31) : 0;   // which pass ps.tl holds right now
-        auto load_pass = [&](int c0) {   // target blocks [c0, c0 + 32) -> ps.tl
-            if (tl_at != c0) {
-                __syncwarp();
-                uint32_t nz2[12];
-                row_masks(T, toff, nullptr, lane, nz2);
-                row_emit(T, toff, nullptr, lane, nz2, ts, c0, 32, ps.tl);
-                tl_at = c0;
-            }
-            __syncwarp();
-        };
         int key = -1, best;
         if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
             auto each = [&](auto f) {
-                for (int c0 = 0; c0 < nout; c0 += 32) {
-                    load_pass(c0);
-                    if (c0 + lane < nout) {
-                        const int e = ps.tl[lane], l = lut[e & 0x7FF], x = lut_x(l);
+                for (int r = 0; r < tg.rounds(); r++) {
+                    const int nt = tg.load(r);
+                    for (int i = lane; i < nt; i += 32) {
+                        const int e = ps.tl[i], l = lut[e & 0x7FF], x = lut_x(l);
                         f((l >> 8) / NCLS, x, (l & 0xFF) - HROW * x, e >> 11);
                     }
                 }
             };
             best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(G) + goff, nullptr, each, rc, n_rot, &key);
         } else {
-            int mykey = -1;
-            auto reg = [&](int c0) {
-                load_pass(c0);
-                mykey = -1;
-                if (c0 + lane < nout) {
-                    const int e = ps.tl[lane], l = lut[e & 0x7FF], x = lut_x(l);
-                    mykey = register_target(ps.es, lane, l >> 8, x, (l & 0xFF) - HROW * x, e >> 11);
-                }
-            };
-            auto unreg = [&](int) { if (mykey >= 0) ps.es.kmask[mykey] = 0u; };
-            best = eval_votes<WANT_KEY>(ps.es, G, goff, nullptr, lut, nout, reg, unreg, rc, n_rot, lane, &key);
+            best = eval_votes<WANT_KEY>(ps.es, G, goff, nullptr, lut, tg, rc, n_rot, lane, &key);
         }
         if (lane == 0) {
             out[pr] = best;

@@ -39,8 +39,9 @@ constexpr int HIST_WORDS = 4 * HROT / 2;         // 924 words = 3696 bytes
 constexpr int NCLS = 13;                         // class of a code: 1..6 colours, 7..12 the values -6..-1 (0 unused)
 constexpr int NKEY = 120;                        // 9 levels x 13 classes = 117 key masks, padded to 16 bytes
 constexpr int CELL_LUT_N = 1092;                 // 1089 cells (+ pad to a multiple of 4)
-constexpr int GL_CAP = 64;                       // grid blocks per voting round
-constexpr int ROW_CHUNKS = GSTRIDE / 16;         // a staged row / window is 69 sixteen-byte chunks
+constexpr int ROW_WORDS = GSTRIDE / 4;           // a staged row / window is 276 words
+constexpr int WL_CAP = 32;                       // non-zero words per compaction round (one per lane)
+constexpr int GL_CAP = 4 * WL_CAP;               // grid blocks per voting round
 
 // Grid / target values are differences of colour ids, i.e. -6..6 (env.py:230, 290). code_of() maps a value
 // to a 4-bit code (value & 15; 8 = "not a valid value", never matches), class_of() a valid code to 1..12.
@@ -54,6 +55,7 @@ struct __align__(16) EvalScratch {
                                  // (all zero between evaluations: every pass clears what it set)
     uint2 tb[32];                // per target block of the pass: the four vote bases (16 bits each)
     uint16_t glist[GL_CAP];      // grid blocks of the current round: cell | code << 11
+    uint16_t wlist[WL_CAP];      // indices of the non-zero words of the current round
 };
 
 // cell index -> (13 * y) << 8 | (HROW * x + z); built once per CTA
@@ -70,84 +72,95 @@ __device__ __forceinline__ int lut_x(int l) { return ((l & 0xFF) * 2979) >> 16; 
 // rows in the env state layout, the source address & 15 for the unaligned rows of a dense [count][1089] array that
 // the stateless sweep brings in with aligned TMA bulk copies. `init` (nullptr, or a 16-byte aligned row in the env
 // layout in global / shared memory; needs off == 0) is subtracted cell-wise: a "block" is a cell whose value differs
-// from init's. Lane L owns the chunks L, L + 32, L + 64; window bytes that are not cells (before `off`, from
-// off + 1089 on) are masked out.
-struct RowScan {
-    int pos;     // slot of this lane's first block
-    int total;   // blocks in the row
-};
-
+// from init's. Window bytes that are not cells (before `off`, from off + 1089 on) are masked out.
+// Two lock-step phases, no per-lane loops:
+//   word_scan   lane L looks at the words L, L + 32, ... (conflict-free 4-byte loads); one ballot per round tells every
+//               lane where its non-zero word goes (running count + popc of the lower lanes: no shuffle scan), and the
+//               indices of the non-zero words with slots [w0, w0 + 32) land in a 32-entry word list;
+//   block_emit  lane i takes word i of that list, finds its non-zero bytes with three logic operations, gets its output
+//               position from three ballots over the bits of its byte count and writes up to four list entries
+//               (cell | code << 11; code 8 = value that is no colour difference).
+// Rows with more than 32 non-zero words are handled in rounds (word_scan again with the next w0).
 __device__ __forceinline__ uint32_t keep_from(int n) { return n <= 0 ? 0xFFFFFFFFu : (n >= 4 ? 0u : 0xFFFFFFFFu << (8 * n)); }
 __device__ __forceinline__ uint32_t keep_below(int n) { return n >= 4 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ~(0xFFFFFFFFu << (8 * n))); }
+// bit 8 j + 7 <-> byte j of x is non-zero
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) { return (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u; }
 
-// The non-zero-byte masks (bit 8 j + 7 <-> byte j) of the twelve words this lane owns; returns their block count.
-__device__ __forceinline__ int row_masks(const uint32_t *win, int off, const int8_t *init, int lane, uint32_t (&nz)[12]) {
-    const int4 *w4 = reinterpret_cast<const int4 *>(win);
-    const int4 *i4 = reinterpret_cast<const int4 *>(init);
-    int cnt = 0;
-#pragma unroll
-    for (int q = 0; q < 3; q++) {
-        const int c = lane + 32 * q;
-        int4 v = make_int4(0, 0, 0, 0);
-        if (q < 2 || c < ROW_CHUNKS) {
-            v = w4[c];
-            if (init) {
-                const int4 s = i4[c];
-                v.x ^= s.x; v.y ^= s.y; v.z ^= s.z; v.w ^= s.w;
-            }
-        }
-        uint32_t x[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
-        const int lo = off - 16 * c, hi = lo + CELLS;   // bytes [lo, hi) of this chunk are cells
-        if (lo > 0 || hi < 16) {                        // first / last chunk of the row only
-#pragma unroll
-            for (int k = 0; k < 4; k++) x[k] &= keep_from(lo - 4 * k) & keep_below(hi - 4 * k);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t m = (x[k] | ((x[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
-            nz[4 * q + k] = m;
-            cnt += __popc(m);
-        }
+// grid ^ init of window word w, non-cell bytes cleared (EDGE: w may hold bytes that are not cells)
+template <bool EDGE>
+__device__ __forceinline__ uint32_t diff_word(const uint32_t *win, int off, const uint32_t *init32, int w) {
+    uint32_t x = win[w];
+    if (init32) x ^= init32[w];
+    if (EDGE) {
+        const int lo = off - 4 * w;   // bytes [lo, lo + CELLS) of this word are cells
+        x &= keep_from(lo) & keep_below(lo + CELLS);
     }
-    return cnt;
+    return x;
 }
 
-// Masks (left in nz for a first row_emit) + exclusive scan of the per-lane block counts.
-__device__ __forceinline__ RowScan row_scan(const uint32_t *win, int off, const int8_t *init, int lane, uint32_t (&nz)[12]) {
-    const int cnt = row_masks(win, off, init, lane, nz);
-    int pos = cnt;
+// Returns the number of non-zero words of the row (warp-uniform); the indices of those with slots [w0, w0 + WL_CAP)
+// are written to wl. COUNT: *nblocks = number of blocks (non-zero cells) of the row.
+template <bool COUNT>
+__device__ __forceinline__ int word_scan(const uint32_t *win, int off, const int8_t *init, int lane, int w0,
+                                         uint16_t *wl, int *nblocks) {
+    const uint32_t *i32 = reinterpret_cast<const uint32_t *>(init);
+    const unsigned lt = (1u << lane) - 1u;
+    int base = -w0, nb = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, pos, d);
-        if (lane >= d) pos += o;
+    for (int q = 0; q < (ROW_WORDS + 31) / 32; q++) {
+        const int w = lane + 32 * q;
+        uint32_t x = 0;
+        if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS)   // only words 0..3 and the last ones can hold non-cell bytes
+            x = (q == 0 || 32 * q + 32 > ROW_WORDS - 4) ? diff_word<true>(win, off, i32, w) : diff_word<false>(win, off, i32, w);
+        const unsigned b = __ballot_sync(0xffffffffu, x != 0);
+        if (COUNT) nb += __popc(nz_bytes(x));
+        const int slot = base + __popc(b & lt);
+        if (x != 0 && (unsigned)slot < (unsigned)WL_CAP) wl[slot] = (uint16_t)w;
+        base += __popc(b);
     }
-    RowScan rs;
-    rs.total = __shfl_sync(0xffffffffu, pos, 31);
-    rs.pos = pos - cnt;
-    return rs;
+    if (COUNT) *nblocks = __reduce_add_sync(0xffffffffu, nb);
+    return base + w0;
 }
 
-// Writes the blocks with slots [r0, r0 + cap) into list[0 .. cap) as cell | code << 11 (code 8 = value that is no
-// colour difference). The caller synchronises the warp before reading the list.
-__device__ __forceinline__ void row_emit(const uint32_t *win, int off, const int8_t *init, int lane,
-                                         const uint32_t (&nz)[12], RowScan rs, int r0, int cap, uint16_t *list) {
-    if (rs.pos >= r0 + cap) return;   // all of this lane's blocks come after the window
-    const int8_t *w8 = reinterpret_cast<const int8_t *>(win);
-    int slot = rs.pos - r0;
+// The blocks of the words wl[0 .. nw) (nw <= 32) -> gl[0 .. returned count) (<= 4 nw entries).
+// The caller synchronises the warp between word_scan, block_emit and the readers of gl.
+__device__ __forceinline__ int block_emit(const uint32_t *win, int off, const int8_t *init, int lane, int nw,
+                                          const uint16_t *wl, uint16_t *gl) {
+    uint32_t g = 0, s = 0, m = 0;
+    int w = 0;
+    if (lane < nw) {
+        w = wl[lane];
+        g = win[w];
+        if (init) s = reinterpret_cast<const uint32_t *>(init)[w];
+        const int lo = off - 4 * w;
+        m = nz_bytes((g ^ s) & keep_from(lo) & keep_below(lo + CELLS));
+    }
+    const int cnt = __popc(m);   // 0..4
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned b0 = __ballot_sync(0xffffffffu, cnt & 1), b1 = __ballot_sync(0xffffffffu, cnt & 2),
+                   b2 = __ballot_sync(0xffffffffu, cnt & 4);
+    int pos = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    const int cell0 = 4 * w - off;
 #pragma unroll
-    for (int q = 0; q < 12; q++) {
-        uint32_t m = nz[q];
-        while (m) {
-            const int j = (__ffs(m) - 1) >> 3;
-            m &= m - 1;
-            if ((unsigned)slot < (unsigned)cap) {
-                const int p = 16 * (lane + 32 * (q >> 2)) + 4 * (q & 3) + j;   // window byte
-                const int d = init ? (int)w8[p] - (int)init[p] : (int)w8[p];
-                list[slot] = (uint16_t)((p - off) | (code_of(d) << 11));
-            }
-            slot++;
+    for (int b = 0; b < 4; b++) {
+        if (m & (0x80u << (8 * b))) {
+            const int d = (int)(int8_t)(g >> (8 * b)) - (int)(int8_t)(s >> (8 * b));
+            gl[pos++] = (uint16_t)((cell0 + b) | (code_of(d) << 11));
         }
     }
+    return __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+}
+
+// Number of blocks of a staged row (warp-uniform).
+__device__ __forceinline__ int count_blocks(const uint32_t *win, int off, const int8_t *init, int lane) {
+    const uint32_t *i32 = reinterpret_cast<const uint32_t *>(init);
+    int nb = 0;
+#pragma unroll
+    for (int q = 0; q < (ROW_WORDS + 31) / 32; q++) {
+        const int w = lane + 32 * q;
+        if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS) nb += __popc(nz_bytes(diff_word<true>(win, off, i32, w)));
+    }
+    return __reduce_add_sync(0xffffffffu, nb);
 }
 
 // Admissible-shift rectangles of the four rotations from the rotation-0 bounding box of the non-zero
@@ -260,60 +273,68 @@ __device__ __forceinline__ int hist_max(EvalScratch &es, int4 rc, int n_rot, int
 
 // Evaluate max intersection of a staged (difference) grid with a set of target blocks.
 //   win / off / init : the staged grid (see the compaction above)
-//   nblk  : number of target blocks; they are handed over in passes of 32: reg(c0) makes lane t register block
-//           c0 + t (register_target) and unreg(c0) makes it clear es.kmask[key] again
+//   tg    : the target blocks, handed over in rounds (tg.rounds(); tg.load(r) makes round r current and returns its
+//           number of blocks) and, inside a round, in passes of 32: tg.reg(c0) makes lane t register block c0 + t of the
+//           round (register_target) and returns its key, or -1
 //   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
-template <bool WANT_KEY, class RegF, class UnregF>
+template <bool WANT_KEY, class Targets>
 __device__ __forceinline__ int eval_votes(EvalScratch &es, const uint32_t *win, int off, const int8_t *init,
-                                          const uint16_t *__restrict__ lut, int nblk, RegF reg, UnregF unreg,
-                                          int4 rc, int n_rot, int lane, int *key_out) {
+                                          const uint16_t *__restrict__ lut, Targets &tg, int4 rc, int n_rot, int lane,
+                                          int *key_out) {
     if (WANT_KEY) *key_out = -1;
-    if (nblk == 0) return 0;
+    if (tg.empty()) return 0;
     hist_clear(es, lane);
-    uint32_t nz[12];
-    const RowScan gs = row_scan(win, off, init, lane, nz);
-    if (gs.total == 0) { __syncwarp(); return 0; }
-    const bool one_round = gs.total <= GL_CAP;
-    if (one_round) row_emit(win, off, init, lane, nz, gs, 0, GL_CAP, es.glist);
-    for (int c0 = 0; c0 < nblk; c0 += 32) {
-        reg(c0);
+    const int nwords = word_scan<false>(win, off, init, lane, 0, es.wlist, nullptr);
+    if (nwords == 0) { __syncwarp(); return 0; }
+    for (int w0 = 0; w0 < nwords; w0 += WL_CAP) {   // crowded grids (> 32 non-zero words): several rounds
+        if (w0) {
+            __syncwarp();
+            word_scan<false>(win, off, init, lane, w0, es.wlist, nullptr);
+        }
         __syncwarp();
-        if (one_round) {
-            vote_round(es, lut, gs.total, n_rot, lane);
-        } else {
-            for (int r0 = 0; r0 < gs.total; r0 += GL_CAP) {   // crowded grids: the masks are rebuilt per round
-                uint32_t nz2[12];
-                row_masks(win, off, init, lane, nz2);
-                row_emit(win, off, init, lane, nz2, gs, r0, GL_CAP, es.glist);
+        const int ng = block_emit(win, off, init, lane, min(WL_CAP, nwords - w0), es.wlist, es.glist);
+        __syncwarp();
+        for (int r = 0; r < tg.rounds(); r++) {
+            const int nt = tg.load(r);
+            for (int c0 = 0; c0 < nt; c0 += 32) {
+                const int mykey = tg.reg(es, c0, lane);
                 __syncwarp();
-                vote_round(es, lut, min(GL_CAP, gs.total - r0), n_rot, lane);
+                vote_round(es, lut, ng, n_rot, lane);
+                __syncwarp();
+                if (mykey >= 0) es.kmask[mykey] = 0u;   // leave the key masks all-zero for the next pass / evaluation
                 __syncwarp();
             }
         }
-        __syncwarp();
-        unreg(c0);   // leave the key masks all-zero for the next pass / evaluation
-        __syncwarp();
     }
     return hist_max<WANT_KEY>(es, rc, n_rot, lane, key_out);
 }
 
-// The env path: the target blocks are a packed list (y | x<<4 | z<<8 | code<<12; shared or global memory) and lane t
-// registers entry c0 + t; the grid is a row in the env layout (off = 0).
+// The env path: the target blocks are a packed list (y | x<<4 | z<<8 | code<<12; shared or global memory) in one
+// round; the grid is a row in the env layout (off = 0).
+struct ListTargets {
+    const uint16_t *__restrict__ tlist;
+    int nblk;
+    uint32_t e0;   // entry of the first pass, fetched when the object is made: the latency hides behind the compaction
+    __device__ __forceinline__ ListTargets(const uint16_t *tl, int n, int lane) : tlist(tl), nblk(n) {
+        e0 = lane < n ? tl[lane] : 0u;
+    }
+    __device__ __forceinline__ bool empty() const { return nblk == 0; }
+    __device__ __forceinline__ int rounds() const { return 1; }
+    __device__ __forceinline__ int load(int) const { return nblk; }
+    __device__ __forceinline__ int reg(EvalScratch &es, int c0, int lane) const {
+        if (c0 + lane >= nblk) return -1;
+        const uint32_t e = c0 == 0 ? e0 : (uint32_t)tlist[c0 + lane];
+        return register_target(es, lane, NCLS * (e & 15), (e >> 4) & 15, (e >> 8) & 15, e >> 12);
+    }
+};
+
 template <bool WANT_KEY>
 __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                                      const uint16_t *__restrict__ lut,
                                                      const uint16_t *__restrict__ tlist, int nblk, int4 rc,
                                                      int n_rot, int lane, int *key_out) {
-    int mykey = -1;
-    uint32_t e_next = lane < nblk ? tlist[lane] : 0u;   // fetched before the grid is compacted: the latency hides there
-    auto reg = [&](int c0) {
-        mykey = -1;
-        const uint32_t e = e_next;
-        if (c0 + 32 + lane < nblk) e_next = tlist[c0 + 32 + lane];
-        if (c0 + lane < nblk) mykey = register_target(es, lane, NCLS * (e & 15), (e >> 4) & 15, (e >> 8) & 15, e >> 12);
-    };
-    auto unreg = [&](int) { if (mykey >= 0) es.kmask[mykey] = 0u; };
-    return eval_votes<WANT_KEY>(es, grid, 0, init, lut, nblk, reg, unreg, rc, n_rot, lane, key_out);
+    ListTargets tg(tlist, nblk, lane);
+    return eval_votes<WANT_KEY>(es, grid, 0, init, lut, tg, rc, n_rot, lane, key_out);
 }
 
 // Direct evaluation for tasks whose every rotation admits exactly ONE shift (targets spanning the whole zone in
