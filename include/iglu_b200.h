@@ -81,8 +81,9 @@ typedef struct iglu_config {
                                    launch where the library would use two launches (physics, then observe);
                                    bit 2 = 1 forces the two-launch form; bit 3 = 1 deals the observe launch's env
                                    groups statically even when iglu_state.sched is given; bit 4 = 1 makes
-                                   iglu_step_walking_host stage pinned buffers through copies too; bits 8-13: envs per
-                                   group of the observe launch (0 = automatic) */
+                                   iglu_step_walking_host stage pinned buffers through copies too; bit 5 = 1 uses the
+                                   group-wise observe launch where the library would use the tiled one; bits 8-13:
+                                   envs per group of the group-wise observe launch (0 = automatic) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
 } iglu_config;
