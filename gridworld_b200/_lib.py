@@ -28,7 +28,7 @@ class Config(C.Structure):
 class State(C.Structure):
     _fields_ = [('n', C.c_int64), ('grid', C.c_void_p), ('init', C.c_void_p), ('target', C.c_void_p),
                 ('pose', C.c_void_p), ('init_pose', C.c_void_p), ('istate', C.c_void_p),
-                ('tlist', C.c_void_p), ('tmeta', C.c_void_p), ('sched', C.c_void_p)]
+                ('tlist', C.c_void_p), ('tmeta', C.c_void_p), ('sched', C.c_void_p), ('worklist', C.c_void_p)]
 
 
 class Obs(C.Structure):
@@ -71,7 +71,7 @@ EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_des
            'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
            'iglu_task_pool_prepare', 'iglu_task_pool_attach', 'iglu_step_walking_host_async', 'iglu_wait',
            'iglu_fetch_env_host', 'iglu_max_intersection_strided', 'iglu_sample_tasks',
-           'iglu_staged_prepare', 'iglu_staged_step')
+           'iglu_staged_prepare', 'iglu_staged_step', 'iglu_debug_overlap_trace')
 
 _lib = None
 
@@ -114,6 +114,8 @@ def load():
         L.iglu_staged_prepare.argtypes = [vp, C.POINTER(StagedTasks), vp, vp, vp]
         L.iglu_staged_step.argtypes = [vp, C.POINTER(State), C.POINTER(StagedTasks), vp, vp]
     L.iglu_last_launch_count.argtypes = [vp]
+    if hasattr(L, 'iglu_debug_overlap_trace'):
+        L.iglu_debug_overlap_trace.argtypes = [vp, vp]
     L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]
     L.iglu_task_pool_attach.argtypes = [vp, C.POINTER(TaskPool)]
     if L.iglu_abi_version() != 1:

@@ -75,7 +75,14 @@ struct StepParams {
     int group;                 // envs per group (<= 32): a warp handles one group at a time, lane j <-> env j of it
     int tiles;                 // tiled observe launch: tiles per CTA (group = envs per tile)
     int64_t tail_begin;        // ... and the first env of the dynamically scheduled tail
+    int overlap;               // physics launch of the overlapped step (k_widen alongside, k_commit afterwards)
 };
+
+// istate w7 as the physics launch of the overlapped step leaves it for k_commit:
+// wrong_placement (2 bits, -1..1) | (edited cell + 1) << 2 | (new value of that cell) << 13 | reset << 17
+__device__ __forceinline__ int pack_w7(int wrong, int edit_cell, int edit_val, bool reset) {
+    return (wrong & 3) | ((edit_cell + 1) << 2) | ((edit_val & 15) << 13) | ((int)reset << 17);
+}
 
 // ---- TMA (bulk async copy) + mbarrier helpers -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -273,7 +280,7 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (
     // Every warp's FIRST group is its static index (thousands of warps asking one counter at kernel start would
     // serialise in the L2: 22 % of round 1's stall samples); the counter only deals the groups after those.
     const bool dynamic = PHASES == 2 && p.dynamic;
-    if (PHASES == 1 && p.st.sched != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.st.sched[0] = 0;
+    if (PHASES == 1 && !p.overlap && p.st.sched != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.st.sched[0] = 0;
     const int total_warps = (int)gridDim.x * WPC;
     int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x;
     while (grp < ngroups) {
@@ -546,10 +553,24 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (
                 p.st.istate[5 * n + i] = dsize;
             }
             const int wrong = HAS_A ? dsize_old - dsize : w[7];                // task.py:111
-            if (PHASES == 1) {  // bookkeeping is finished by the observe launch
+            if (PHASES == 1 && p.overlap && !(do_reset || edit_cell >= 0)) {
+                // overlapped step, nothing edited and no reset: the cached max_int stands (task.py:112, wrong == 0)
+                // and the observation row k_widen writes from the unchanged grid is final -- finish the env here
+                const bool done = max_int == target_size || step_no == p.cfg.max_steps;   // task.py:113, env.py:292
+                const double reward = (double)wrong * p.cfg.wrong_placement_scale;      // right == 0 (env.py:293-296)
+                p.obs.reward[i] = reward;
+                p.obs.done[i] = (uint8_t)done;
+                if (p.reward_host) {
+                    p.reward_host[i] = reward;
+                    p.done_host[i] = (uint8_t)done;
+                }
+                p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
+                p.st.istate[6 * n + i] = max_int;
+                p.st.istate[7 * n + i] = 0;
+            } else if (PHASES == 1) {  // bookkeeping is finished by the observe launch / by k_commit
                 p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((a.err & 0xFF) << 24);
                 p.st.istate[6 * n + i] = max_int;
-                p.st.istate[7 * n + i] = wrong;
+                p.st.istate[7 * n + i] = p.overlap ? pack_w7(wrong, edit_cell, edit_val, do_reset) : wrong;
             } else {
                 const int mi = wrong != 0 ? mi_eval : max_int;                 // task.py:112
                 bool done = mi == target_size;                                 // task.py:113
@@ -565,6 +586,16 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (
                 }
                 p.st.istate[3 * n + i] = (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((int)done << 16) | ((a.err & 0xFF) << 24);
                 p.st.istate[6 * n + i] = mi;
+            }
+        }
+        if (PHASES == 1 && p.overlap) {   // envs k_commit has to visit: edited or reset this step
+            const bool special = valid && (do_reset || edit_cell >= 0);
+            const unsigned sm = __ballot_sync(0xffffffffu, special);
+            if (sm) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(p.st.sched + 4, __popc(sm));
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (special) p.st.worklist[b + __popc(sm & ((1u << lane) - 1u))] = (int32_t)i;
             }
         }
         grp = dynamic ? (int64_t)__shfl_sync(0xffffffffu, grp_next, 0) : grp + (int64_t)gridDim.x * WPC;
@@ -829,6 +860,231 @@ __global__ void __launch_bounds__(IGLU_OBS_WARPS * 32, IGLU_OBS_CTAS) k_observe(
     }
     if (p.st.sched != nullptr && lane == 0 && evals_done)
         atomicAdd(reinterpret_cast<unsigned long long *>(p.st.sched + 2), (unsigned long long)evals_done);
+}
+
+// ------------------------------------------------------------------ overlapped step: k_widen || physics, then k_commit
+// A step's physics launch is a latency chain that moves almost no bytes, and the observation rewrite is a stream of
+// bytes that needs few issue slots; they only depend on each other through the (at most one) cell an env edits and
+// through resets. The overlapped step therefore runs
+//   k_widen   (caller's stream): obs['grid'] rows and (every-step reward) maximal_intersection from the grids AS THEY
+//             ARE WHEN THE STEP STARTS, one 16-warp CTA per SM at 64 registers, next to
+//   physics   (k_step<KIND, 1>, second stream): two 4-warp CTAs per SM in the registers k_widen leaves; it finishes
+//             reward / done itself for every env it neither edited nor reset (the cached max_int stands, task.py:112)
+//             and lists the others in st.worklist;
+//   k_commit  (caller's stream, after both): for the listed envs only -- patch the edited cell into obs['grid'] or
+//             rewrite the row after a reset, evaluate maximal_intersection on the new grid, reward / done.
+// k_widen reads state the physics launch may be rewriting (an edited byte, a reset env's rows): what it writes for
+// such an env is replaced by k_commit, and the evaluation tolerates arbitrary bytes (register_target / hist_max
+// check their inputs).
+#ifndef IGLU_WIDEN_RING
+#define IGLU_WIDEN_RING 4
+#endif
+struct __align__(16) WidenWarp {
+    ObsSlot slot[IGLU_WIDEN_RING];
+    EvalScratch es;
+    unsigned long long bar[IGLU_WIDEN_RING];
+};
+constexpr int WIDEN_WARPS = 16;
+constexpr size_t widen_smem_bytes() { return TABLE_BYTES + WIDEN_WARPS * sizeof(WidenWarp); }
+
+// Shared by k_widen / k_commit: ring producer and consumer over a warp's slots (see k_observe).
+template <int NBUF, class Warp, bool SAFE>
+struct Ring {
+    const StepParams &p;
+    Warp &ws;
+    const uint16_t *lut;
+    int lane;
+    uint32_t seq_issue = 0, seq_cons = 0;
+    int evals = 0;
+    __device__ __forceinline__ Ring(const StepParams &p_, Warp &ws_, const uint16_t *lut_, int lane_)
+        : p(p_), ws(ws_), lut(lut_), lane(lane_) {}
+    __device__ __forceinline__ void issue(int64_t ej, bool evj) {
+        if (lane == 0) {
+            const uint32_t sa = smem_u32(&ws.slot[seq_issue % NBUF]), ba = smem_u32(&ws.bar[seq_issue % NBUF]);
+            const uint32_t bytes = GSTRIDE + (evj ? 16u : 0u);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ba), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sa), "l"(p.st.grid + ej * GSTRIDE), "r"((uint32_t)GSTRIDE), "r"(ba) : "memory");
+            if (evj)
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sa + (uint32_t)GSTRIDE), "l"(p.st.tlist + ej * p.cfg.tlist_cap), "r"(16u), "r"(ba) : "memory");
+        }
+        seq_issue++;
+    }
+    __device__ __forceinline__ ObsSlot &wait() {
+        mbar_wait(&ws.bar[seq_cons % NBUF], (seq_cons / NBUF) & 1u);
+        return ws.slot[seq_cons % NBUF];
+    }
+    __device__ __forceinline__ int evaluate(ObsSlot &sl, int64_t ej, bool hs, int nb) {
+        const int4 rc = sl.rects;
+        const uint16_t *tl = p.st.tlist + ej * p.cfg.tlist_cap + TL_HDR;
+        evals++;
+        if (single_shift_rects(rc, 4)) {
+            auto each = [&](auto f) {
+                for (int b = lane; b < nb; b += 32) {
+                    const uint32_t e = tl[b];
+                    f(e & 15, (e >> 4) & 15, (e >> 8) & 15, e >> 12);
+                }
+            };
+            return eval_single_shift<false, SAFE>(reinterpret_cast<const int8_t *>(sl.grid),
+                                                  hs ? p.st.init + ej * GSTRIDE : nullptr, each, rc, 4, nullptr);
+        }
+        return eval_max_intersection<false, SAFE>(ws.es, sl.grid, hs ? p.st.init + ej * GSTRIDE : nullptr, lut, tl, nb, rc, 4,
+                                                  lane, nullptr);
+    }
+    __device__ __forceinline__ void release() {
+        __syncwarp();  // every lane is done with the slot before it is refilled
+        seq_cons++;
+    }
+};
+
+__global__ void __launch_bounds__(WIDEN_WARPS * 32, 2) k_widen(const __grid_constant__ StepParams p) {
+    constexpr int NBUF = IGLU_WIDEN_RING;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
+    WidenWarp *scratch = reinterpret_cast<WidenWarp *>(smem_raw + TABLE_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    WidenWarp &ws = scratch[wid];
+    for (int q = tid; q < CELL_LUT_N / 2; q += WIDEN_WARPS * 32)
+        reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
+    for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < NBUF; s++) mbar_init(&ws.bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n = p.st.n;
+    const int GS = p.group;
+    const int64_t ngroups = (n + GS - 1) / GS;
+    const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    Ring<NBUF, WidenWarp, true> ring(p, ws, lut, lane);
+    const int total_warps = (int)gridDim.x * WIDEN_WARPS;
+    // every warp's first group is its static index; the counter st.sched[0] (left at zero by k_commit) deals the rest
+    int64_t grp = (int64_t)wid * gridDim.x + blockIdx.x;
+    while (grp < ngroups) {
+        int grp_next = 0;
+        if (lane == 0) grp_next = total_warps + atomicAdd(p.st.sched, 1);
+        const int64_t e0 = grp * GS;
+        const int64_t i = e0 + lane;
+        const bool valid = lane < GS && i < n;
+        int w3 = 0, dsize = 0, nblk = 0, has_start = 0;
+        if (valid && every_step) {   // may be mid-rewrite by the physics launch: see the note above
+            w3 = p.st.istate[3 * n + i]; dsize = p.st.istate[5 * n + i];
+            nblk = p.st.tmeta[0 * n + i]; has_start = p.st.tmeta[5 * n + i];
+        }
+        // evaluated here: envs that hold blocks and are not reset by this step (done_prev with auto-reset)
+        const bool ev = valid && every_step && nblk > 0 && nblk <= p.cfg.tlist_cap - TL_HDR && dsize != 0 &&
+                        !(p.cfg.auto_reset && ((w3 >> 16) & 0xFF));
+        const unsigned em = __ballot_sync(0xffffffffu, ev);
+        const unsigned nm = __ballot_sync(0xffffffffu, valid);
+        const unsigned hm = __ballot_sync(0xffffffffu, has_start != 0);
+        unsigned pend = nm, todo = nm;
+        for (int f = 0; f < NBUF && pend; f++) {
+            const int j = __ffs(pend) - 1;
+            pend &= pend - 1;
+            ring.issue(e0 + j, (em >> j) & 1u);
+        }
+        while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t ej = e0 + j;
+            ObsSlot &sl = ring.wait();
+            write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
+            if ((em >> j) & 1u) ring.evaluate(sl, ej, (hm >> j) & 1u, __shfl_sync(0xffffffffu, nblk, j));
+            ring.release();
+            if (pend) {
+                const int jn = __ffs(pend) - 1;
+                pend &= pend - 1;
+                ring.issue(e0 + jn, (em >> jn) & 1u);
+            }
+        }
+        grp = (int64_t)__shfl_sync(0xffffffffu, grp_next, 0);
+    }
+    if (lane == 0 && ring.evals)
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.st.sched + 2), (unsigned long long)ring.evals);
+}
+
+struct __align__(16) CommitWarp {
+    ObsSlot slot[1];
+    EvalScratch es;
+    unsigned long long bar[1];
+    unsigned long long pad;
+};
+constexpr int COMMIT_WARPS = 16;
+constexpr size_t commit_smem_bytes() { return TABLE_BYTES + COMMIT_WARPS * sizeof(CommitWarp); }
+
+__global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_constant__ StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
+    CommitWarp *scratch = reinterpret_cast<CommitWarp *>(smem_raw + TABLE_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    CommitWarp &ws = scratch[wid];
+    for (int q = tid; q < CELL_LUT_N / 2; q += COMMIT_WARPS * 32)
+        reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
+    for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
+    if (lane == 0) {
+        mbar_init(&ws.bar[0], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n = p.st.n;
+    const int count = p.st.sched[4];
+    const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    Ring<1, CommitWarp, false> ring(p, ws, lut, lane);
+    int counted = 0;
+    for (int k = wid * (int)gridDim.x + (int)blockIdx.x; k < count; k += (int)gridDim.x * COMMIT_WARPS) {
+        const int64_t e = p.st.worklist[k];
+        ring.issue(e, true);   // grid row + rectangle header: asked for before the env's words (one round trip less)
+        // warp-uniform loads (one transaction each)
+        const int w3 = p.st.istate[3 * n + e], step_no = p.st.istate[4 * n + e], dsize = p.st.istate[5 * n + e];
+        const int max_int = p.st.istate[6 * n + e], w7 = p.st.istate[7 * n + e];
+        const int nblk = p.st.tmeta[0 * n + e], target_size = p.st.tmeta[1 * n + e], has_start = p.st.tmeta[5 * n + e];
+        const int wrong = (w7 << 30) >> 30;              // sign-extended 2 bits
+        const int edit_cell = ((w7 >> 2) & 0x7FF) - 1, edit_val = (w7 >> 13) & 15;
+        const bool reset = (w7 >> 17) & 1;
+        const bool ev = wrong != 0 && nblk > 0 && dsize != 0;   // task.py:111-112 (an all-zero difference grid scores 0)
+        int mi_eval = 0;
+        {
+            ObsSlot &sl = ring.wait();
+            if (reset) write_grid_obs(p.obs.grid, e * CELLS, sl.grid, lane);   // the row k_widen wrote predates the reset
+            if (ev) {
+                mi_eval = ring.evaluate(sl, e, has_start != 0, nblk);
+                // evaluations k_widen did not already count for this env (it skips empty grids and reset envs)
+                if (!(every_step && dsize + wrong != 0 && !reset)) counted++;
+            }
+            ring.release();
+        }
+        if (lane == 0) {
+            if (!reset && edit_cell >= 0) p.obs.grid[e * CELLS + edit_cell] = edit_val;
+            const int mi = wrong != 0 ? mi_eval : max_int;                           // task.py:112
+            bool done = mi == target_size;                                          // task.py:113
+            const int right = mi - max_int;                                         // task.py:115
+            done = done || (step_no == p.cfg.max_steps);                            // env.py:292
+            const double reward = right == 0 ? (double)wrong * p.cfg.wrong_placement_scale
+                                             : (double)right * p.cfg.right_placement_scale;
+            p.obs.reward[e] = reward;
+            p.obs.done[e] = (uint8_t)done;
+            if (p.reward_host) {
+                p.reward_host[e] = reward;
+                p.done_host[e] = (uint8_t)done;
+            }
+            p.st.istate[3 * n + e] = (w3 & 0xFF00FFFF) | ((int)done << 16);
+            p.st.istate[6 * n + e] = mi;
+            p.st.istate[7 * n + e] = wrong;
+        }
+    }
+    // evaluations of this launch that k_widen did not count: only those (bench.py's evaluated_frac counts envs)
+    if (lane == 0 && counted)
+        atomicAdd(reinterpret_cast<unsigned long long *>(p.st.sched + 2), (unsigned long long)(unsigned)counted);
+    ring.evals = 0;
+    // the last CTA out leaves the launch-to-launch counters at zero for the next step
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const int t = atomicAdd(p.st.sched + 5, 1);
+        if (t == (int)gridDim.x - 1) { p.st.sched[0] = 0; p.st.sched[4] = 0; p.st.sched[5] = 0; }
+    }
 }
 
 // ------------------------------------------------------------------ task preparation
@@ -1216,6 +1472,10 @@ struct iglu_ctx {
     int num_sms;
     int last_launches;
     iglu_task_pool pool;  // copy of the attached generator (m == 0: none)
+    cudaStream_t side;    // overlapped step: the physics launch runs here, next to k_widen on the caller's stream
+    cudaEvent_t fork, join;
+    cudaEvent_t trace[6];  // IGLU_B200_TRACE=1: start / end of k_widen, the physics launch and k_commit of the last step
+    int tracing;
 };
 
 static int check(cudaError_t e) { return e == cudaSuccess ? IGLU_OK : IGLU_ERR_CUDA; }
@@ -1282,14 +1542,45 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes()));
-    if (rc) { delete c; return rc; }
+    if (!rc) rc = check(cudaFuncSetAttribute(k_widen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes()));
+    c->side = nullptr; c->fork = nullptr; c->join = nullptr;
+    c->tracing = 0;
+    for (int i = 0; i < 6; i++) c->trace[i] = nullptr;
+    if (const char *tr = getenv("IGLU_B200_TRACE")) {
+        if (tr[0] == '1') {
+            c->tracing = 1;
+            for (int i = 0; i < 6 && !rc; i++) rc = check(cudaEventCreate(&c->trace[i]));
+        }
+    }
+    if (!rc) rc = check(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    if (!rc) rc = check(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    if (!rc) rc = check(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
+    if (rc) { iglu_ctx_destroy(c); return rc; }
     *out = c;
     return IGLU_OK;
 }
 
-extern "C" void iglu_ctx_destroy(iglu_ctx *ctx) { delete ctx; }
+extern "C" void iglu_ctx_destroy(iglu_ctx *ctx) {
+    if (!ctx) return;
+    for (int i = 0; i < 6; i++) if (ctx->trace[i]) cudaEventDestroy(ctx->trace[i]);
+    if (ctx->join) cudaEventDestroy(ctx->join);
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    delete ctx;
+}
 
 extern "C" int iglu_last_launch_count(const iglu_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
+
+// Tuning aid (IGLU_B200_TRACE=1 when the context was created; synchronises): milliseconds, relative to the start of
+// k_widen, of [k_widen end, physics start, physics end, k_commit start, k_commit end] of the last overlapped step.
+extern "C" int iglu_debug_overlap_trace(iglu_ctx *ctx, float *out5) {
+    if (!ctx || !out5 || !ctx->tracing) return IGLU_ERR_INVALID_ARG;
+    if (cudaEventSynchronize(ctx->trace[5]) != cudaSuccess) return IGLU_ERR_CUDA;
+    for (int i = 1; i < 6; i++)
+        if (cudaEventElapsedTime(&out5[i - 1], ctx->trace[0], ctx->trace[i]) != cudaSuccess) return IGLU_ERR_CUDA;
+    return IGLU_OK;
+}
 
 static bool state_ok(const iglu_state *st, const iglu_obs *obs) {
     return st && obs && st->n > 0 && st->grid && st->init && st->target && st->pose && st->init_pose &&
@@ -1403,6 +1694,42 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     const int64_t n = p.st.n;
     // measured (profiles/r01_launch_policy.txt): the fused launch only wins for on_change reward + fully
     // rewritten obs['grid'] (its ring prefetch hides behind the physics); everything else is faster split
+    // Overlapped step (k_widen || physics, then k_commit): whenever obs['grid'] is rewritten in full and the batch is
+    // big enough for the overlap to pay for the third launch (measured, profiles/). reserved bit 6 = 1 turns it off.
+    if (p.cfg.write_grid_obs == 1 && p.obs.grid && p.st.worklist && p.st.sched && (n >= 8192 || (p.cfg.reserved & 128)) &&
+        !(p.cfg.reserved & (64 | 2 | 4))) {
+        int64_t chunk = (n + (int64_t)ctx->num_sms * WIDEN_WARPS - 1) / ((int64_t)ctx->num_sms * WIDEN_WARPS);
+        chunk /= 6;
+        chunk = chunk < 2 ? 2 : (chunk > IGLU_OBS_DYN_GROUP ? IGLU_OBS_DYN_GROUP : chunk);
+        if ((p.cfg.reserved >> 8) & 63) chunk = (p.cfg.reserved >> 8) & 63;     // tuning override
+        p.group = (int)(chunk > 32 ? 32 : chunk);
+        p.overlap = 1;
+        int rc = check(cudaEventRecord(ctx->fork, s));
+        if (!rc) rc = check(cudaStreamWaitEvent(ctx->side, ctx->fork, 0));
+        if (rc) return rc;
+        const int64_t groups_w = (n + p.group - 1) / p.group;
+        const int64_t ctas_w = (groups_w + WIDEN_WARPS - 1) / WIDEN_WARPS;
+        const bool tr = ctx->tracing != 0;
+        if (tr) cudaEventRecord(ctx->trace[0], s);
+        k_widen<<<(unsigned)(ctas_w < ctx->num_sms ? ctas_w : ctx->num_sms), WIDEN_WARPS * 32, widen_smem_bytes(), s>>>(p);
+        if (tr) cudaEventRecord(ctx->trace[1], s);
+        StepParams pa = p;
+        pa.group = 32;
+        if (tr) cudaEventRecord(ctx->trace[2], ctx->side);
+        k_step<KIND, 1><<<(unsigned)(((n + 31) / 32 + StepCfg<1>::WPC - 1) / StepCfg<1>::WPC), StepCfg<1>::WPC * 32, 0,
+                          ctx->side>>>(pa);
+        if (tr) cudaEventRecord(ctx->trace[3], ctx->side);
+        rc = check(cudaEventRecord(ctx->join, ctx->side));
+        if (!rc) rc = check(cudaStreamWaitEvent(s, ctx->join, 0));
+        if (rc) return rc;
+        const int64_t ctas_c = (n / 8 + COMMIT_WARPS - 1) / COMMIT_WARPS;   // ~1 listed env in 14: about one per warp
+        const int64_t max_c = (int64_t)ctx->num_sms * 2;
+        if (tr) cudaEventRecord(ctx->trace[4], s);
+        k_commit<<<(unsigned)(ctas_c < max_c ? (ctas_c > 0 ? ctas_c : 1) : max_c), COMMIT_WARPS * 32, commit_smem_bytes(), s>>>(p);
+        if (tr) cudaEventRecord(ctx->trace[5], s);
+        ctx->last_launches = 3;
+        return check(cudaPeekAtLastError());
+    }
     const bool fused_better = p.cfg.reward_mode != IGLU_REWARD_EVERY_STEP && p.cfg.write_grid_obs == 1 && p.obs.grid;
     const bool split = ((!fused_better) && !(p.cfg.reserved & 2)) || (p.cfg.reserved & 4);
     if (!split) {
@@ -1447,7 +1774,7 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     lc.attrs = at;
     lc.numAttrs = 1;
     int rc;
-    if (dynamic && !(p.cfg.reserved & 32)) {
+    if (dynamic && !(p.cfg.write_grid_obs == 1 && p.obs.grid) && !(p.cfg.reserved & 32)) {   // measured: profiles/
         // tiled observe launch: one tile per resident CTA when the batch is small, OBS_TILE-env tiles otherwise
         // static part: `share` / 64 of each CTA's chunks, in tiles of <= OBS_TILE envs; the rest is the dynamic tail
         const int64_t chunks = n / OBS_CHUNK;

@@ -196,8 +196,12 @@ __device__ __forceinline__ void hist_clear(EvalScratch &es, int lane) {
 
 // Target block (y13 = 13 * level, x, z, code) becomes slot t (0..31) of the current pass: its four vote bases and
 // its (level, class) key mask bit. Returns the key (for un-registering), or -1 for a code that matches nothing.
+// SAFE: entries that are not cells of the zone match nothing (k_widen of the overlapped step may look at a block list
+// while a reset rewrites it; everything it derives from such a list is discarded, but it must stay inside its tables).
+template <bool SAFE = false>
 __device__ __forceinline__ int register_target(EvalScratch &es, int t, int y13, int x, int z, int code) {
     if (code == 8) return -1;
+    if (SAFE && ((unsigned)x > 10u || (unsigned)z > 10u || (unsigned)y13 > 8u * NCLS)) return -1;
     // vote base of rotation k: k * HROT + (x_k + 10) * HROW + (z_k + 10) with the rotations of task.py:52-53
     const uint32_t b0 = 0 * HROT + (x + 10) * HROW + (z + 10);                 // (x, z)
     const uint32_t b1 = 1 * HROT + (z + 10) * HROW + (20 - x);                 // (z, 10 - x)
@@ -241,11 +245,16 @@ __device__ __forceinline__ void vote_round(EvalScratch &es, const uint16_t *__re
 // Maximum of the vote table over the admissible rectangles: one (rotation, dx) row per lane and pass. Returns
 // (warp-uniform) the best count; if WANT_KEY also the first (rot, dx, dz) reaching it in the reference's iteration
 // order, encoded k*441 + (dx+10)*21 + (dz+10), or -1 if the best is 0.
-template <bool WANT_KEY>
+template <bool WANT_KEY, bool SAFE = false>
 __device__ __forceinline__ int hist_max(EvalScratch &es, int4 rc, int n_rot, int lane, int *key_out) {
     const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
-    const int n0 = (rw[0] >> 8) & 0x1F, n1 = n_rot > 1 ? (rw[1] >> 8) & 0x1F : 0;
-    const int n2 = n_rot > 1 ? (rw[2] >> 8) & 0x1F : 0, n3 = n_rot > 1 ? (rw[3] >> 8) & 0x1F : 0;
+    // number of dx rows of a rotation; SAFE: 0 for a rectangle that does not lie inside the 21 x 21 table
+    auto rows = [](int r) -> int {
+        const int dx = rect_byte(r, 0), nx = (r >> 8) & 0x1F, dz = rect_byte(r, 2), nz = (r >> 24) & 0xFF;
+        return (!SAFE || (dx >= -10 && dx + nx <= 11 && dz >= -10 && dz + nz <= 11)) ? nx : 0;
+    };
+    const int n0 = rows(rw[0]), n1 = n_rot > 1 ? rows(rw[1]) : 0;
+    const int n2 = n_rot > 1 ? rows(rw[2]) : 0, n3 = n_rot > 1 ? rows(rw[3]) : 0;
     const int c1 = n0, c2 = n0 + n1, c3 = c2 + n2, total = c3 + n3;
     const unsigned short *h16 = reinterpret_cast<const unsigned short *>(es.hist);
     int best = 0;  // WANT_KEY: count << 12 | 4095 - key
@@ -277,7 +286,7 @@ __device__ __forceinline__ int hist_max(EvalScratch &es, int4 rc, int n_rot, int
 //           number of blocks) and, inside a round, in passes of 32: tg.reg(c0) makes lane t register block c0 + t of the
 //           round (register_target) and returns its key, or -1
 //   rc    : the four rotation rectangles (see rects_from_bbox); n_rot rotations are evaluated
-template <bool WANT_KEY, class Targets>
+template <bool WANT_KEY, bool SAFE = false, class Targets>
 __device__ __forceinline__ int eval_votes(EvalScratch &es, const uint32_t *win, int off, const int8_t *init,
                                           const uint16_t *__restrict__ lut, Targets &tg, int4 rc, int n_rot, int lane,
                                           int *key_out) {
@@ -306,11 +315,12 @@ __device__ __forceinline__ int eval_votes(EvalScratch &es, const uint32_t *win, 
             }
         }
     }
-    return hist_max<WANT_KEY>(es, rc, n_rot, lane, key_out);
+    return hist_max<WANT_KEY, SAFE>(es, rc, n_rot, lane, key_out);
 }
 
 // The env path: the target blocks are a packed list (y | x<<4 | z<<8 | code<<12; shared or global memory) in one
 // round; the grid is a row in the env layout (off = 0).
+template <bool SAFE = false>
 struct ListTargets {
     const uint16_t *__restrict__ tlist;
     int nblk;
@@ -324,17 +334,17 @@ struct ListTargets {
     __device__ __forceinline__ int reg(EvalScratch &es, int c0, int lane) const {
         if (c0 + lane >= nblk) return -1;
         const uint32_t e = c0 == 0 ? e0 : (uint32_t)tlist[c0 + lane];
-        return register_target(es, lane, NCLS * (e & 15), (e >> 4) & 15, (e >> 8) & 15, e >> 12);
+        return register_target<SAFE>(es, lane, NCLS * (e & 15), (e >> 4) & 15, (e >> 8) & 15, e >> 12);
     }
 };
 
-template <bool WANT_KEY>
+template <bool WANT_KEY, bool SAFE = false>
 __device__ __forceinline__ int eval_max_intersection(EvalScratch &es, const uint32_t *grid, const int8_t *init,
                                                      const uint16_t *__restrict__ lut,
                                                      const uint16_t *__restrict__ tlist, int nblk, int4 rc,
                                                      int n_rot, int lane, int *key_out) {
-    ListTargets tg(tlist, nblk, lane);
-    return eval_votes<WANT_KEY>(es, grid, 0, init, lut, tg, rc, n_rot, lane, key_out);
+    ListTargets<SAFE> tg(tlist, nblk, lane);
+    return eval_votes<WANT_KEY, SAFE>(es, grid, 0, init, lut, tg, rc, n_rot, lane, key_out);
 }
 
 // Direct evaluation for tasks whose every rotation admits exactly ONE shift (targets spanning the whole zone in
@@ -351,10 +361,13 @@ __device__ __forceinline__ bool single_shift_rects(int4 rc, int n_rot) {
     return ok;
 }
 
-template <bool WANT_KEY, class ForEachT>
+template <bool WANT_KEY, bool SAFE = false, class ForEachT>
 __device__ __forceinline__ int eval_single_shift(const int8_t *g8, const int8_t *__restrict__ sub,
                                                  ForEachT for_each_target, int4 rc, int n_rot, int *key_out) {
-    auto at = [&](int idx) -> int { return sub ? (int)g8[idx] - (int)sub[idx] : (int)g8[idx]; };
+    // (SAFE: the index into the global-memory row is clamped; valid tasks never leave the row)
+    auto at = [&](int idx) -> int {
+        return sub ? (int)g8[idx] - (int)sub[SAFE ? min(max(idx, 0), CELLS - 1) : idx] : (int)g8[idx];
+    };
     const int dx0 = rect_byte(rc.x, 0), dz0 = rect_byte(rc.x, 2), dx1 = rect_byte(rc.y, 0), dz1 = rect_byte(rc.y, 2);
     const int dx2 = rect_byte(rc.z, 0), dz2 = rect_byte(rc.z, 2), dx3 = rect_byte(rc.w, 0), dz3 = rect_byte(rc.w, 2);
     // cell index of (y, x_k - dx_k, z_k - dz_k) = 121 y + a_k x + b_k z + o_k  with the rotations of task.py:52-53

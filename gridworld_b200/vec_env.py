@@ -140,6 +140,7 @@ class IGLUVecEnv:
         self._tlist = z(n, tlist_cap, dtype=torch.int16)
         self._tmeta = z(8, n, dtype=torch.int32)
         self._sched = z(8, dtype=torch.int32)
+        self._worklist = z(n, dtype=torch.int32)   # scratch of the overlapped step
         # ---- observations / results ----
         self._obs_grid = z(n, 9, 11, 11, dtype=torch.int32) if self.grid_obs else None
         self._obs_target = z(n, 9, 11, 11, dtype=torch.int32) if self.target_in_obs else None
@@ -152,7 +153,8 @@ class IGLUVecEnv:
 
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._st = _lib.State(n, p(self._grid), p(self._init), p(self._target), p(self._pose),
-                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._tmeta), p(self._sched))
+                              p(self._init_pose), p(self._istate), p(self._tlist), p(self._tmeta), p(self._sched),
+                              p(self._worklist))
         self._ob = _lib.Obs(p(self._obs_grid), p(self._obs_target), p(self._obs_pos), p(self._obs_inv),
                             p(self._obs_compass), p(self._reward), p(self._done))
         cfg = _lib.Config(kind, int(self.select_and_place), self.max_steps, int(self.auto_reset),

@@ -82,7 +82,9 @@ typedef struct iglu_config {
                                    bit 2 = 1 forces the two-launch form; bit 3 = 1 deals the observe launch's env
                                    groups statically even when iglu_state.sched is given; bit 4 = 1 makes
                                    iglu_step_walking_host stage pinned buffers through copies too; bit 5 = 1 uses the
-                                   group-wise observe launch where the library would use the tiled one; bits 8-13:
+                                   group-wise observe launch where the library would use the tiled one; bit 6 = 1 turns
+                                   the overlapped step (widen next to the physics, then commit) off, bit 7 = 1 uses
+                                   it for small batches too; bits 8-13:
                                    envs per group of the group-wise observe launch (0 = automatic) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */
@@ -112,7 +114,10 @@ typedef struct iglu_state {
                                   w5: 1 if the starting grid is non-empty; w6: 1 once a task is set; w7: reserved */
     int32_t *sched;    /* [8] launch-to-launch scratch, or NULL = groups of envs are dealt statically. Word 0: work
                                   counter of the observe launch; words 2-3 (one uint64): running count of the
-                                  maximal_intersection evaluations the step calls performed (a caller may zero it) */
+                                  maximal_intersection evaluations the step calls performed (a caller may zero it);
+                                  words 4-5: counters of the overlapped step (left at zero by every step) */
+    int32_t *worklist; /* [n] scratch of the overlapped step (the envs a step edited or reset), or NULL = steps use
+                                  the two-launch / fused forms only */
 } iglu_state;
 
 /* Observation / result buffers (reference env.py:283-303). They persist between steps and are
@@ -315,6 +320,11 @@ int iglu_max_intersection_strided(const int8_t *grids, int64_t grid_stride, cons
 
 /* Number of kernels the last step call on this ctx launched (bench.py's gpu_launches claim). */
 int iglu_last_launch_count(const iglu_ctx *ctx);
+
+/* Tuning aid, no reference counterpart: with IGLU_B200_TRACE=1 in the environment when the ctx was created, the
+ * overlapped step brackets its three launches with timing events; this call waits for the last step and returns, in
+ * milliseconds after the start of the widen launch: widen end, physics start, physics end, commit start, commit end. */
+int iglu_debug_overlap_trace(iglu_ctx *ctx, float *out5);
 
 #ifdef __cplusplus
 }

@@ -247,17 +247,26 @@ def _tasks(rng, n):
     return T, S, poses
 
 
-@pytest.mark.parametrize('reward_mode,alternate,grid_obs', [('on_change', True, True), ('every_step', True, True),
-                                                            ('every_step', False, True),
-                                                            ('on_change', False, 'incremental'),
-                                                            ('every_step', True, 'incremental')])
-def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs):
+# scheduling switches of iglu_config.reserved (results identical): 128 = the overlapped step (k_widen next to the physics
+# launch, then k_commit) also for small batches, 64 = never; 32 = group-wise instead of tiled observe launch
+OVERLAP, NO_OVERLAP, GROUPWISE = 128, 64, 32
+
+
+@pytest.mark.parametrize('reward_mode,alternate,grid_obs,bits', [('on_change', True, True, 0), ('every_step', True, True, 0),
+                                                                 ('every_step', False, True, 0),
+                                                                 ('on_change', False, 'incremental', 0),
+                                                                 ('every_step', True, 'incremental', 0),
+                                                                 ('every_step', True, 'incremental', GROUPWISE),
+                                                                 ('every_step', True, False, 0),
+                                                                 ('on_change', True, True, OVERLAP),
+                                                                 ('every_step', True, True, OVERLAP)])
+def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs, bits):
     import gridworld_b200 as gw
     n, steps = 2048, 400
     rng = np.random.RandomState(3)
     T, S, poses = _tasks(rng, n)
     env = gw.make_vec(n, action_space='walking', max_steps=100, auto_reset=True, reward_mode=reward_mode,
-                      alternate_phases=alternate, grid_obs=grid_obs)
+                      alternate_phases=alternate, grid_obs=grid_obs, _sched_bits=bits)
     env.set_tasks(T, S, poses)
     orc = O.OracleBatch(n, 'walking', max_steps=100, threads=8)
     orc.set_tasks(T, S, poses)
@@ -280,14 +289,15 @@ def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs):
             assert np.array_equal(env.time_int_steps.cpu().numpy(), s['tis']), t
             o = orc.obs()
             ob = env.observation()
-            assert np.array_equal(ob['grid'].cpu().numpy(), o['grid']), t
+            if grid_obs:
+                assert np.array_equal(ob['grid'].cpu().numpy(), o['grid']), t
             assert np.array_equal(ob['agentPos'].cpu().numpy(), o['agentPos']), t
             assert np.array_equal(ob['compass'].cpu().numpy(), o['compass']), t
             assert np.array_equal(ob['inventory'].cpu().numpy(), o['inventory']), t
 
 
-@pytest.mark.parametrize('reward_mode', ['on_change', 'every_step'])
-def test_walking_zone_spanning_targets_vs_oracle(reward_mode):
+@pytest.mark.parametrize('reward_mode,bits', [('on_change', 0), ('every_step', 0), ('every_step', OVERLAP)])
+def test_walking_zone_spanning_targets_vs_oracle(reward_mode, bits):
     """Targets that span the zone in x and z admit one shift per rotation (task.py:57-72): the kernels then
     compare grid bytes directly instead of building occupancy rows. With and without starting grids."""
     import gridworld_b200 as gw
@@ -301,7 +311,7 @@ def test_walking_zone_spanning_targets_vs_oracle(reward_mode):
     T[:, 2:] = 0
     T[::4] = _synth(rng, len(T[::4]), 0.1, 'compact')  # a quarter keeps many shifts (row path in the same launch)
     _, S, poses = _tasks(rng, n)
-    env = gw.make_vec(n, max_steps=90, auto_reset=True, reward_mode=reward_mode)
+    env = gw.make_vec(n, max_steps=90, auto_reset=True, reward_mode=reward_mode, _sched_bits=bits)
     env.set_tasks(T, S, poses)
     orc = O.OracleBatch(n, 'walking', max_steps=90, threads=8)
     orc.set_tasks(T, S, poses)
@@ -318,12 +328,13 @@ def test_walking_zone_spanning_targets_vs_oracle(reward_mode):
     assert (s['max_int'] > 0).mean() > 0.1  # the scenario really scores
 
 
-def test_flying_batch_vs_oracle():
+@pytest.mark.parametrize('bits', [0, OVERLAP])
+def test_flying_batch_vs_oracle(bits):
     import gridworld_b200 as gw
     n, steps = 1024, 300
     rng = np.random.RandomState(5)
     T, S, poses = _tasks(rng, n)
-    env = gw.make_vec(n, action_space='flying', max_steps=120, auto_reset=True, target_in_obs=True)
+    env = gw.make_vec(n, action_space='flying', max_steps=120, auto_reset=True, target_in_obs=True, _sched_bits=bits)
     env.set_tasks(T, S, poses)
     orc = O.OracleBatch(n, 'flying', max_steps=120, threads=8)
     orc.set_tasks(T, S, poses)
@@ -425,15 +436,17 @@ def _pool(rng, m):
     return T, S
 
 
-@pytest.mark.parametrize('reward_mode,grid_obs', [('on_change', True), ('every_step', True),
-                                                  ('on_change', 'incremental')])
-def test_task_generator_batch_vs_oracle(reward_mode, grid_obs):
+@pytest.mark.parametrize('reward_mode,grid_obs,bits', [('on_change', True, 0), ('every_step', True, 0),
+                                                       ('on_change', 'incremental', 0), ('every_step', True, OVERLAP),
+                                                       ('on_change', True, OVERLAP)])
+def test_task_generator_batch_vs_oracle(reward_mode, grid_obs, bits):
     """Counter-based draws on device (fused and two-launch step forms) vs the oracle's restatement."""
     import gridworld_b200 as gw
     n, m, steps = 1536, 37, 260
     rng = np.random.RandomState(21)
     T, S = _pool(rng, m)
-    env = gw.make_vec(n, max_steps=24, auto_reset=True, reward_mode=reward_mode, grid_obs=grid_obs, target_in_obs=True)
+    env = gw.make_vec(n, max_steps=24, auto_reset=True, reward_mode=reward_mode, grid_obs=grid_obs, target_in_obs=True,
+                      _sched_bits=bits)
     env.set_task_pool(T, S, seed=0x1234567890ABCDEF, env_offset=5000)
     orc = O.OracleBatch(n, 'walking', max_steps=24, threads=8)
     orc.set_pool(T, S, seed=0x1234567890ABCDEF, env_offset=5000)
@@ -566,23 +579,23 @@ def test_step_host_routes():
         assert torch.equal(env.grid, ref.grid) and torch.equal(env._pose, ref._pose)
 
 
-@pytest.mark.parametrize('reward_mode', ['on_change', 'every_step'])
-def test_step_is_cuda_graph_capturable(reward_mode):
+@pytest.mark.parametrize('reward_mode,bits', [('on_change', 0), ('every_step', 0), ('every_step', OVERLAP)])
+def test_step_is_cuda_graph_capturable(reward_mode, bits):
     """The step entry points only enqueue work on the caller's stream (no allocation, no sync), so a sequence of
     steps can be captured once and replayed; replays equal eager stepping."""
     import gridworld_b200 as gw
     n, per = 700, 6
     rng = np.random.RandomState(41)
     T, S, poses = _tasks(rng, n)
-    eager = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+    eager = gw.make_vec(n, max_steps=20, reward_mode=reward_mode, _sched_bits=bits)
     eager.set_tasks(T, S, poses)
-    graphed = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+    graphed = gw.make_vec(n, max_steps=20, reward_mode=reward_mode, _sched_bits=bits)
     graphed.set_tasks(T, S, poses)
     acts = torch.zeros(per, n, dtype=torch.int32, device='cuda')  # static input buffer of the graph
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):  # warm-up on a side stream (lazy module loading must not happen during capture)
-        warm = gw.make_vec(n, max_steps=20, reward_mode=reward_mode)
+        warm = gw.make_vec(n, max_steps=20, reward_mode=reward_mode, _sched_bits=bits)
         warm.set_tasks(T, S, poses)
         warm.step(acts[0])
     torch.cuda.current_stream().wait_stream(side)

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from gridworld_b200 import _lib
     assert C.sizeof(_lib.Config) == 8 * 4 + 2 * 8
-    assert C.sizeof(_lib.State) == 8 * 10
+    assert C.sizeof(_lib.State) == 8 * 11
     assert C.sizeof(_lib.TaskPool) == 8 * 9
     assert C.sizeof(_lib.Obs) == 8 * 7
     assert _lib.GRID_STRIDE % 16 == 0 and _lib.GRID_STRIDE >= _lib.CELLS
