@@ -71,7 +71,7 @@ EXPORTS = ('iglu_abi_version', 'iglu_strerror', 'iglu_ctx_create', 'iglu_ctx_des
            'iglu_step_walking_host', 'iglu_max_intersection', 'iglu_last_launch_count',
            'iglu_task_pool_prepare', 'iglu_task_pool_attach', 'iglu_step_walking_host_async', 'iglu_wait',
            'iglu_fetch_env_host', 'iglu_max_intersection_strided', 'iglu_sample_tasks',
-           'iglu_staged_prepare', 'iglu_staged_step', 'iglu_debug_overlap_trace')
+           'iglu_staged_prepare', 'iglu_staged_step', 'iglu_debug_overlap_trace', 'iglu_render_pov')
 
 _lib = None
 
@@ -114,6 +114,8 @@ def load():
         L.iglu_staged_prepare.argtypes = [vp, C.POINTER(StagedTasks), vp, vp, vp]
         L.iglu_staged_step.argtypes = [vp, C.POINTER(State), C.POINTER(StagedTasks), vp, vp]
     L.iglu_last_launch_count.argtypes = [vp]
+    if hasattr(L, 'iglu_render_pov'):
+        L.iglu_render_pov.argtypes = [vp, C.POINTER(State), vp, i32, i32, vp, vp]
     if hasattr(L, 'iglu_debug_overlap_trace'):
         L.iglu_debug_overlap_trace.argtypes = [vp, vp]
     L.iglu_task_pool_prepare.argtypes = [vp, C.POINTER(TaskPool), vp, vp, vp]

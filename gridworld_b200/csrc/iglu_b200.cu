@@ -26,6 +26,7 @@
 #include "../../include/iglu_b200.h"
 #include "iglu_physics.cuh"
 #include "iglu_reward.cuh"
+#include "iglu_render.cuh"
 
 namespace iglu {
 
@@ -1087,6 +1088,27 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------ obs['pov'] (iglu_render.cuh)
+// One CTA per env: the grid row is staged in shared memory, every thread traces height * width / 256 pixels.
+__global__ void __launch_bounds__(256) k_render_pov(iglu_state st, uint8_t *__restrict__ pov, int height, int width,
+                                                    const uint8_t *__restrict__ atlas) {
+    __shared__ __align__(16) int8_t g8[GSTRIDE];
+    const int64_t e = blockIdx.x, n = st.n;
+    const int4 *src = reinterpret_cast<const int4 *>(st.grid + e * GSTRIDE);
+    for (int q = threadIdx.x; q < GSTRIDE / 16; q += blockDim.x) reinterpret_cast<int4 *>(g8)[q] = src[q];
+    const PovCamera cam = pov_camera(st.pose[0 * n + e], st.pose[1 * n + e], st.pose[2 * n + e], st.pose[3 * n + e],
+                                     st.pose[4 * n + e]);
+    __syncthreads();
+    const float kx = 2.0f / (float)width, ky = 2.0f / (float)height, aspect = (float)width / (float)height;
+    uint8_t *out = pov + e * (int64_t)height * width * 3;
+    for (int pix = threadIdx.x; pix < height * width; pix += blockDim.x) {
+        const int j = pix / width, i = pix - j * width;
+        const float sx = ((float)i + 0.5f) * kx - 1.0f, sy = 1.0f - ((float)j + 0.5f) * ky;
+        const uchar3 c = pov_trace(g8, atlas, cam, sx * aspect, sy);
+        out[3 * pix + 0] = c.x; out[3 * pix + 1] = c.y; out[3 * pix + 2] = c.z;
+    }
+}
+
 // ------------------------------------------------------------------ task preparation
 // Task.__init__ of the synthetic task (env.py:227-232, task.py:9-72) + Tasks.to_dense'd starting grid.
 // One warp per row.
@@ -1939,6 +1961,16 @@ static int launch_mi(const int8_t *grids, const int8_t *targets, const int8_t *f
     if (rc) return rc;
     k_max_intersection<WANT_KEY><<<grid, MI_WARPS * 32, smem, s>>>(grids, targets, fulls, gs, ts, fs, invariant, out,
                                                                   argmax, count);
+    return check(cudaPeekAtLastError());
+}
+
+extern "C" int iglu_render_pov(iglu_ctx *ctx, const iglu_state *st, uint8_t *pov, int height, int width,
+                               const uint8_t *atlas_rgba, void *stream) {
+    if (!ctx || !st || st->n <= 0 || !st->grid || !st->pose || !pov || height < 1 || width < 1 || height > 1024 ||
+        width > 1024)
+        return IGLU_ERR_INVALID_ARG;
+    k_render_pov<<<(unsigned)st->n, 256, 0, (cudaStream_t)stream>>>(*st, pov, height, width, atlas_rgba);
+    ctx->last_launches = 1;
     return check(cudaPeekAtLastError());
 }
 

@@ -3,7 +3,7 @@
 Mirrors reference gridworld/env.py: GridWorld (26-303), Wrapper (306-314), SizeReward (316-331),
 create_env (333-350) and the 'IGLUGridworld-v0' / 'IGLUGridworldVector-v0' registrations (352-362).
 Observations come back as numpy arrays with the reference's keys, dtypes and shapes; all state
-updates run in libiglu_b200.so on the GPU (no CPU fallback). render=True is not part of this path.
+updates run in libiglu_b200.so on the GPU (no CPU fallback). render=True adds obs['pov'] from a CUDA voxel ray caster.
 """
 import warnings
 
@@ -71,11 +71,11 @@ class GridWorld:
     def __init__(self, render=True, max_steps=250, select_and_place=False, discretize=False,
                  right_placement_scale=1., wrong_placement_scale=0.1, render_size=(64, 64),
                  target_in_obs=False, action_space='walking', vector_state=True, fake=False, name='',
-                 device='cuda'):
-        if render:
-            raise NotImplementedError(
-                "gridworld_b200 implements the render=False step path only; create the env with render=False")
+                 device='cuda', texture=None):
+        # render=True: obs['pov'] comes from the CUDA voxel ray caster (csrc/iglu_render.cuh), the stand-in for the
+        # reference's pyglet / OpenGL renderer; `texture` = the reference's texture atlas as an array (None = flat colours)
         self._vec = IGLUVecEnv(1, device=device, action_space=action_space, discretize=discretize,
+                               render=bool(render) and not fake, render_size=render_size, texture=texture,
                                select_and_place=select_and_place, max_steps=max_steps,
                                right_placement_scale=right_placement_scale,
                                wrong_placement_scale=wrong_placement_scale, target_in_obs=target_in_obs,
@@ -105,9 +105,13 @@ class GridWorld:
         self.initial_rotation = (0, 0)
         self.action_space = self._vec.action_space
         self.observation_space = self._vec.observation_space
+        if render and fake:   # env.py:93-94: the space has 'pov' even when the frames are fake samples
+            from .vec_env import make_observation_space
+            self.observation_space = make_observation_space(vector_state, target_in_obs, True,
+                                                            (int(render_size[1]), int(render_size[0])))
         self.max_int = 0
         self.name = name
-        self.do_render = False
+        self.do_render = bool(render)
         self.renderer = None
 
     @property
@@ -178,6 +182,10 @@ class GridWorld:
             obs['agentPos'] = as_np(sn.agent_pos).copy()
         if self.target_in_obs:
             obs['target_grid'] = as_np(sn.target_grid).reshape(9, 11, 11).copy()
+        if self.do_render and not self.fake:      # env.py:257-258, 299-300
+            obs['pov'] = self._vec._pov[0].cpu().numpy()
+        elif self.do_render:                      # env.py:259-260, 301-302
+            obs['pov'] = self.observation_space['pov'].sample()
         return obs
 
     def reset(self):
@@ -208,7 +216,10 @@ class GridWorld:
         return self._obs_numpy()
 
     def render(self):
-        raise ValueError('create env with render=True')
+        """env.py:263-266; RGB frame, uint8 [h, w, 3] (the reference returns RGBA and drops alpha for obs['pov'])"""
+        if not self.do_render or self.fake:
+            raise ValueError('create env with render=True')
+        return self._vec.render()[0].cpu().numpy()
 
     def step(self, action):
         """env.py:268-303"""

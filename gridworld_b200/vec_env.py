@@ -47,8 +47,8 @@ def make_action_space(action_space, discretize):
     raise ValueError(f'unknown action_space {action_space!r}')
 
 
-def make_observation_space(vector_state, target_in_obs):
-    """reference gridworld/env.py:79-95 (render=False: no 'pov')"""
+def make_observation_space(vector_state, target_in_obs, render=False, render_size=(64, 64)):
+    """reference gridworld/env.py:79-95"""
     sp = {'inventory': Box(low=0, high=20, shape=(6,), dtype=np.float32),
           'compass': Box(low=-180, high=180, shape=(1,), dtype=np.float32),
           'dialog': String()}
@@ -58,6 +58,8 @@ def make_observation_space(vector_state, target_in_obs):
         sp['grid'] = Box(low=-1, high=7, shape=(9, 11, 11), dtype=np.int32)
     if target_in_obs:
         sp['target_grid'] = Box(low=-1, high=7, shape=(9, 11, 11), dtype=np.int32)
+    if render:
+        sp['pov'] = Box(low=0, high=255, shape=(*render_size, 3), dtype=np.uint8)
     return Dict(sp)
 
 
@@ -74,7 +76,11 @@ class IGLUVecEnv:
       alternate_phases (scheduling only: in the fused launch half of the warps write observations before the
       physics), split_launch (scheduling only: True = the library's measured policy -- physics and
       observation/reward as two launches except for on_change reward with a full obs rewrite; False = always one
-      fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list).
+      fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list),
+      render / render_size / texture (render=True adds obs['pov'], uint8 [n, h, w, 3]: the reference's OpenGL frame
+      (render.py) restated as a voxel ray caster, one more launch per step / reset; texture = the reference's
+      128 x 128 RGBA atlas as an array (e.g. np.asarray(PIL.Image.open('gridworld/texture.png'))), None = flat
+      colours per block id).
 
     step() returns device tensors that alias persistent buffers: a policy reads them in place.
     set_tasks / set_task_pool / set_task_generator assign tasks (the latter two keep a device-resident generator
@@ -85,9 +91,7 @@ class IGLUVecEnv:
                  select_and_place=True, max_steps=250, right_placement_scale=1., wrong_placement_scale=0.1,
                  target_in_obs=False, vector_state=True, auto_reset=True, reward_mode='on_change',
                  grid_obs=True, render=False, max_target_blocks=_lib.TLIST_MAX, alternate_phases=None, split_launch=True,
-                 _sched_bits=0):
-        if render:
-            raise NotImplementedError('render=True (pov observation) is outside the B200 step path')
+                 render_size=(64, 64), texture=None, _sched_bits=0):
         if reward_mode not in ('on_change', 'every_step'):
             raise ValueError("reward_mode must be 'on_change' or 'every_step'")
         self.device = _require_cuda(device)
@@ -97,7 +101,10 @@ class IGLUVecEnv:
         self.action_space_type = action_space
         self.discretize = bool(discretize)
         self.action_space = make_action_space(action_space, discretize)
-        self.observation_space = make_observation_space(vector_state, target_in_obs)
+        self.do_render = bool(render)
+        self.render_size = (int(render_size[0]), int(render_size[1]))   # (width, height) as in the reference (env.py:109-111)
+        self.observation_space = make_observation_space(vector_state, target_in_obs, self.do_render,
+                                                        (self.render_size[1], self.render_size[0]))
         self.vector_state = bool(vector_state)
         self.target_in_obs = bool(target_in_obs)
         self.select_and_place = bool(select_and_place)
@@ -150,6 +157,13 @@ class IGLUVecEnv:
         self._reward = z(n, dtype=torch.float64)
         self._done = z(n, dtype=torch.uint8)
         self._actions_dev = z(n, dtype=torch.int32)
+        self._pov = z(n, self.render_size[1], self.render_size[0], 3, dtype=torch.uint8) if self.do_render else None
+        self._atlas = None
+        if self.do_render and texture is not None:
+            a = torch.as_tensor(np.ascontiguousarray(np.asarray(texture, dtype=np.uint8)))
+            if tuple(a.shape) != (128, 128, 4):
+                raise ValueError('texture must be the 128 x 128 RGBA atlas as a uint8 array [128, 128, 4]')
+            self._atlas = a.to(dev)
 
         p = lambda t: None if t is None else t.data_ptr()  # noqa: E731
         self._st = _lib.State(n, p(self._grid), p(self._init), p(self._target), p(self._pose),
@@ -406,11 +420,27 @@ class IGLUVecEnv:
             self._reset_seen = m.clone() if self._reset_seen is None else (self._reset_seen | m)
             if bool(self._reset_seen.all()):
                 self._was_reset, self._reset_seen = True, None
+        if self.do_render:
+            self.render()
         return self.observation()
 
     # ------------------------------------------------------------------ step
+    def render(self):
+        """obs['pov'] of every env for the current state (reference env.py:263-266 / render.py:128-156): uint8
+        [n, h, w, 3] on the device, written by one ray-casting launch."""
+        if not self.do_render:
+            raise ValueError('create env with render=True')
+        with self._guard():
+            _lib.check(self._L.iglu_render_pov(self._ctx, C.byref(self._st), self._pov.data_ptr(), self.render_size[1],
+                                               self.render_size[0], None if self._atlas is None else self._atlas.data_ptr(),
+                                               self._stream()))
+            self._count()
+        return self._pov
+
     def observation(self):
         obs = {'inventory': self._obs_inv, 'compass': self._obs_compass}
+        if self.do_render:
+            obs['pov'] = self._pov
         if self.vector_state:
             obs['agentPos'] = self._obs_pos
             obs['grid'] = self._obs_grid if self.grid_obs else self.grid
@@ -456,6 +486,8 @@ class IGLUVecEnv:
                 _lib.check(L.iglu_staged_step(self._ctx, st, C.byref(self._staged['struct']),
                                               self._pool['cursor'].data_ptr(), self._stream()))
                 self._count()
+        if self.do_render:   # env.py:299-300
+            self.render()
         return self.observation(), self._reward, self._done.view(torch.bool), {}
 
     def step_host(self, actions_host, reward_host, done_host, wait=True):
@@ -637,7 +669,6 @@ class IGLUVecEnv:
 def make_vec(num_envs, device='cuda', **kwargs):
     """Batched counterpart of gym.make('IGLUGridworld-v0', ...) (reference env.py:333-362)."""
     kwargs.pop('size_reward', None)
-    kwargs.pop('render_size', None)
     kwargs.pop('name', None)
     kwargs.pop('fake', None)
     return IGLUVecEnv(num_envs, device=device, **kwargs)

@@ -318,6 +318,15 @@ int iglu_max_intersection_strided(const int8_t *grids, int64_t grid_stride, cons
                                   int64_t target_stride, const int8_t *fulls, int64_t full_stride, int invariant,
                                   int32_t *out, int32_t *argmax, int64_t count, void *stream);
 
+/* obs['pov'] (reference: gridworld/render.py set_3d 94-113 / add_block 159-170, env.py:257-258, 299-300: the RGB
+ * frame of the OpenGL renderer, 64 x 64 by default): a voxel ray caster over every env's grid and pose -- 90 degree
+ * vertical field of view, near 0.1 / far 30, cubes seen from outside only (GL_CULL_FACE), top-only floor, nearest texel,
+ * clear colour (0.5, 0.69, 1.0); the restatement is spelled out in csrc/iglu_render.cuh. pov: uint8 [n][height][width][3]
+ * on the device, rows top-down. atlas_rgba: the 128 x 128 RGBA texture atlas (gridworld/texture.png as an array
+ * [128][128][4], rows top-down) on the device, or NULL = flat colours per block id. Enqueues one kernel. */
+int iglu_render_pov(iglu_ctx *ctx, const iglu_state *st, uint8_t *pov, int height, int width, const uint8_t *atlas_rgba,
+                    void *stream);
+
 /* Number of kernels the last step call on this ctx launched (bench.py's gpu_launches claim). */
 int iglu_last_launch_count(const iglu_ctx *ctx);
 

@@ -913,3 +913,124 @@ void orc_staged_step(orc_staged *s, const int8_t *grid, int32_t *out /* right, w
     }
     out[0] = right; out[1] = wrong; out[2] = done; out[3] = s->task_goal; out[4] = s->cur.max_int;
 }
+
+/* ------------------------------------------------------------------ obs['pov']
+ * Restatement of what the reference's OpenGL renderer draws (gridworld/render.py: set_3d 94-113 -- gluPerspective(90,
+ * w / h, 0.1, 30), glRotatef(yaw, 0,1,0), glRotatef(-pitch, cos yaw, 0, sin yaw), glTranslatef(-pos); setup 42-50 --
+ * clear colour (0.5, 0.69, 1.0), GL_CULL_FACE, GL_NEAREST; add_block 159-170 -- cubes with all six faces, floor blocks
+ * top-only; gridworld/utils.py: cube_vertices 26-41, tex_coord / tex_coords 75-118, id2texture 130-139) as one ray per
+ * pixel centre. PARITY UNPINNED against OpenGL itself: no GL context can be created in the build container, so this
+ * function is checked by known answers (tests/test_oracle_golden.py) and serves as the bit-exact twin of the CUDA ray
+ * caster (csrc/iglu_render.cuh): fp32, same operation order, no FMA contraction.
+ * grid: int8 [CELLS]; pose: x, y, z, yaw, pitch; atlas: [128][128][4] RGBA rows top-down, or NULL = flat palette;
+ * out: uint8 [height][width][3], rows top-down (render()[::-1][..., :-1], render.py:139-146, env.py:258). */
+static const uint8_t POV_PALETTE[8][3] = {{245, 245, 245}, {70, 72, 76}, {0, 90, 128}, {17, 101, 36},
+                                          {133, 16, 17},   {146, 71, 22}, {92, 37, 96}, {145, 137, 0}};
+
+static void pov_texel(const uint8_t *atlas, int id, int qx, int qy, float u, float v, uint8_t *rgb) {
+    if (!atlas) { memcpy(rgb, POV_PALETTE[id + 1], 3); return; }
+    static const int TX[8] = {0, 1, 2, 3, 0, 1, 2, 3}, TY[8] = {0, 0, 0, 0, 1, 1, 1, 1}; /* utils.py:130-139, index id + 1 */
+    const int res = id <= 0 ? 32 : 16; /* whole tile on the floor (split=False), a quarter per face otherwise */
+    int tu = (int)(u * (float)res), tv = (int)(v * (float)res);
+    tu = tu < 0 ? 0 : (tu > res - 1 ? res - 1 : tu);
+    tv = tv < 0 ? 0 : (tv > res - 1 ? res - 1 : tv);
+    const int tx = 32 * TX[id + 1] + (id <= 0 ? 0 : qx) + tu, ty = 32 * TY[id + 1] + (id <= 0 ? 0 : qy) + tv;
+    memcpy(rgb, atlas + ((127 - ty) * 128 + tx) * 4, 3); /* texture origin is bottom-left */
+}
+
+void orc_render_pov(const int8_t *grid, const double *pose, int height, int width, const uint8_t *atlas, uint8_t *out) {
+    const double yaw = pose[3], pitch = pose[4];
+    const double sy_ = sin(py_radians(yaw)), cy = cos(py_radians(yaw)), sp = sin(py_radians(pitch)), cp = cos(py_radians(pitch));
+    const float o[3] = {(float)pose[0], (float)pose[1], (float)pose[2]};
+    const float f[3] = {(float)(sy_ * cp), (float)sp, (float)(-(cy * cp))}; /* sight vector, world.py:145-161 */
+    const float rx = (float)cy, rz = (float)sy_;                            /* camera x axis after the yaw rotation */
+    const float u3[3] = {-(rz * f[1]), rz * f[0] - rx * f[2], rx * f[1]};   /* up = right x forward */
+    const float kx = 2.0f / (float)width, ky = 2.0f / (float)height, aspect = (float)width / (float)height;
+    const float lo[3] = {-5.5f, -1.5f, -5.5f};
+    const int dim[3] = {GX, GY, GZ};
+    for (int j = 0; j < height; j++)
+        for (int i = 0; i < width; i++) {
+            uint8_t *px_out = out + 3 * (j * width + i);
+            const float sx = ((float)i + 0.5f) * kx - 1.0f, sy = 1.0f - ((float)j + 0.5f) * ky, sxa = sx * aspect;
+            const float d[3] = {(f[0] + sxa * rx) + sy * u3[0], f[1] + sy * u3[1], (f[2] + sxa * rz) + sy * u3[2]};
+            float best_t = 30.0f;
+            px_out[0] = 128; px_out[1] = 176; px_out[2] = 255; /* glClearColor(0.5, 0.69, 1.0) */
+            if (d[1] < 0.0f && o[1] > -1.5f) { /* floor: top faces at y = -2 + 0.5, seen from above only */
+                const float t = (-1.5f - o[1]) / d[1];
+                const float px = o[0] + d[0] * t, pz = o[2] + d[2] * t;
+                if (t >= 0.1f && t <= best_t && px >= -18.5f && px <= 18.5f && pz >= -18.5f && pz <= 18.5f) {
+                    const float cx = floorf(px + 0.5f), cz = floorf(pz + 0.5f);
+                    const int id = (cx >= -5.0f && cx <= 5.0f && cz >= -5.0f && cz <= 5.0f) ? WHITE : GREY; /* world.py:60-71 */
+                    pov_texel(atlas, id, 0, 0, pz - (cz - 0.5f), px - (cx - 0.5f), px_out);
+                    best_t = t;
+                }
+            }
+            float t_in = 0.0f, t_out = best_t;
+            int axis_in = -1, miss = 0;
+            for (int a = 0; a < 3; a++) {
+                const float hi = lo[a] + (float)dim[a];
+                if (d[a] != 0.0f) {
+                    const float t1 = (lo[a] - o[a]) / d[a], t2 = (hi - o[a]) / d[a];
+                    const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
+                    if (tn > t_in) { t_in = tn; axis_in = a; }
+                    t_out = fminf(t_out, tf);
+                } else if (o[a] < lo[a] || o[a] > hi) {
+                    miss = 1;
+                }
+            }
+            if (miss || t_in > t_out) continue;
+            int cell[3], step[3];
+            float t_max[3], t_delta[3];
+            for (int a = 0; a < 3; a++) {
+                const float p = (o[a] + d[a] * t_in) - lo[a];
+                int ci = (int)floorf(p);
+                ci = ci < 0 ? 0 : (ci > dim[a] - 1 ? dim[a] - 1 : ci);
+                if (a == axis_in) ci = d[a] > 0.0f ? 0 : dim[a] - 1;
+                cell[a] = ci;
+                step[a] = d[a] > 0.0f ? 1 : -1;
+                if (d[a] != 0.0f) {
+                    const float bound = lo[a] + (float)(ci + (d[a] > 0.0f ? 1 : 0));
+                    t_max[a] = (bound - o[a]) / d[a];
+                    t_delta[a] = fabsf(1.0f / d[a]);
+                } else {
+                    t_max[a] = 3.0e38f;
+                    t_delta[a] = 0.0f;
+                }
+            }
+            int axis = axis_in; /* face the current cell was entered through; -1: the eye is inside the zone */
+            float t = t_in;
+            for (int it = 0; it < 40; it++) {
+                if (axis >= 0 && t >= 0.1f) { /* a cube is seen from outside, in front of the near plane */
+                    if (t > best_t) break;
+                    const int v = grid[cell[1] * 121 + cell[0] * 11 + cell[2]];
+                    if (v != 0) {
+                        const int id = v < -1 ? 0 : (v > 6 ? 6 : v);
+                        const float px = o[0] + d[0] * t, py = o[1] + d[1] * t, pz = o[2] + d[2] * t;
+                        const float X = (float)(cell[0] - 5), Y = (float)(cell[1] - 1), Z = (float)(cell[2] - 5);
+                        float u, w;
+                        int qx, qy;
+                        if (axis == 1) { /* cube_vertices: top / bottom */
+                            if (step[1] < 0) { u = pz - (Z - 0.5f); w = px - (X - 0.5f); qx = 0; qy = 16; }
+                            else { u = px - (X - 0.5f); w = pz - (Z - 0.5f); qx = 16; qy = 0; }
+                        } else if (axis == 0) { /* left (-x) / right (+x) */
+                            if (step[0] > 0) { u = pz - (Z - 0.5f); w = py - (Y - 0.5f); }
+                            else { u = (Z + 0.5f) - pz; w = py - (Y - 0.5f); }
+                            qx = 0; qy = 0;
+                        } else { /* front (+z) / back (-z) */
+                            if (step[2] < 0) { u = px - (X - 0.5f); w = py - (Y - 0.5f); }
+                            else { u = (X + 0.5f) - px; w = py - (Y - 0.5f); }
+                            qx = 16; qy = 16;
+                        }
+                        pov_texel(atlas, id, qx, qy, u, w, px_out);
+                        break;
+                    }
+                }
+                axis = (t_max[0] <= t_max[1] && t_max[0] <= t_max[2]) ? 0 : (t_max[1] <= t_max[2] ? 1 : 2);
+                t = t_max[axis];
+                if (t > t_out) break;
+                cell[axis] += step[axis];
+                if (cell[axis] < 0 || cell[axis] >= dim[axis]) break;
+                t_max[axis] += t_delta[axis];
+            }
+        }
+}

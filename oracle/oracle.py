@@ -58,6 +58,7 @@ def lib():
         L.orc_staged_reset.argtypes = [vp, i32]
         L.orc_staged_step.argtypes = [vp, vp, vp]
         L.orc_sample_tasks.argtypes = [vp, i64, i32, i32, i32, i32, C.c_uint64, i64]
+        L.orc_render_pov.argtypes = [vp, vp, i32, i32, vp, vp]
         _lib = L
     return _lib
 
@@ -242,3 +243,14 @@ class Staged:
         if getattr(self, '_h', None) and _lib is not None:
             _lib.orc_staged_destroy(self._h)
             self._h = None
+
+
+def render_pov(grid, pose, height=64, width=64, atlas=None):
+    """obs['pov'] of one env (orc_render_pov: the ray-cast restatement of gridworld/render.py). grid: int8 [9, 11, 11];
+    pose: (x, y, z, yaw, pitch); atlas: uint8 [128, 128, 4] (texture.png, rows top-down) or None = flat palette."""
+    g = _i8(grid, (CELLS,))
+    p = np.ascontiguousarray(np.asarray(pose, np.float64).reshape(5))
+    a = None if atlas is None else np.ascontiguousarray(np.asarray(atlas, np.uint8).reshape(128, 128, 4))
+    out = np.zeros((int(height), int(width), 3), np.uint8)
+    lib().orc_render_pov(_p(g), _p(p), int(height), int(width), None if a is None else _p(a), _p(out))
+    return out

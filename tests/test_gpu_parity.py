@@ -1050,3 +1050,72 @@ def test_staged_tasks_golden_on_device():
             rr, ww, dd, goal, _ = orcs[e][0].step(grids[e])
             assert (sg['right'][e], sg['wrong'][e], int(sg['done'][e]), sg['goal'][e] - base[orcs[e][1]]) == \
                 (rr, ww, dd, goal), (t, e)
+
+
+def _coded_atlas(rng):
+    a = rng.randint(0, 256, (128, 128, 4)).astype(np.uint8)
+    a[..., 3] = 255
+    return a
+
+
+@pytest.mark.parametrize('with_atlas,size', [(False, (64, 64)), (True, (64, 64)), (True, (48, 32))])
+def test_render_pov_vs_oracle(with_atlas, size):
+    """obs['pov'] (csrc/iglu_render.cuh) against its C restatement, bit for bit, on random worlds and poses whose angles
+    are multiples of 5 degrees (host-libm trig table); arbitrary angles may flip a pixel on a face edge."""
+    import gridworld_b200 as gw
+    n = 160
+    rng = np.random.RandomState(77)
+    atlas = _coded_atlas(rng) if with_atlas else None
+    S = _synth(rng, n, 0.08, 'full')
+    S[:n // 4] = 0
+    T = _synth(rng, n, 0.1, 'compact')
+    poses = np.zeros((n, 5))
+    poses[:, 0] = rng.randint(-28, 29, n) * 0.25
+    poses[:, 1] = rng.randint(-6, 37, n) * 0.25
+    poses[:, 2] = rng.randint(-28, 29, n) * 0.25
+    poses[:, 3] = rng.randint(0, 72, n) * 5.0
+    poses[:, 4] = rng.randint(-18, 19, n) * 5.0
+    poses[n // 2:, 3:] += rng.uniform(-2.4, 2.4, (n - n // 2, 2))       # second half: arbitrary angles
+    poses[:, 4] = np.clip(poses[:, 4], -90, 90)
+    env = gw.make_vec(n, max_steps=50, render=True, render_size=size, texture=atlas, auto_reset=False)
+    env.set_tasks(T, S, poses)
+    obs = env.reset()
+    w, h = size
+    assert obs['pov'].shape == (n, h, w, 3) and obs['pov'].dtype == torch.uint8
+    pov = obs['pov'].cpu().numpy()
+    bad = 0
+    for e in range(n):
+        want = O.render_pov(S[e], poses[e], h, w, atlas)
+        if e < n // 2:
+            assert np.array_equal(pov[e], want), e
+        else:
+            bad += int((pov[e] != want).any(axis=2).sum())
+    assert bad <= 1e-3 * (n // 2) * h * w, bad
+    assert len(np.unique(pov.reshape(-1, 3), axis=0)) > (20 if with_atlas else 5)     # the frames really show things
+    # after a few steps (walking actions keep the angles on the 5 degree lattice for the first half)
+    for t in range(6):
+        obs, _, _, _ = env.step(rng.randint(0, 18, n).astype(np.int32))
+    pov = obs['pov'].cpu().numpy()
+    grid = env.grid.cpu().numpy()
+    pos, rot = env.position.cpu().numpy(), env.rotation.cpu().numpy()
+    for e in range(n // 2):
+        want = O.render_pov(grid[e], (*pos[e], *rot[e]), h, w, atlas)
+        assert np.array_equal(pov[e], want), e
+
+
+def test_render_pov_dropin_surface():
+    """gym surface with render=True (reference env.py:93-94, 257-258, 299-300): obs['pov'] uint8 (64, 64, 3)."""
+    import gridworld_b200 as gw
+    env = gw.GridWorld(render=True, vector_state=True, discretize=True, select_and_place=True, max_steps=20)
+    assert env.observation_space['pov'].shape == (64, 64, 3)
+    env.set_task(gw.Task('', gw.Tasks.to_dense([(0, 0, -3, 3)]), starting_grid=[(0, 0, -3, 3), (1, 0, -2, 5)]))
+    obs = env.reset()
+    assert obs['pov'].shape == (64, 64, 3) and obs['pov'].dtype == np.uint8
+    want = O.render_pov(env.grid, (0, 0, 0, 0, 0))
+    assert np.array_equal(obs['pov'], want)
+    obs, _, _, _ = env.step(13)            # turn the camera: the frame follows
+    assert np.array_equal(obs['pov'], O.render_pov(env.grid, (*env.agent.position, *env.agent.rotation)))
+    assert not np.array_equal(obs['pov'], want)
+    assert np.array_equal(env.render(), obs['pov'])
+    fake = gw.GridWorld(render=True, fake=True, vector_state=True, discretize=True)
+    assert 'pov' in fake.observation_space.spaces

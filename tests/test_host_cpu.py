@@ -47,7 +47,7 @@ def test_no_cpu_fallback():
         gw.make('IGLUGridworld-v0', render=False)
     with pytest.raises(RuntimeError):
         gw.max_intersection(np.zeros((1, 9, 11, 11)), np.zeros((1, 9, 11, 11)))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
         gw.GridWorld(render=True)
 
 

@@ -236,3 +236,62 @@ def test_staged_tasks_golden():
         want = (int(z['right'][i]), int(z['wrong'][i]), int(z['done'][i]), int(z['goal'][i]), int(z['max_int'][i]))
         assert got == want, (i, got, want)
     assert set(z['goal'].tolist()) == {0, 1, 2, 3}   # every turn incl. the one past the last was reached
+
+
+def _coded_atlas():
+    """A 128 x 128 RGBA atlas whose texel (tx, ty) -- ty counted from the BOTTOM like OpenGL -- holds (tx, ty, 7)."""
+    a = np.zeros((128, 128, 4), np.uint8)
+    ty, tx = np.meshgrid(np.arange(128), np.arange(128), indexing='ij')
+    a[127 - ty, tx, 0] = tx
+    a[127 - ty, tx, 1] = ty
+    a[..., 2] = 7
+    a[..., 3] = 255
+    return a
+
+
+def test_render_pov_known_answers():
+    """obs['pov'] restatement (reference gridworld/render.py:94-113, 159-170; utils.py:26-41, 75-139): answers that
+    follow from the camera / geometry / texture rules by hand."""
+    SKY, WHITE_, GREY_, RED_ = (128, 176, 255), (245, 245, 245), (70, 72, 76), (133, 16, 17)
+    empty = np.zeros((9, 11, 11), np.int8)
+    # straight up: only sky; straight down from the origin: only the white build-zone floor (1.5 below, 90 degree fov)
+    assert (O.render_pov(empty, (0, 0, 0, 0, 90)) == SKY).all()
+    assert (O.render_pov(empty, (0, 0, 0, 35, -90)) == WHITE_).all()
+    # level view: sky above the horizon and just under it (row 33: the floor lies beyond the far plane, 1.5 / (1.5 / 32)
+    # = 32 > 30; row 34: beyond the floor's edge, 19.2 > 18.5), then grey floor, white build-zone floor near the bottom
+    img = O.render_pov(empty, (0, 0, 0, 0, 0))
+    assert (img[:35] == SKY).all() and (img[35] == GREY_).all() and (img[63] == WHITE_).all()
+    # below the floor nothing is drawn (top faces are culled from underneath)
+    assert (O.render_pov(empty, (0, -3, 0, 0, -45)) == SKY).all()
+    # one red block at (0, -1, -3), i.e. its front face 2.5 ahead of an eye at the origin looking along -z: the face
+    # spans sx in [-0.2, 0.2] -> columns 26..37 and sy in [-0.6, -0.2] -> rows 38..50; its top face (y = -0.5, seen from
+    # above) fills sy in [-0.2, -0.5 / 3.5] -> row 37, columns 27..36 (half-width 0.5 / 3.06 at that depth)
+    g = empty.copy()
+    g[0, 5, 2] = 3
+    img = O.render_pov(g, (0, 0, 0, 0, 0))
+    red = (img == RED_).all(axis=2)
+    ys, xs = np.nonzero(red)
+    assert (xs.min(), xs.max(), ys.min(), ys.max()) == (26, 37, 37, 50), (xs.min(), xs.max(), ys.min(), ys.max())
+    assert np.array_equal(np.nonzero(red[37])[0], np.arange(27, 37)) and red[38:51, 26:38].all()
+    assert (red[:, :32] == red[:, :31:-1]).all()              # mirror symmetry
+    # the same block seen after turning: yaw 90 looks along +x, so the block has to be at x = +3 to show the same picture
+    g2 = empty.copy()
+    g2[0, 8, 5] = 3
+    # (cos 90 degrees is 6e-17, not 0, in fp64: a couple of pixels on face edges may flip)
+    assert (O.render_pov(g2, (0, 0, 0, 90, 0)) != img).any(axis=2).sum() <= 4
+    # inside a block (or closer than the near plane to its face) the block is not seen
+    g3 = empty.copy()
+    g3[1, 5, 5] = 3                                           # the cell the eye is in
+    assert np.array_equal(O.render_pov(g3, (0, 0, 0, 0, 0)), O.render_pov(empty, (0, 0, 0, 0, 0)))
+    # texel addressing: white floor tile (0, 0) uses the whole 32 x 32 tile, u with z and v with x
+    atlas = _coded_atlas()
+    img = O.render_pov(empty, (0.25, 0, -0.25, 0, -90), atlas=atlas)
+    c = img[32, 32]                                           # ray through (0.25 + eps, -1.5, -0.25 + eps') of cell (0, 0)
+    assert c[2] == 7 and c[0] in (7, 8) and c[1] in (23, 24), c     # u = z + .5 = .25 -> texel 8; v = x + .5 = .75 -> 24
+    # a colour block's side faces use quarter (0, 0) of its tile, the top quarter (0, 16): RED is tile (0, 1)
+    img = O.render_pov(g, (0, -1, 0, 0, 0), atlas=atlas)      # eye level with the block centre: its front (+z) face
+    c = img[32, 32]
+    assert 16 <= c[0] < 32 and 32 + 16 <= c[1] < 64, c        # front / back faces: quarter (16, 16) of tile (0, 1)
+    img = O.render_pov(g, (0, 3, -3, 0, -90), atlas=atlas)    # from above: top face, quarter (0, 16)
+    c = img[32, 32]
+    assert 0 <= c[0] < 16 and 32 + 16 <= c[1] < 64, c
