@@ -1021,6 +1021,10 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_co
     CommitWarp *scratch = reinterpret_cast<CommitWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     CommitWarp &ws = scratch[wid];
+    // the list length and this warp's first entry are asked for before the set-up below: their latency hides behind it
+    const int count = p.st.sched[4];
+    const int k0 = wid * (int)gridDim.x + (int)blockIdx.x;
+    int64_t e_first = k0 < count ? p.st.worklist[k0] : 0;
     for (int q = tid; q < CELL_LUT_N / 2; q += COMMIT_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -1030,12 +1034,11 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_co
     }
     __syncthreads();
     const int64_t n = p.st.n;
-    const int count = p.st.sched[4];
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     Ring<1, CommitWarp, false> ring(p, ws, lut, lane);
     int counted = 0;
-    for (int k = wid * (int)gridDim.x + (int)blockIdx.x; k < count; k += (int)gridDim.x * COMMIT_WARPS) {
-        const int64_t e = p.st.worklist[k];
+    for (int k = k0; k < count; k += (int)gridDim.x * COMMIT_WARPS) {
+        const int64_t e = k == k0 ? e_first : (int64_t)p.st.worklist[k];
         ring.issue(e, true);   // grid row + rectangle header: asked for before the env's words (one round trip less)
         // warp-uniform loads (one transaction each)
         const int w3 = p.st.istate[3 * n + e], step_no = p.st.istate[4 * n + e], dsize = p.st.istate[5 * n + e];
