@@ -216,6 +216,9 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #ifndef IGLU_OBS_DYN_GROUP
 #define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
 #endif
+#ifndef IGLU_PHYS_CTAS
+#define IGLU_PHYS_CTAS 4       // 4-warp CTAs of the physics launch per SM the register budget is set for (4: 128 registers)
+#endif
 template <int PHASES> struct StepCfg {
     static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
     static constexpr int NBUF = PHASES == 2 ? IGLU_OBS_RING : NB;
@@ -230,7 +233,7 @@ template <int PHASES> constexpr size_t step_smem_bytes() {
 }
 
 template <int KIND, int PHASES>
-__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (PHASES == 2 ? IGLU_OBS_CTAS : CTAS_PER_SM)) k_step(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? IGLU_PHYS_CTAS : (PHASES == 2 ? IGLU_OBS_CTAS : CTAS_PER_SM)) k_step(const __grid_constant__ StepParams p) {
     constexpr int WPC = StepCfg<PHASES>::WPC;
     constexpr int NBUF = StepCfg<PHASES>::NBUF;
     constexpr bool HAS_A = PHASES != 2, HAS_B = PHASES != 1;
@@ -596,7 +599,12 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? 4 : (
                 int b = 0;
                 if (lane == 0) b = atomicAdd(p.st.sched + 4, __popc(sm));
                 b = __shfl_sync(0xffffffffu, b, 0);
-                if (special) p.st.worklist[b + __popc(sm & ((1u << lane) - 1u))] = (int32_t)i;
+                if (special) {   // one 32-byte record per listed env: everything k_commit needs except the grid
+                    int4 *rec = reinterpret_cast<int4 *>(p.st.worklist) + 2 * (int64_t)(b + __popc(sm & ((1u << lane) - 1u)));
+                    rec[0] = make_int4((int)i, (a.active & 0xFF) | ((a.tis & 0xFF) << 8) | ((a.err & 0xFF) << 24), step_no, dsize);
+                    rec[1] = make_int4(max_int, pack_w7(dsize_old - dsize, edit_cell, edit_val, do_reset),
+                                       nblk | ((int)has_start << 16), target_size);
+                }
             }
         }
         grp = dynamic ? (int64_t)__shfl_sync(0xffffffffu, grp_next, 0) : grp + (int64_t)gridDim.x * WPC;
@@ -885,7 +893,10 @@ struct __align__(16) WidenWarp {
     EvalScratch es;
     unsigned long long bar[IGLU_WIDEN_RING];
 };
-constexpr int WIDEN_WARPS = 16;
+#ifndef IGLU_WIDEN_WARPS
+#define IGLU_WIDEN_WARPS 16
+#endif
+constexpr int WIDEN_WARPS = IGLU_WIDEN_WARPS;
 constexpr size_t widen_smem_bytes() { return TABLE_BYTES + WIDEN_WARPS * sizeof(WidenWarp); }
 
 // Shared by k_widen / k_commit: ring producer and consumer over a warp's slots (see k_observe).
@@ -1012,19 +1023,21 @@ struct __align__(16) CommitWarp {
     unsigned long long bar[1];
     unsigned long long pad;
 };
-constexpr int COMMIT_WARPS = 16;
+constexpr int COMMIT_WARPS = 4;    // small CTAs: they start and retire independently (the launch is a latency chain)
 constexpr size_t commit_smem_bytes() { return TABLE_BYTES + COMMIT_WARPS * sizeof(CommitWarp); }
 
-__global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(COMMIT_WARPS * 32, 8) k_commit(const __grid_constant__ StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
     CommitWarp *scratch = reinterpret_cast<CommitWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     CommitWarp &ws = scratch[wid];
-    // the list length and this warp's first entry are asked for before the set-up below: their latency hides behind it
+    // the list length and this warp's first record are asked for before the set-up below: their latency hides behind it
     const int count = p.st.sched[4];
-    const int k0 = wid * (int)gridDim.x + (int)blockIdx.x;
-    int64_t e_first = k0 < count ? p.st.worklist[k0] : 0;
+    const int4 *recs = reinterpret_cast<const int4 *>(p.st.worklist);
+    const int k0 = wid * (int)gridDim.x + (int)blockIdx.x, kstep = (int)gridDim.x * COMMIT_WARPS;
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    if ((int64_t)k0 < p.st.n) { r0 = recs[2 * (int64_t)k0]; r1 = recs[2 * (int64_t)k0 + 1]; }   // valid iff k0 < count
     for (int q = tid; q < CELL_LUT_N / 2; q += COMMIT_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -1037,13 +1050,12 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_co
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     Ring<1, CommitWarp, false> ring(p, ws, lut, lane);
     int counted = 0;
-    for (int k = k0; k < count; k += (int)gridDim.x * COMMIT_WARPS) {
-        const int64_t e = k == k0 ? e_first : (int64_t)p.st.worklist[k];
-        ring.issue(e, true);   // grid row + rectangle header: asked for before the env's words (one round trip less)
-        // warp-uniform loads (one transaction each)
-        const int w3 = p.st.istate[3 * n + e], step_no = p.st.istate[4 * n + e], dsize = p.st.istate[5 * n + e];
-        const int max_int = p.st.istate[6 * n + e], w7 = p.st.istate[7 * n + e];
-        const int nblk = p.st.tmeta[0 * n + e], target_size = p.st.tmeta[1 * n + e], has_start = p.st.tmeta[5 * n + e];
+    for (int k = k0; k < count; k += kstep) {
+        if (k != k0) { r0 = recs[2 * (int64_t)k]; r1 = recs[2 * (int64_t)k + 1]; }
+        const int64_t e = r0.x;
+        ring.issue(e, true);   // grid row + rectangle header
+        const int w3 = r0.y, step_no = r0.z, dsize = r0.w, max_int = r1.x, w7 = r1.y;
+        const int nblk = r1.z & 0xFFFF, has_start = r1.z >> 16, target_size = r1.w;
         const int wrong = (w7 << 30) >> 30;              // sign-extended 2 bits
         const int edit_cell = ((w7 >> 2) & 0x7FF) - 1, edit_val = (w7 >> 13) & 15;
         const bool reset = (w7 >> 17) & 1;
@@ -1084,8 +1096,7 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 2) k_commit(const __grid_co
     ring.evals = 0;
     // the last CTA out leaves the launch-to-launch counters at zero for the next step
     __syncthreads();
-    if (tid == 0) {
-        __threadfence();
+    if (tid == 0) {   // (every CTA's ticket follows its own use of `count`: the last one may clear it)
         const int t = atomicAdd(p.st.sched + 5, 1);
         if (t == (int)gridDim.x - 1) { p.st.sched[0] = 0; p.st.sched[4] = 0; p.st.sched[5] = 0; }
     }
@@ -1748,7 +1759,7 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         if (!rc) rc = check(cudaStreamWaitEvent(s, ctx->join, 0));
         if (rc) return rc;
         const int64_t ctas_c = (n / 8 + COMMIT_WARPS - 1) / COMMIT_WARPS;   // ~1 listed env in 14: about one per warp
-        const int64_t max_c = (int64_t)ctx->num_sms * 2;
+        const int64_t max_c = (int64_t)ctx->num_sms * 8;
         if (tr) cudaEventRecord(ctx->trace[4], s);
         k_commit<<<(unsigned)(ctas_c < max_c ? (ctas_c > 0 ? ctas_c : 1) : max_c), COMMIT_WARPS * 32, commit_smem_bytes(), s>>>(p);
         if (tr) cudaEventRecord(ctx->trace[5], s);

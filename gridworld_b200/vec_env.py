@@ -147,7 +147,7 @@ class IGLUVecEnv:
         self._tlist = z(n, tlist_cap, dtype=torch.int16)
         self._tmeta = z(8, n, dtype=torch.int32)
         self._sched = z(8, dtype=torch.int32)
-        self._worklist = z(n, dtype=torch.int32)   # scratch of the overlapped step
+        self._worklist = z(8, n, dtype=torch.int32)   # scratch of the overlapped step
         # ---- observations / results ----
         self._obs_grid = z(n, 9, 11, 11, dtype=torch.int32) if self.grid_obs else None
         self._obs_target = z(n, 9, 11, 11, dtype=torch.int32) if self.target_in_obs else None

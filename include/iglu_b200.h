@@ -116,8 +116,8 @@ typedef struct iglu_state {
                                   counter of the observe launch; words 2-3 (one uint64): running count of the
                                   maximal_intersection evaluations the step calls performed (a caller may zero it);
                                   words 4-5: counters of the overlapped step (left at zero by every step) */
-    int32_t *worklist; /* [n] scratch of the overlapped step (the envs a step edited or reset), or NULL = steps use
-                                  the two-launch / fused forms only */
+    int32_t *worklist; /* [8][n] scratch of the overlapped step (a 32-byte record per env a step edited or reset;
+                                  16-byte aligned), or NULL = steps use the two-launch / fused forms only */
 } iglu_state;
 
 /* Observation / result buffers (reference env.py:283-303). They persist between steps and are
