@@ -1,6 +1,4 @@
-mkdir -p gpurun_out; : > gpurun_out/r2u_tune.jsonl
-timeout 300 python scripts/tune_r2.py default >> gpurun_out/r2u_tune.jsonl 2>gpurun_out/r2u_tune.err
-for v in p5w16 p6w16 p5w12 p6w12 p8w16; do
-  IGLU_B200_SO=$PWD/gridworld_b200/csrc/libiglu_b200_$v.so timeout 300 python scripts/tune_r2.py $v >> gpurun_out/r2u_tune.jsonl 2>>gpurun_out/r2u_tune.err
-done
-cut -c1-200 gpurun_out/r2u_tune.jsonl; tail -3 gpurun_out/r2u_tune.err
+mkdir -p gpurun_out
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 200 --warmup 10 > gpurun_out/r2v_bench_2gpu.log 2> gpurun_out/r2v_bench_2gpu.err; echo "exit $?"
+tail -c 1500 gpurun_out/r2v_bench_2gpu.log | head -c 700; echo; tail -5 gpurun_out/r2v_bench_2gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2v_ref_2gpu.log 2> gpurun_out/r2v_ref_2gpu.err; echo "exit $?"; tail -c 400 gpurun_out/r2v_ref_2gpu.log

@@ -68,5 +68,18 @@ for t in range(5):
     fenv.step({'movement': torch.rand(n, 3, device='cuda'), 'camera': torch.rand(n, 2, device='cuda'),
                'inventory': torch.randint(0, 7, (n,), device='cuda', dtype=torch.int32),
                'placement': torch.randint(0, 3, (n,), device='cuda', dtype=torch.int32)})
+# round 2: the overlapped step (forced for this small batch), the group-wise observe launch, staged tasks, device-made
+# task pools and the pov ray caster
+for mode in ('every_step', 'on_change'):
+    for bits in (128, 32):
+        env = gw.make_vec(n, max_steps=8, reward_mode=mode, grid_obs=(True if bits == 128 else False), _sched_bits=bits)
+        env.set_task_pool(T[:17], S[:17], seed=9)
+        for t in range(20):
+            env.step(acts())
+renv = gw.make_vec(n, max_steps=8, render=True, render_size=(32, 24), texture=rng.randint(0, 256, (128, 128, 4)).astype(np.uint8),
+                   _sched_bits=128)
+renv.set_random_task_pool(23, max_blocks=5, height_levels=2, max_dist=2, num_colors=3, task_seed=4)
+for t in range(6):
+    renv.step(acts())
 torch.cuda.synchronize()
 print('sanitize workload done')
