@@ -709,7 +709,8 @@ def run_b200_arm(args):
             idx = torch.arange(npairs) % goals.shape[0]
             Tp = goals[idx].to(dev)
             keep = torch.rand(Tp.shape, device=dev, generator=gen) < 0.5
-            Gp = torch.rot90(torch.where(keep, Tp, torch.zeros((), dtype=torch.int8, device=dev)), k=1, dims=(2, 3))
+            Gp = torch.rot90(torch.where(keep, Tp, torch.zeros((), dtype=torch.int8, device=dev)), k=1,
+                             dims=(2, 3)).contiguous()   # (a strided view would be re-packed inside every timed call)
             sweeps.append(reward_sweep(gw, D, dev, world, barrier, peaks,
                                        'goals.pkl structures tiled; grid = rotated random half of the target', Tp, Gp))
             del Tp, Gp

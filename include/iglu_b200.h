@@ -84,7 +84,8 @@ typedef struct iglu_config {
                                    iglu_step_walking_host stage pinned buffers through copies too; bit 5 = 1 uses the
                                    group-wise observe launch where the library would use the tiled one; bit 6 = 1 turns
                                    the overlapped step (widen next to the physics, then commit) off, bit 7 = 1 uses
-                                   it for small batches too; bits 8-13:
+                                   it for small batches too, bit 15 = 1 gives its commit launch a 3-CTA grid (tests: many
+                                   records per warp); bits 8-13:
                                    envs per group of the group-wise observe launch (0 = automatic) */
     double right_placement_scale; /* env.py:29, 296 */
     double wrong_placement_scale; /* env.py:29, 294 */

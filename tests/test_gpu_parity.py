@@ -250,6 +250,7 @@ def _tasks(rng, n):
 # scheduling switches of iglu_config.reserved (results identical): 128 = the overlapped step (k_widen next to the physics
 # launch, then k_commit) also for small batches, 64 = never; 32 = group-wise instead of tiled observe launch
 OVERLAP, NO_OVERLAP, GROUPWISE = 128, 64, 32
+SMALL_COMMIT = 32768   # 3-CTA commit launch: every warp works through a dozen records (its two-slot ring)
 
 
 @pytest.mark.parametrize('reward_mode,alternate,grid_obs,bits', [('on_change', True, True, 0), ('every_step', True, True, 0),
@@ -259,7 +260,8 @@ OVERLAP, NO_OVERLAP, GROUPWISE = 128, 64, 32
                                                                  ('every_step', True, 'incremental', GROUPWISE),
                                                                  ('every_step', True, False, 0),
                                                                  ('on_change', True, True, OVERLAP),
-                                                                 ('every_step', True, True, OVERLAP)])
+                                                                 ('every_step', True, True, OVERLAP),
+                                                                 ('every_step', True, True, OVERLAP | SMALL_COMMIT)])
 def test_walking_batch_vs_oracle(reward_mode, alternate, grid_obs, bits):
     import gridworld_b200 as gw
     n, steps = 2048, 400
