@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? IGLU_
     }
     // Programmatic dependent launch: the prologue above overlaps the tail of the previous launch on the stream;
     // nothing that launch wrote is read before this point. (A no-op when launched without the PDL attribute.)
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // (The physics launch of the overlapped step is itself a programmatic dependent of k_widen and must NOT wait for
+    // it here -- it runs next to it; its last CTA waits at the very end instead, see below.)
+    if (!(PHASES == 1 && p.overlap)) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int64_t n = p.st.n;
     const int GS = p.group;
@@ -613,6 +615,21 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? IGLU_
     // 64-bit add per warp and launch
     if (HAS_B && p.st.sched != nullptr && lane == 0 && evals_done)
         atomicAdd(reinterpret_cast<unsigned long long *>(p.st.sched + 2), (unsigned long long)evals_done);
+    if (PHASES == 1 && p.overlap) {
+        // Overlapped step: this launch follows k_widen on the same stream as its programmatic dependent and was allowed to
+        // start as soon as k_widen's CTAs were resident. k_commit, launched normally behind this grid, must not start
+        // before k_widen has finished as well: the LAST CTA of this grid to get here (ticket in st.sched[6]) waits for the
+        // prerequisite grid before it exits, which holds this grid's completion back until then. (Only that one CTA:
+        // CTAs of the first wave that waited here would keep the second wave from ever starting.)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int t = atomicAdd(p.st.sched + 6, 1);
+            if (t == (int)gridDim.x - 1) {
+                p.st.sched[6] = 0;
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------ observe launch (tiled)
@@ -875,13 +892,15 @@ __global__ void __launch_bounds__(IGLU_OBS_WARPS * 32, IGLU_OBS_CTAS) k_observe(
 // A step's physics launch is a latency chain that moves almost no bytes, and the observation rewrite is a stream of
 // bytes that needs few issue slots; they only depend on each other through the (at most one) cell an env edits and
 // through resets. The overlapped step therefore runs
-//   k_widen   (caller's stream): obs['grid'] rows and (every-step reward) maximal_intersection from the grids AS THEY
+//   k_widen   obs['grid'] rows and (every-step reward) maximal_intersection from the grids AS THEY
 //             ARE WHEN THE STEP STARTS, one 16-warp CTA per SM at 64 registers, next to
-//   physics   (k_step<KIND, 1>, second stream): two 4-warp CTAs per SM in the registers k_widen leaves; it finishes
-//             reward / done itself for every env it neither edited nor reset (the cached max_int stands, task.py:112)
-//             and lists the others in st.worklist;
-//   k_commit  (caller's stream, after both): for the listed envs only -- patch the edited cell into obs['grid'] or
-//             rewrite the row after a reset, evaluate maximal_intersection on the new grid, reward / done.
+//   physics   (k_step<KIND, 1>, same stream, launched as k_widen's PROGRAMMATIC DEPENDENT: it starts as soon as every
+//             k_widen CTA is resident and never waits for that grid's results): two 4-warp CTAs per SM in the registers
+//             k_widen leaves; it finishes reward / done itself for every env it neither edited nor reset (the cached
+//             max_int stands, task.py:112) and lists the others in st.worklist; its last CTA waits for k_widen's
+//             completion before exiting, so that
+//   k_commit  (same stream, normal launch) runs after both: for the listed envs only -- patch the edited cell into
+//             obs['grid'] or rewrite the row after a reset, evaluate maximal_intersection on the new grid, reward / done.
 // k_widen reads state the physics launch may be rewriting (an edited byte, a reset env's rows): what it writes for
 // such an env is replaced by k_commit, and the evaluation tolerates arbitrary bytes (register_target / hist_max
 // check their inputs).
@@ -957,6 +976,7 @@ __global__ void __launch_bounds__(WIDEN_WARPS * 32, 2) k_widen(const __grid_cons
     WidenWarp *scratch = reinterpret_cast<WidenWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     WidenWarp &ws = scratch[wid];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the physics launch may start next to this grid
     for (int q = tid; q < CELL_LUT_N / 2; q += WIDEN_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -1514,9 +1534,7 @@ struct iglu_ctx {
     int num_sms;
     int last_launches;
     iglu_task_pool pool;  // copy of the attached generator (m == 0: none)
-    cudaStream_t side;    // overlapped step: the physics launch runs here, next to k_widen on the caller's stream
-    cudaEvent_t fork, join;
-    cudaEvent_t trace[6];  // IGLU_B200_TRACE=1: start / end of k_widen, the physics launch and k_commit of the last step
+    cudaEvent_t trace[6];  // IGLU_B200_TRACE=1: timing events around the launches of the last overlapped step
     int tracing;
 };
 
@@ -1586,7 +1604,6 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!rc) rc = check(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes()));
     if (!rc) rc = check(cudaFuncSetAttribute(k_widen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
     if (!rc) rc = check(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes()));
-    c->side = nullptr; c->fork = nullptr; c->join = nullptr;
     c->tracing = 0;
     for (int i = 0; i < 6; i++) c->trace[i] = nullptr;
     if (const char *tr = getenv("IGLU_B200_TRACE")) {
@@ -1595,9 +1612,6 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
             for (int i = 0; i < 6 && !rc; i++) rc = check(cudaEventCreate(&c->trace[i]));
         }
     }
-    if (!rc) rc = check(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    if (!rc) rc = check(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
-    if (!rc) rc = check(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
     if (rc) { iglu_ctx_destroy(c); return rc; }
     *out = c;
     return IGLU_OK;
@@ -1606,9 +1620,6 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
 extern "C" void iglu_ctx_destroy(iglu_ctx *ctx) {
     if (!ctx) return;
     for (int i = 0; i < 6; i++) if (ctx->trace[i]) cudaEventDestroy(ctx->trace[i]);
-    if (ctx->join) cudaEventDestroy(ctx->join);
-    if (ctx->fork) cudaEventDestroy(ctx->fork);
-    if (ctx->side) cudaStreamDestroy(ctx->side);
     delete ctx;
 }
 
@@ -1746,24 +1757,30 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         if ((p.cfg.reserved >> 8) & 63) chunk = (p.cfg.reserved >> 8) & 63;     // tuning override
         p.group = (int)(chunk > 32 ? 32 : chunk);
         p.overlap = 1;
-        int rc = check(cudaEventRecord(ctx->fork, s));
-        if (!rc) rc = check(cudaStreamWaitEvent(ctx->side, ctx->fork, 0));
-        if (rc) return rc;
+        // one stream, three launches: k_widen; the physics launch as its PROGRAMMATIC dependent (it starts once every
+        // k_widen CTA is resident -- so k_widen has its CTA per SM -- and runs next to it); k_commit behind both
+        const bool tr = ctx->tracing != 0;
         const int64_t groups_w = (n + p.group - 1) / p.group;
         const int64_t ctas_w = (groups_w + WIDEN_WARPS - 1) / WIDEN_WARPS;
-        const bool tr = ctx->tracing != 0;
         if (tr) cudaEventRecord(ctx->trace[0], s);
         k_widen<<<(unsigned)(ctas_w < ctx->num_sms ? ctas_w : ctx->num_sms), WIDEN_WARPS * 32, widen_smem_bytes(), s>>>(p);
-        if (tr) cudaEventRecord(ctx->trace[1], s);
+        int rc = check(cudaPeekAtLastError());
+        if (rc) return rc;
         StepParams pa = p;
         pa.group = 32;
-        if (tr) cudaEventRecord(ctx->trace[2], ctx->side);
-        k_step<KIND, 1><<<(unsigned)(((n + 31) / 32 + StepCfg<1>::WPC - 1) / StepCfg<1>::WPC), StepCfg<1>::WPC * 32, 0,
-                          ctx->side>>>(pa);
-        if (tr) cudaEventRecord(ctx->trace[3], ctx->side);
-        rc = check(cudaEventRecord(ctx->join, ctx->side));
-        if (!rc) rc = check(cudaStreamWaitEvent(s, ctx->join, 0));
+        cudaLaunchConfig_t lp = {};
+        lp.gridDim = dim3((unsigned)(((n + 31) / 32 + StepCfg<1>::WPC - 1) / StepCfg<1>::WPC));
+        lp.blockDim = dim3(StepCfg<1>::WPC * 32);
+        lp.dynamicSmemBytes = 0;
+        lp.stream = s;
+        cudaLaunchAttribute ap[1];
+        ap[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        ap[0].val.programmaticStreamSerializationAllowed = 1;
+        lp.attrs = ap;
+        lp.numAttrs = 1;
+        rc = check(cudaLaunchKernelEx(&lp, k_step<KIND, 1>, pa));
         if (rc) return rc;
+        if (tr) { cudaEventRecord(ctx->trace[1], s); cudaEventRecord(ctx->trace[2], s); cudaEventRecord(ctx->trace[3], s); }
         const int64_t ctas_c = (n / 8 + COMMIT_WARPS - 1) / COMMIT_WARPS;   // ~1 listed env in 14: about one per warp
         const int64_t max_c = (p.cfg.reserved & 32768) ? 3 : (int64_t)ctx->num_sms * 7;   // bit 15: tiny grid (tests)
         if (tr) cudaEventRecord(ctx->trace[4], s);

@@ -116,7 +116,7 @@ typedef struct iglu_state {
     int32_t *sched;    /* [8] launch-to-launch scratch, or NULL = groups of envs are dealt statically. Word 0: work
                                   counter of the observe launch; words 2-3 (one uint64): running count of the
                                   maximal_intersection evaluations the step calls performed (a caller may zero it);
-                                  words 4-5: counters of the overlapped step (left at zero by every step) */
+                                  words 4-6: counters of the overlapped step (left at zero by every step) */
     int32_t *worklist; /* [8][n] scratch of the overlapped step (a 32-byte record per env a step edited or reset;
                                   16-byte aligned), or NULL = steps use the two-launch / fused forms only */
 } iglu_state;
@@ -332,8 +332,9 @@ int iglu_render_pov(iglu_ctx *ctx, const iglu_state *st, uint8_t *pov, int heigh
 int iglu_last_launch_count(const iglu_ctx *ctx);
 
 /* Tuning aid, no reference counterpart: with IGLU_B200_TRACE=1 in the environment when the ctx was created, the
- * overlapped step brackets its three launches with timing events; this call waits for the last step and returns, in
- * milliseconds after the start of the widen launch: widen end, physics start, physics end, commit start, commit end. */
+ * overlapped step records timing events around its launches; this call waits for the last step and returns, in
+ * milliseconds after the start of the widen launch: out5[0..2] = end of widen + physics (the physics launch is the
+ * widen launch's programmatic dependent: nothing may be recorded between them), out5[3] = commit start, [4] = commit end. */
 int iglu_debug_overlap_trace(iglu_ctx *ctx, float *out5);
 
 #ifdef __cplusplus

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Timeline of the overlapped step (k_widen || physics, then k_commit) at steady state: per-launch start / end times
-from the library's tracing events (IGLU_B200_TRACE=1). usage: python scripts/overlap_trace.py [n] [sched_bits]"""
+"""Timeline of the overlapped step (k_widen || physics, then k_commit) at steady state from the library's tracing events
+(IGLU_B200_TRACE=1): end of the widen + physics pair and start / end of the commit launch, relative to the start of the
+widen launch. (The round-2 two-stream prototype could time the two concurrent launches separately:
+profiles/r02_overlap_trace_two_streams.jsonl.) usage: python scripts/overlap_trace.py [n] [sched_bits]"""
 import ctypes as C
 import json
 import os
@@ -33,7 +35,6 @@ for mode in ('every_step', 'on_change'):
             gw._lib.check(env._L.iglu_debug_overlap_trace(env._ctx, buf))
             rows.append(list(buf))
     r = np.median(np.array(rows), axis=0) * 1e3
-    print(json.dumps({'n': n, 'mode': mode, 'bits': bits, 'widen_end_us': round(float(r[0]), 1),
-                      'physics_start_us': round(float(r[1]), 1), 'physics_end_us': round(float(r[2]), 1),
+    print(json.dumps({'n': n, 'mode': mode, 'bits': bits, 'widen_and_physics_end_us': round(float(r[2]), 1),
                       'commit_start_us': round(float(r[3]), 1), 'commit_end_us': round(float(r[4]), 1)}), flush=True)
     del env
