@@ -399,7 +399,8 @@ def reward_sweep(gw, D, dev, world, barrier, peaks, name, T, G, reps=5):
         ach = evals / world * pe
         out['roofline'] = {'bound': 'int_pipe', 'achieved': ach, 'unit': 'popcount-ANDs/s (evals/s x P_eval)',
                            'popc_peak': peaks['popc'], 'frac': ach / peaks['popc'],
-                           'alu_pipe_pct': recorded('max_intersection_ncu.json', 'alu_pipe_pct')}
+                           # ncu sm__pipe_alu_cycles_active of the committed capture of this workload, where there is one
+                           'alu_pipe_pct': (recorded('max_intersection_ncu.json', name) or {}).get('alu_pipe_pct')}
     return out
 
 

@@ -217,7 +217,8 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
 #endif
 #ifndef IGLU_PHYS_CTAS
-#define IGLU_PHYS_CTAS 4       // 4-warp CTAs of the physics launch per SM the register budget is set for (4: 128 registers)
+#define IGLU_PHYS_CTAS 5       // 4-warp CTAs of the physics launch per SM the register budget is set for (5: 96 registers,
+                               // no spills; 4: 128 registers -- same speed alone, one CTA fewer next to k_widen)
 #endif
 template <int PHASES> struct StepCfg {
     static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
@@ -969,7 +970,10 @@ struct Ring {
     }
 };
 
-__global__ void __launch_bounds__(WIDEN_WARPS * 32, 2) k_widen(const __grid_constant__ StepParams p) {
+#ifndef IGLU_WIDEN_REGS
+#define IGLU_WIDEN_REGS 56     // 16 warps x 56 registers + three 4-warp physics CTAs x 96 registers = the register file
+#endif
+__global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ StepParams p) {
     constexpr int NBUF = IGLU_WIDEN_RING;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);

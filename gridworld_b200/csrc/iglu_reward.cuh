@@ -113,10 +113,12 @@ __device__ __forceinline__ int word_scan(const uint32_t *win, int off, const int
         if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS)   // only words 0..3 and the last ones can hold non-cell bytes
             x = (q == 0 || 32 * q + 32 > ROW_WORDS - 4) ? diff_word<true>(win, off, i32, w) : diff_word<false>(win, off, i32, w);
         const unsigned b = __ballot_sync(0xffffffffu, x != 0);
-        if (COUNT) nb += __popc(nz_bytes(x));
-        const int slot = base + __popc(b & lt);
-        if (x != 0 && (unsigned)slot < (unsigned)WL_CAP) wl[slot] = (uint16_t)w;
-        base += __popc(b);
+        if (b) {   // (warp-uniform: sparse rows skip most rounds)
+            if (COUNT) nb += __popc(nz_bytes(x));
+            const int slot = base + __popc(b & lt);
+            if (x != 0 && (unsigned)slot < (unsigned)WL_CAP) wl[slot] = (uint16_t)w;
+            base += __popc(b);
+        }
     }
     if (COUNT) *nblocks = __reduce_add_sync(0xffffffffu, nb);
     return base + w0;
