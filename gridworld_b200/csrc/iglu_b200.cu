@@ -1137,19 +1137,46 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
 __global__ void __launch_bounds__(256) k_render_pov(iglu_state st, uint8_t *__restrict__ pov, int height, int width,
                                                     const uint8_t *__restrict__ atlas) {
     __shared__ __align__(16) int8_t g8[GSTRIDE];
+    __shared__ int box[6];   // x0, x1, y0, y1, z0, z1 of the blocks
     const int64_t e = blockIdx.x, n = st.n;
     const int4 *src = reinterpret_cast<const int4 *>(st.grid + e * GSTRIDE);
     for (int q = threadIdx.x; q < GSTRIDE / 16; q += blockDim.x) reinterpret_cast<int4 *>(g8)[q] = src[q];
+    if (threadIdx.x < 6) box[threadIdx.x] = (threadIdx.x & 1) ? -1 : 16;
     const PovCamera cam = pov_camera(st.pose[0 * n + e], st.pose[1 * n + e], st.pose[2 * n + e], st.pose[3 * n + e],
                                      st.pose[4 * n + e]);
     __syncthreads();
+    for (int c = threadIdx.x; c < CELLS; c += blockDim.x)
+        if (g8[c] != 0) {
+            const int y = c / 121, r = c - 121 * y, x = r / 11, z = r - 11 * x;
+            atomicMin(&box[0], x); atomicMax(&box[1], x); atomicMin(&box[2], y); atomicMax(&box[3], y);
+            atomicMin(&box[4], z); atomicMax(&box[5], z);
+        }
+    __syncthreads();
+    const PovBox bb = {box[0], box[1], box[2], box[3], box[4], box[5]};
     const float kx = 2.0f / (float)width, ky = 2.0f / (float)height, aspect = (float)width / (float)height;
     uint8_t *out = pov + e * (int64_t)height * width * 3;
-    for (int pix = threadIdx.x; pix < height * width; pix += blockDim.x) {
-        const int j = pix / width, i = pix - j * width;
-        const float sx = ((float)i + 0.5f) * kx - 1.0f, sy = 1.0f - ((float)j + 0.5f) * ky;
-        const uchar3 c = pov_trace(g8, atlas, cam, sx * aspect, sy);
-        out[3 * pix + 0] = c.x; out[3 * pix + 1] = c.y; out[3 * pix + 2] = c.z;
+    // 256 pixels per pass: colours go through shared memory so that the frame is written with 4-byte stores of
+    // consecutive lanes (the frame of env e starts at a multiple of 4 bytes when 3 * h * w is one; else byte stores)
+    __shared__ __align__(16) uint8_t stage[256 * 3];
+    const int npix = height * width;
+    const bool wide = ((3 * npix) & 3) == 0 && ((reinterpret_cast<uintptr_t>(pov)) & 3) == 0;
+    for (int p0 = 0; p0 < npix; p0 += 256) {
+        const int pix = p0 + threadIdx.x;
+        if (pix < npix) {
+            const int j = pix / width, i = pix - j * width;
+            const float sx = ((float)i + 0.5f) * kx - 1.0f, sy = 1.0f - ((float)j + 0.5f) * ky;
+            const uchar3 c = pov_trace(g8, bb, atlas, cam, sx * aspect, sy);
+            stage[3 * threadIdx.x + 0] = c.x; stage[3 * threadIdx.x + 1] = c.y; stage[3 * threadIdx.x + 2] = c.z;
+        }
+        __syncthreads();
+        const int nbytes = 3 * min(256, npix - p0);
+        if (wide && (nbytes & 3) == 0) {   // 3 * p0 is a multiple of 4 (p0 is a multiple of 256)
+            if (threadIdx.x < nbytes / 4)
+                reinterpret_cast<uint32_t *>(out + 3 * p0)[threadIdx.x] = reinterpret_cast<const uint32_t *>(stage)[threadIdx.x];
+        } else {
+            for (int b = threadIdx.x; b < nbytes; b += 256) out[3 * p0 + b] = stage[b];
+        }
+        __syncthreads();
     }
 }
 

@@ -49,13 +49,26 @@ __device__ __forceinline__ PovCamera pov_camera(double x, double y, double z, do
     return c;
 }
 
-// flat stand-in palette, index id + 1 (WHITE -1 .. YELLOW 6), close to the tile means of the reference atlas
-__device__ __constant__ uint8_t g_pov_palette[8][3] = {
-    {245, 245, 245}, {70, 72, 76}, {0, 90, 128}, {17, 101, 36}, {133, 16, 17}, {146, 71, 22}, {92, 37, 96}, {145, 137, 0}};
+// flat stand-in palette (WHITE -1 .. YELLOW 6), close to the tile means of the reference atlas, packed r | g << 8 | b << 16
+__device__ __forceinline__ uint32_t pov_palette(int id) {
+    switch (id) {
+        case -1: return 245u | (245u << 8) | (245u << 16);
+        case 0: return 70u | (72u << 8) | (76u << 16);
+        case 1: return 0u | (90u << 8) | (128u << 16);
+        case 2: return 17u | (101u << 8) | (36u << 16);
+        case 3: return 133u | (16u << 8) | (17u << 16);
+        case 4: return 146u | (71u << 8) | (22u << 16);
+        case 5: return 92u | (37u << 8) | (96u << 16);
+        default: return 145u | (137u << 8) | (0u << 16);
+    }
+}
 
 // texel of block id `id` (-1..6), face quarter (qx, qy in texels, split tiles), face coordinates u, v in [0, 1]
 __device__ __forceinline__ uchar3 pov_texel(const uint8_t *__restrict__ atlas, int id, int qx, int qy, float u, float v) {
-    if (!atlas) return make_uchar3(g_pov_palette[id + 1][0], g_pov_palette[id + 1][1], g_pov_palette[id + 1][2]);
+    if (!atlas) {
+        const uint32_t c = pov_palette(id);
+        return make_uchar3((uint8_t)c, (uint8_t)(c >> 8), (uint8_t)(c >> 16));
+    }
     // tile of the id: utils.py:130-139
     const int tile_x = id == -1 ? 0 : (id == 0 ? 1 : (id == 1 ? 2 : (id == 2 ? 3 : (id == 3 ? 0 : (id == 4 ? 1 : (id == 5 ? 2 : 3))))));
     const int tile_y = id >= 3 ? 1 : 0;
@@ -68,16 +81,24 @@ __device__ __forceinline__ uchar3 pov_texel(const uint8_t *__restrict__ atlas, i
     return make_uchar3(p[0], p[1], p[2]);
 }
 
+// Bounding box of the env's blocks in cell indices (x: 0..10, y: 0..8, z: 0..10), lo > hi when there is none. The walk
+// through the cells is restricted to it: most worlds hold a few dozen blocks, so most rays never enter the box.
+struct PovBox {
+    int x0, x1, y0, y1, z0, z1;
+};
+
 // Colour of the ray o + t d, d = f + sxa r + sy u. g8 = the env's int8 grid (cell (y+1) * 121 + (x+5) * 11 + (z+5)).
-__device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__restrict__ atlas, const PovCamera &c, float sxa,
-                                            float sy) {
+__device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const PovBox &bb, const uint8_t *__restrict__ atlas,
+                                            const PovCamera &c, float sxa, float sy) {
     const float o[3] = {c.ox, c.oy, c.oz};
     const float d[3] = {(c.fx + sxa * c.rx) + sy * c.ux, c.fy + sy * c.uy, (c.fz + sxa * c.rz) + sy * c.uz};
+    // one IEEE reciprocal per axis; every plane distance below is (plane - origin) * inv (mirrored by the restatement)
+    const float inv[3] = {d[0] != 0.0f ? 1.0f / d[0] : 0.0f, d[1] != 0.0f ? 1.0f / d[1] : 0.0f, d[2] != 0.0f ? 1.0f / d[2] : 0.0f};
     float best_t = POV_FAR;   // nearest accepted hit so far (hits beyond the far plane are clipped)
     uchar3 col = make_uchar3(128, 176, 255);   // glClearColor(0.5, 0.69, 1.0)
     // ---- floor: top faces at y = -1.5 over |x|, |z| <= 18.5, seen from above only
     if (d[1] < 0.0f && o[1] > -1.5f) {
-        const float t = (-1.5f - o[1]) / d[1];
+        const float t = (-1.5f - o[1]) * inv[1];
         const float px = o[0] + d[0] * t, pz = o[2] + d[2] * t;
         if (t >= POV_NEAR && t <= best_t && px >= -18.5f && px <= 18.5f && pz >= -18.5f && pz <= 18.5f) {
             const float cx = floorf(px + 0.5f), cz = floorf(pz + 0.5f);
@@ -87,9 +108,11 @@ __device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__r
             best_t = t;
         }
     }
-    // ---- blocks: DDA through the 11 x 9 x 11 cells of the zone, [-5.5, 5.5] x [-1.5, 7.5] x [-5.5, 5.5]
-    const float lo[3] = {-5.5f, -1.5f, -5.5f};
-    const int dim[3] = {11, 9, 11};
+    // ---- blocks: DDA through the cells of the blocks' bounding box (cell (i, j, k) of the zone is the unit cube with
+    // lower corner (i - 5.5, j - 1.5, k - 5.5))
+    if (bb.x0 > bb.x1) return col;
+    const float lo[3] = {(float)bb.x0 - 5.5f, (float)bb.y0 - 1.5f, (float)bb.z0 - 5.5f};
+    const int dim[3] = {bb.x1 - bb.x0 + 1, bb.y1 - bb.y0 + 1, bb.z1 - bb.z0 + 1};
     float t_in = 0.0f, t_out = best_t;
     int axis_in = -1;
     bool miss = false;
@@ -97,7 +120,7 @@ __device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__r
     for (int a = 0; a < 3; a++) {
         const float hi = lo[a] + (float)dim[a];
         if (d[a] != 0.0f) {
-            const float t1 = (lo[a] - o[a]) / d[a], t2 = (hi - o[a]) / d[a];
+            const float t1 = (lo[a] - o[a]) * inv[a], t2 = (hi - o[a]) * inv[a];
             const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
             if (tn > t_in) { t_in = tn; axis_in = a; }
             t_out = fminf(t_out, tf);
@@ -117,8 +140,8 @@ __device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__r
         if (a == axis_in) ci = d[a] > 0.0f ? 0 : dim[a] - 1;
         if (d[a] != 0.0f) {
             const float bound = lo[a] + (float)(ci + (d[a] > 0.0f ? 1 : 0));
-            tm = (bound - o[a]) / d[a];
-            td = fabsf(1.0f / d[a]);
+            tm = (bound - o[a]) * inv[a];
+            td = fabsf(inv[a]);
         } else {
             tm = 3.0e38f;
             td = 0.0f;
@@ -133,11 +156,12 @@ __device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__r
     for (int it = 0; it < 40; it++) {
         if (axis >= 0 && t >= POV_NEAR) {   // an entry event in front of the near plane
             if (t > best_t) break;
-            const int v = g8[c1 * 121 + c0 * 11 + c2];
+            const int gx = c0 + bb.x0, gy = c1 + bb.y0, gz = c2 + bb.z0;   // cell in the zone
+            const int v = g8[gy * 121 + gx * 11 + gz];
             if (v != 0) {
                 const int id = v < -1 ? 0 : (v > 6 ? 6 : v);
                 const float px = o[0] + d[0] * t, py = o[1] + d[1] * t, pz = o[2] + d[2] * t;
-                const float X = (float)(c0 - 5), Y = (float)(c1 - 1), Z = (float)(c2 - 5);
+                const float X = (float)(gx - 5), Y = (float)(gy - 1), Z = (float)(gz - 5);
                 float u, w;
                 int qx, qy;
                 if (axis == 1) {
@@ -160,19 +184,19 @@ __device__ __forceinline__ uchar3 pov_trace(const int8_t *g8, const uint8_t *__r
             axis = 0; t = m0;
             if (t > t_out) break;
             c0 += s0;
-            if (c0 < 0 || c0 >= 11) break;
+            if (c0 < 0 || c0 >= dim[0]) break;
             m0 += e0;
         } else if (m1 <= m2) {
             axis = 1; t = m1;
             if (t > t_out) break;
             c1 += s1;
-            if (c1 < 0 || c1 >= 9) break;
+            if (c1 < 0 || c1 >= dim[1]) break;
             m1 += e1;
         } else {
             axis = 2; t = m2;
             if (t > t_out) break;
             c2 += s2;
-            if (c2 < 0 || c2 >= 11) break;
+            if (c2 < 0 || c2 >= dim[2]) break;
             m2 += e2;
         }
     }

@@ -946,17 +946,26 @@ void orc_render_pov(const int8_t *grid, const double *pose, int height, int widt
     const float rx = (float)cy, rz = (float)sy_;                            /* camera x axis after the yaw rotation */
     const float u3[3] = {-(rz * f[1]), rz * f[0] - rx * f[2], rx * f[1]};   /* up = right x forward */
     const float kx = 2.0f / (float)width, ky = 2.0f / (float)height, aspect = (float)width / (float)height;
-    const float lo[3] = {-5.5f, -1.5f, -5.5f};
-    const int dim[3] = {GX, GY, GZ};
+    /* the walk through the cells is restricted to the bounding box of the blocks (cell indices; empty: b0 > b1) */
+    int b0[3] = {16, 16, 16}, b1[3] = {-1, -1, -1};
+    for (int c = 0; c < CELLS; c++)
+        if (grid[c] != 0) {
+            const int q[3] = {(c % 121) / 11, c / 121, c % 11};
+            for (int a = 0; a < 3; a++) { if (q[a] < b0[a]) b0[a] = q[a]; if (q[a] > b1[a]) b1[a] = q[a]; }
+        }
+    const float lo[3] = {(float)b0[0] - 5.5f, (float)b0[1] - 1.5f, (float)b0[2] - 5.5f};
+    const int dim[3] = {b1[0] - b0[0] + 1, b1[1] - b0[1] + 1, b1[2] - b0[2] + 1};
     for (int j = 0; j < height; j++)
         for (int i = 0; i < width; i++) {
             uint8_t *px_out = out + 3 * (j * width + i);
             const float sx = ((float)i + 0.5f) * kx - 1.0f, sy = 1.0f - ((float)j + 0.5f) * ky, sxa = sx * aspect;
             const float d[3] = {(f[0] + sxa * rx) + sy * u3[0], f[1] + sy * u3[1], (f[2] + sxa * rz) + sy * u3[2]};
+            const float inv[3] = {d[0] != 0.0f ? 1.0f / d[0] : 0.0f, d[1] != 0.0f ? 1.0f / d[1] : 0.0f,
+                                  d[2] != 0.0f ? 1.0f / d[2] : 0.0f}; /* plane distances are (plane - origin) * inv */
             float best_t = 30.0f;
             px_out[0] = 128; px_out[1] = 176; px_out[2] = 255; /* glClearColor(0.5, 0.69, 1.0) */
             if (d[1] < 0.0f && o[1] > -1.5f) { /* floor: top faces at y = -2 + 0.5, seen from above only */
-                const float t = (-1.5f - o[1]) / d[1];
+                const float t = (-1.5f - o[1]) * inv[1];
                 const float px = o[0] + d[0] * t, pz = o[2] + d[2] * t;
                 if (t >= 0.1f && t <= best_t && px >= -18.5f && px <= 18.5f && pz >= -18.5f && pz <= 18.5f) {
                     const float cx = floorf(px + 0.5f), cz = floorf(pz + 0.5f);
@@ -965,12 +974,13 @@ void orc_render_pov(const int8_t *grid, const double *pose, int height, int widt
                     best_t = t;
                 }
             }
+            if (b0[0] > b1[0]) continue;
             float t_in = 0.0f, t_out = best_t;
             int axis_in = -1, miss = 0;
             for (int a = 0; a < 3; a++) {
                 const float hi = lo[a] + (float)dim[a];
                 if (d[a] != 0.0f) {
-                    const float t1 = (lo[a] - o[a]) / d[a], t2 = (hi - o[a]) / d[a];
+                    const float t1 = (lo[a] - o[a]) * inv[a], t2 = (hi - o[a]) * inv[a];
                     const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
                     if (tn > t_in) { t_in = tn; axis_in = a; }
                     t_out = fminf(t_out, tf);
@@ -990,8 +1000,8 @@ void orc_render_pov(const int8_t *grid, const double *pose, int height, int widt
                 step[a] = d[a] > 0.0f ? 1 : -1;
                 if (d[a] != 0.0f) {
                     const float bound = lo[a] + (float)(ci + (d[a] > 0.0f ? 1 : 0));
-                    t_max[a] = (bound - o[a]) / d[a];
-                    t_delta[a] = fabsf(1.0f / d[a]);
+                    t_max[a] = (bound - o[a]) * inv[a];
+                    t_delta[a] = fabsf(inv[a]);
                 } else {
                     t_max[a] = 3.0e38f;
                     t_delta[a] = 0.0f;
@@ -1002,11 +1012,12 @@ void orc_render_pov(const int8_t *grid, const double *pose, int height, int widt
             for (int it = 0; it < 40; it++) {
                 if (axis >= 0 && t >= 0.1f) { /* a cube is seen from outside, in front of the near plane */
                     if (t > best_t) break;
-                    const int v = grid[cell[1] * 121 + cell[0] * 11 + cell[2]];
+                    const int gx = cell[0] + b0[0], gy = cell[1] + b0[1], gz = cell[2] + b0[2];
+                    const int v = grid[gy * 121 + gx * 11 + gz];
                     if (v != 0) {
                         const int id = v < -1 ? 0 : (v > 6 ? 6 : v);
                         const float px = o[0] + d[0] * t, py = o[1] + d[1] * t, pz = o[2] + d[2] * t;
-                        const float X = (float)(cell[0] - 5), Y = (float)(cell[1] - 1), Z = (float)(cell[2] - 5);
+                        const float X = (float)(gx - 5), Y = (float)(gy - 1), Z = (float)(gz - 5);
                         float u, w;
                         int qx, qy;
                         if (axis == 1) { /* cube_vertices: top / bottom */

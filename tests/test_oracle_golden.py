@@ -249,6 +249,23 @@ def _coded_atlas():
     return a
 
 
+def _box_mask(block, pose, h=64, w=64):
+    """Pixels whose centre ray hits the unit cube centred on `block` in front of the near plane (numpy slab test)."""
+    x, y, z, yaw, pitch = pose
+    sy_, cy = np.sin(np.radians(yaw)), np.cos(np.radians(yaw))
+    sp, cp = np.sin(np.radians(pitch)), np.cos(np.radians(pitch))
+    f, r = np.array([sy_ * cp, sp, -cy * cp]), np.array([cy, 0, sy_])
+    u = np.cross(r, f)
+    i, j = (np.arange(w) + 0.5) * 2 / w - 1, 1 - (np.arange(h) + 0.5) * 2 / h
+    d = f[None, None, :] + i[None, :, None] * r[None, None, :] * (w / h) + j[:, None, None] * u[None, None, :]
+    o = np.array([x, y, z], float)
+    lo = np.array(block, float) - 0.5
+    with np.errstate(divide='ignore', invalid='ignore'):
+        t1, t2 = (lo - o) / d, (lo + 1 - o) / d
+    tn, tf = np.minimum(t1, t2).max(axis=2), np.maximum(t1, t2).min(axis=2)
+    return (tn <= tf) & (tn >= 0.1) & (tn <= 30)
+
+
 def test_render_pov_known_answers():
     """obs['pov'] restatement (reference gridworld/render.py:94-113, 159-170; utils.py:26-41, 75-139): answers that
     follow from the camera / geometry / texture rules by hand."""
@@ -265,15 +282,26 @@ def test_render_pov_known_answers():
     assert (O.render_pov(empty, (0, -3, 0, 0, -45)) == SKY).all()
     # one red block at (0, -1, -3), i.e. its front face 2.5 ahead of an eye at the origin looking along -z: the face
     # spans sx in [-0.2, 0.2] -> columns 26..37 and sy in [-0.6, -0.2] -> rows 38..50; its top face (y = -0.5, seen from
-    # above) fills sy in [-0.2, -0.5 / 3.5] -> row 37, columns 27..36 (half-width 0.5 / 3.06 at that depth)
+    # above) fills row 37 (sy = -0.172: the ray reaches y = -0.5 at depth 2.91, where the block is 0.344 wide in sx ->
+    # columns 27..36, plus the two rays that graze the block's vertical edges exactly: ties, either way is right)
     g = empty.copy()
     g[0, 5, 2] = 3
     img = O.render_pov(g, (0, 0, 0, 0, 0))
     red = (img == RED_).all(axis=2)
     ys, xs = np.nonzero(red)
     assert (xs.min(), xs.max(), ys.min(), ys.max()) == (26, 37, 37, 50), (xs.min(), xs.max(), ys.min(), ys.max())
-    assert np.array_equal(np.nonzero(red[37])[0], np.arange(27, 37)) and red[38:51, 26:38].all()
+    assert red[37, 27:37].all() and red[38:51, 26:38].all() and red.sum() in (166, 168)
     assert (red[:, :32] == red[:, :31:-1]).all()              # mirror symmetry
+    # the same picture from the slab test of the block's box, for a few poses (independent of the cell walk)
+    for pose in ((0, 0, 0, 0, 0), (0.3, 1.2, 1.0, 20, -25), (-1.7, 2.4, 0.9, 340, -35), (2, 0.5, -1, 215, -10)):
+        got = (O.render_pov(g, pose) == RED_).all(axis=2)
+        assert (got != _box_mask((0, -1, -3), pose)).sum() <= 2, pose
+    # ... also when other blocks enlarge the walked region (far corners, not in front of the red block)
+    g_far = g.copy()
+    g_far[8, 0, 10] = 1
+    g_far[8, 10, 10] = 1
+    got = (O.render_pov(g_far, (0.3, 1.2, 1.0, 20, -25)) == RED_).all(axis=2)
+    assert (got != _box_mask((0, -1, -3), (0.3, 1.2, 1.0, 20, -25))).sum() <= 2
     # the same block seen after turning: yaw 90 looks along +x, so the block has to be at x = +3 to show the same picture
     g2 = empty.copy()
     g2[0, 8, 5] = 3
