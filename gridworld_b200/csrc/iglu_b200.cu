@@ -216,12 +216,15 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #ifndef IGLU_OBS_DYN_GROUP
 #define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
 #endif
+#ifndef IGLU_PHYS_WARPS
+#define IGLU_PHYS_WARPS 4      // warps per CTA of the physics launch
+#endif
 #ifndef IGLU_PHYS_CTAS
 #define IGLU_PHYS_CTAS 5       // 4-warp CTAs of the physics launch per SM the register budget is set for (5: 96 registers,
                                // no spills; 4: 128 registers -- same speed alone, one CTA fewer next to k_widen)
 #endif
 template <int PHASES> struct StepCfg {
-    static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? 4 : WARPS_PER_CTA);
+    static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? IGLU_PHYS_WARPS : WARPS_PER_CTA);
     static constexpr int NBUF = PHASES == 2 ? IGLU_OBS_RING : NB;
 };
 template <int NBUF> struct __align__(16) WarpScratchT {

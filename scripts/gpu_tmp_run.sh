@@ -1,17 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 -k "render" 2>&1 | tail -4
-python - <<'PY' 2>&1 | tail -4
-import torch, sys
-sys.path.insert(0,'.')
-import bench as B, gridworld_b200 as gw
-dev=torch.device('cuda',0)
-for n in (16384, 65536):
-    env=gw.make_vec(n, device=dev, render=True, max_steps=250)
-    T=B.synth_targets(n,0.2,'compact',1).to(dev); env.set_tasks(T, T)
-    torch.cuda.synchronize()
-    e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
-    env.render(); e0.record()
-    for _ in range(5): env.render()
-    e1.record(); torch.cuda.synchronize()
-    print('render', n, 'envs:', e0.elapsed_time(e1)/5, 'ms per frame batch')
-    del env
-PY
+mkdir -p gpurun_out; : > gpurun_out/r2x_tune.jsonl
+timeout 300 python scripts/tune_r2.py default >> gpurun_out/r2x_tune.jsonl 2>gpurun_out/r2x_tune.err
+for v in pw2_w12r56 pw2_w14r48 pw2_w16r40 pw2_w16r56; do
+  IGLU_B200_SO=$PWD/gridworld_b200/csrc/libiglu_b200_$v.so timeout 300 python scripts/tune_r2.py $v >> gpurun_out/r2x_tune.jsonl 2>>gpurun_out/r2x_tune.err
+done
+cut -c1-200 gpurun_out/r2x_tune.jsonl; tail -3 gpurun_out/r2x_tune.err
