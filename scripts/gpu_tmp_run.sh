@@ -1,6 +1,6 @@
-mkdir -p gpurun_out; : > gpurun_out/r2x_tune.jsonl
-timeout 300 python scripts/tune_r2.py default >> gpurun_out/r2x_tune.jsonl 2>gpurun_out/r2x_tune.err
-for v in pw2_w12r56 pw2_w14r48 pw2_w16r40 pw2_w16r56; do
-  IGLU_B200_SO=$PWD/gridworld_b200/csrc/libiglu_b200_$v.so timeout 300 python scripts/tune_r2.py $v >> gpurun_out/r2x_tune.jsonl 2>>gpurun_out/r2x_tune.err
-done
-cut -c1-200 gpurun_out/r2x_tune.jsonl; tail -3 gpurun_out/r2x_tune.err
+mkdir -p gpurun_out
+timeout 1200 python bench.py > gpurun_out/r02_bench.log 2> gpurun_out/r02_bench.err; echo "exit $?"
+grep '^{"metric' gpurun_out/r02_bench.log | tail -1 > gpurun_out/r02_bench_line.json
+timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r02_bench_ref.log 2>&1; tail -c 600 gpurun_out/r02_bench_ref.log
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_driver.log 2>&1; grep '^{"metric' gpurun_out/r02_bench_driver.log | tail -1 > gpurun_out/r02_bench_driver_line.json
+tail -3 gpurun_out/r02_bench.err
