@@ -704,6 +704,14 @@ def run_b200_arm(args):
             Gp[:npairs // 2] = torch.rot90(Tp[:npairs // 2], k=1, dims=(2, 3))  # half are rotated copies
             sweeps.append(reward_sweep(gw, D, dev, world, barrier, peaks, f'compact rho={rho:.2f}', Tp, Gp))
             del Tp, Gp
+        for rho in (0.05, 0.20, 0.50):   # full support: targets span the zone, one shift per rotation (byte-compare paths)
+            Tp = synth_targets(npairs, rho, 'full', 1237, device=dev)
+            Gp = synth_targets(npairs, rho, 'full', 1238, device=dev)
+            Gp[:npairs // 2] = torch.rot90(Tp[:npairs // 2], k=1, dims=(2, 3))
+            sw = reward_sweep(gw, D, dev, world, barrier, peaks, f'full rho={rho:.2f}', Tp, Gp)
+            sw['hbm_frac'] = sw['hbm_gbs'] / peak   # these are bandwidth- / byte-compare-bound, not shift-bound
+            sweeps.append(sw)
+            del Tp, Gp
         gpath = os.path.join(ROOT, 'tests', 'golden', 'goals.npz')
         if os.path.exists(gpath):
             goals = torch.as_tensor(np.load(gpath)['targets']).to(torch.int8)

@@ -1519,6 +1519,8 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
                 const int8_t *f = fulls + pr * fstride;
                 for (int c = lane; c < CELLS; c += 32)
                     if (f[c] != 0) grow(c);
+            } else if (tg.rounds() > 1) {   // crowded target: look at its columns instead of compacting round after round
+                column_bbox(reinterpret_cast<const int8_t *>(T) + toff, lane, x0, x1, z0, z1);
             } else {
                 for (int r = tg.rounds() - 1; r >= 0; r--) {   // backwards: round 0 stays loaded for the evaluation
                     const int nt = tg.load(r);
@@ -1531,7 +1533,11 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             n_rot = 4;
         }
         int key = -1, best;
-        if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
+        if (single_shift_rects(rc, n_rot) && zero_shift_rects(rc, n_rot) && tg.rounds() > 1) {   // more than 32 non-zero words
+            // zone-spanning target with many blocks: dense cell-by-cell comparison under the four rotations
+            best = eval_zero_shift_dense<WANT_KEY>(reinterpret_cast<const int8_t *>(T) + toff,
+                                                   reinterpret_cast<const int8_t *>(G) + goff, n_rot, lane, &key);
+        } else if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
             auto each = [&](auto f) {
                 for (int r = 0; r < tg.rounds(); r++) {
                     const int nt = tg.load(r);

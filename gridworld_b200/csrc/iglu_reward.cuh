@@ -407,4 +407,77 @@ __device__ __forceinline__ int eval_single_shift(const int8_t *g8, const int8_t 
     return best;
 }
 
+// Zone-spanning targets in the stateless sweep, dense form: when every rotation admits exactly one shift, that shift is
+// (0, 0) (a bounding box that leaves one admissible dx spans x = 0..10, task.py:67-72), so rotation k just compares
+// every target cell with the grid cell it rotates onto -- no compacted block list (such targets hold hundreds of
+// blocks). The rotations act on the 121 (x, z) columns only (task.py:52-53): column 11 x + z goes to 11 z + 10 - x
+// (rotation 1), 120 - column (rotation 2) and 11 (10 - z) + x (rotation 3); a lane owns columns lane, lane + 32, ... and
+// walks the nine levels.
+// t8 / g8: cell 0 of the staged target / grid rows. Returns what eval_single_shift returns for shifts (0, 0).
+template <bool WANT_KEY>
+__device__ __forceinline__ int eval_zero_shift_dense(const int8_t *t8, const int8_t *g8, int n_rot, int lane, int *key_out) {
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int col = lane + 32 * q;
+        if (col < 121) {
+            const int x = (col * 373) >> 12, z = col - 11 * x;   // col / 11 for col < 121
+            const int col1 = 11 * z + 10 - x, col2 = 120 - col, col3 = 11 * (10 - z) + x;
+#pragma unroll
+            for (int y = 0; y < 9; y++) {
+                const int t = t8[121 * y + col];
+                const bool on = t != 0 && (unsigned)(t + 6) <= 12u;   // values that are no colour difference match nothing
+                c0 += on && g8[121 * y + col] == t;
+                if (n_rot > 1) {
+                    c1 += on && g8[121 * y + col1] == t;
+                    c2 += on && g8[121 * y + col2] == t;
+                    c3 += on && g8[121 * y + col3] == t;
+                }
+            }
+        }
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    int best = c0, kbest = 0;
+    if (n_rot > 1) {
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 > best) { best = c1; kbest = 1; }          // strict: the first rotation reaching the max wins
+        if (c2 > best) { best = c2; kbest = 2; }
+        if (c3 > best) { best = c3; kbest = 3; }
+    }
+    if (WANT_KEY) *key_out = best > 0 ? kbest * 441 + 10 * 21 + 10 : -1;
+    return best;
+}
+
+// x / z extent of the non-zero cells of a staged row, by columns (for crowded rows: no compaction). Warp-uniform result.
+__device__ __forceinline__ void column_bbox(const int8_t *t8, int lane, int &x0, int &x1, int &z0, int &z1) {
+    x0 = 10; x1 = 0; z0 = 10; z1 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int col = lane + 32 * q;
+        if (col < 121) {
+            int any = 0;
+#pragma unroll
+            for (int y = 0; y < 9; y++) any |= t8[121 * y + col];
+            if (any != 0) {
+                const int x = (col * 373) >> 12, z = col - 11 * x;
+                x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+            }
+        }
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+    z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+}
+
+// true when every evaluated rotation's single shift is (0, 0)
+__device__ __forceinline__ bool zero_shift_rects(int4 rc, int n_rot) {
+    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < n_rot) ok = ok && (rw[k] & 0x00FF00FF) == 0;
+    return ok;
+}
+
 }  // namespace iglu
