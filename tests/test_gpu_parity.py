@@ -562,7 +562,7 @@ def test_step_host_routes():
     ref = gw.make_vec(n, max_steps=50, reward_mode='every_step')
     ref.set_tasks(T, S, poses)
     variants = []
-    for pinned, bits in ((True, 0), (False, 0), (True, 16)):
+    for pinned, bits in ((True, 0), (False, 0), (True, 16), (True, OVERLAP), (False, OVERLAP)):   # + the overlapped step
         env = gw.make_vec(n, max_steps=50, reward_mode='every_step', _sched_bits=bits)
         env.set_tasks(T, S, poses)
         mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
