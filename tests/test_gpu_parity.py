@@ -31,8 +31,8 @@ def _make(tr, kind, n=1, **kw):
                        wrong_placement_scale=tr['wrong_scale'], auto_reset=True, **kw)
 
 
-def _replay_gpu(tr, kind, reward_mode='on_change', exact_pose=True):
-    env = _make(tr, kind, reward_mode=reward_mode)
+def _replay_gpu(tr, kind, reward_mode='on_change', exact_pose=True, bits=0):
+    env = _make(tr, kind, reward_mode=reward_mode, _sched_bits=bits)
     dev = env.device
     env.set_tasks(tr['target'][None], tr['start'][None], tr['pose'][None])
     T = tr['n']
@@ -119,6 +119,16 @@ def test_flying_golden(tr):
 @pytest.mark.parametrize('tr', G.dict_traces(), ids=lambda t: t['name'])
 def test_walking_dict_golden(tr):
     _replay_gpu(tr, 'dict', exact_pose=False)
+
+
+@pytest.mark.parametrize('kind', ['walking', 'flying', 'dict'])
+def test_golden_traces_overlapped_step(kind):
+    """The reference-recorded traces of every action space through the overlapped step (k_widen next to the physics
+    launch, then k_commit), forced for these single-env worlds, with every-step reward."""
+    traces = {'walking': G.walking_traces()[-8:], 'flying': G.flying_traces(), 'dict': G.dict_traces()}[kind]
+    for tr in traces:
+        _replay_gpu(tr, kind, reward_mode='every_step', exact_pose=(kind == 'walking' and tr['name'] != 'odd_rotation'),
+                    bits=128)
 
 
 # ------------------------------------------------------------------------- reward kernel
