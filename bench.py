@@ -554,8 +554,8 @@ def run_b200_arm(args):
     line = None
     if rank == 0:
         bytes_per_env = A_WALK_BYTES if not args.inplace else A_INPLACE_BYTES
-        # A step is three launches: k_widen (moves ~all the bytes) next to the physics launch k_step<0,1> on a second
-        # stream, then k_commit. They are timed together: dividing the step's algorithmic bytes by the whole step
+        # A step is three launches on one stream: k_widen (moves ~all the bytes), the physics launch k_step<0,1> as its
+        # programmatic dependent (it runs next to it), then k_commit. They are timed together: dividing the step's algorithmic bytes by the whole step
         # duration charges everything to the dominant kernel, i.e. the fraction below is a lower bound for it.
         kernel_ms = total_ms / K
         achieved = bytes_per_env * n / (kernel_ms * 1e-3) / 1e9

@@ -74,9 +74,9 @@ class IGLUVecEnv:
       'incremental': keep the persistent obs['grid'] buffer up to date cell by cell -- same contents, ~20x
       fewer bytes; False: no int32 copy, obs['grid'] is the int8 state view),
       alternate_phases (scheduling only: in the fused launch half of the warps write observations before the
-      physics), split_launch (scheduling only: True = the library's measured policy -- physics and
-      observation/reward as two launches except for on_change reward with a full obs rewrite; False = always one
-      fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list),
+      physics), split_launch (scheduling only: True = the library's measured policy -- the overlapped step (widen next
+      to the physics, then commit) for a fully rewritten obs['grid'] on batches >= 8,192 envs, otherwise physics and
+      observation/reward as two launches or one fused launch; False = always one fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list),
       render / render_size / texture (render=True adds obs['pov'], uint8 [n, h, w, 3]: the reference's OpenGL frame
       (render.py) restated as a voxel ray caster, one more launch per step / reset; texture = the reference's
       128 x 128 RGBA atlas as an array (e.g. np.asarray(PIL.Image.open('gridworld/texture.png'))), None = flat
