@@ -983,7 +983,6 @@ __global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ Ste
     WidenWarp *scratch = reinterpret_cast<WidenWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     WidenWarp &ws = scratch[wid];
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the physics launch may start next to this grid
     for (int q = tid; q < CELL_LUT_N / 2; q += WIDEN_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -993,6 +992,11 @@ __global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ Ste
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // This launch is itself a programmatic dependent of whatever precedes it on the stream (the previous step's k_commit
+    // triggers early; any other kernel triggers when it completes): the set-up above overlaps that kernel's tail.
+    // Only after the wait may the physics launch -- this grid's own dependent -- be allowed to start.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int64_t n = p.st.n;
     const int GS = p.group;
     const int64_t ngroups = (n + GS - 1) / GS;
@@ -1058,12 +1062,6 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
     CommitWarp *scratch = reinterpret_cast<CommitWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     CommitWarp &ws = scratch[wid];
-    // the list length and this warp's first record are asked for before the set-up below: their latency hides behind it
-    const int count = p.st.sched[4];
-    const int4 *recs = reinterpret_cast<const int4 *>(p.st.worklist);
-    const int k0 = wid * (int)gridDim.x + (int)blockIdx.x, kstep = (int)gridDim.x * COMMIT_WARPS;
-    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
-    if ((int64_t)k0 < p.st.n) { r0 = recs[2 * (int64_t)k0]; r1 = recs[2 * (int64_t)k0 + 1]; }   // valid iff k0 < count
     for (int q = tid; q < CELL_LUT_N / 2; q += COMMIT_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -1073,6 +1071,16 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // This launch is the programmatic dependent of the physics launch: its CTAs become resident (and run the set-up
+    // above) while that grid drains; nothing it wrote -- and, through its last CTA, nothing k_widen wrote -- is touched
+    // before this point.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the next launch on the stream may set itself up
+    const int count = p.st.sched[4];
+    const int4 *recs = reinterpret_cast<const int4 *>(p.st.worklist);
+    const int k0 = wid * (int)gridDim.x + (int)blockIdx.x, kstep = (int)gridDim.x * COMMIT_WARPS;
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = r0;
+    if ((int64_t)k0 < p.st.n) { r0 = recs[2 * (int64_t)k0]; r1 = recs[2 * (int64_t)k0 + 1]; }   // valid iff k0 < count
     const int64_t n = p.st.n;
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     Ring<2, CommitWarp, false> ring(p, ws, lut, lane);
@@ -1803,8 +1811,17 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         const int64_t groups_w = (n + p.group - 1) / p.group;
         const int64_t ctas_w = (groups_w + WIDEN_WARPS - 1) / WIDEN_WARPS;
         if (tr) cudaEventRecord(ctx->trace[0], s);
-        k_widen<<<(unsigned)(ctas_w < ctx->num_sms ? ctas_w : ctx->num_sms), WIDEN_WARPS * 32, widen_smem_bytes(), s>>>(p);
-        int rc = check(cudaPeekAtLastError());
+        cudaLaunchAttribute ap[1];
+        ap[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        ap[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t lw = {};
+        lw.gridDim = dim3((unsigned)(ctas_w < ctx->num_sms ? ctas_w : ctx->num_sms));
+        lw.blockDim = dim3(WIDEN_WARPS * 32);
+        lw.dynamicSmemBytes = widen_smem_bytes();
+        lw.stream = s;
+        lw.attrs = ap;
+        lw.numAttrs = tr ? 0 : 1;   // (a timing event in front of the launch: nothing to overlap with)
+        int rc = check(cudaLaunchKernelEx(&lw, k_widen, p));
         if (rc) return rc;
         StepParams pa = p;
         pa.group = 32;
@@ -1813,9 +1830,6 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         lp.blockDim = dim3(StepCfg<1>::WPC * 32);
         lp.dynamicSmemBytes = 0;
         lp.stream = s;
-        cudaLaunchAttribute ap[1];
-        ap[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        ap[0].val.programmaticStreamSerializationAllowed = 1;
         lp.attrs = ap;
         lp.numAttrs = 1;
         rc = check(cudaLaunchKernelEx(&lp, k_step<KIND, 1>, pa));
@@ -1824,7 +1838,15 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         const int64_t ctas_c = (n / 8 + COMMIT_WARPS - 1) / COMMIT_WARPS;   // ~1 listed env in 14: about one per warp
         const int64_t max_c = (p.cfg.reserved & 32768) ? 3 : (int64_t)ctx->num_sms * 7;   // bit 15: tiny grid (tests)
         if (tr) cudaEventRecord(ctx->trace[4], s);
-        k_commit<<<(unsigned)(ctas_c < max_c ? (ctas_c > 0 ? ctas_c : 1) : max_c), COMMIT_WARPS * 32, commit_smem_bytes(), s>>>(p);
+        cudaLaunchConfig_t lcm = {};
+        lcm.gridDim = dim3((unsigned)(ctas_c < max_c ? (ctas_c > 0 ? ctas_c : 1) : max_c));
+        lcm.blockDim = dim3(COMMIT_WARPS * 32);
+        lcm.dynamicSmemBytes = commit_smem_bytes();
+        lcm.stream = s;
+        lcm.attrs = ap;
+        lcm.numAttrs = tr ? 0 : 1;
+        rc = check(cudaLaunchKernelEx(&lcm, k_commit, p));
+        if (rc) return rc;
         if (tr) cudaEventRecord(ctx->trace[5], s);
         ctx->last_launches = 3;
         return check(cudaPeekAtLastError());
