@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(StepCfg<PHASES>::WPC * 32, PHASES == 1 ? IGLU_
     // (The physics launch of the overlapped step is itself a programmatic dependent of k_widen and must NOT wait for
     // it here -- it runs next to it; its last CTA waits at the very end instead, see below.)
     if (!(PHASES == 1 && p.overlap)) asm volatile("griddepcontrol.wait;" ::: "memory");
+    // the fused launch is the programmatic dependent of whatever precedes it on the stream (the previous step's fused
+    // launch, say): it may become resident while that grid drains -- and waits, like this one, before it reads.
+    // (Measured: the same chaining costs 3-5 % for the physics launch of the two-launch form -- early-resident physics
+    // CTAs get in the way of the observe launch's tail -- so that launch stays a normal one.)
+    if (PHASES == 3) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int64_t n = p.st.n;
     const int GS = p.group;
@@ -1851,6 +1856,9 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         ctx->last_launches = 3;
         return check(cudaPeekAtLastError());
     }
+    cudaLaunchAttribute pdl[1];   // every step launch may overlap its set-up with the tail of the kernel before it
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = 1;
     const bool fused_better = p.cfg.reward_mode != IGLU_REWARD_EVERY_STEP && p.cfg.write_grid_obs == 1 && p.obs.grid;
     const bool split = ((!fused_better) && !(p.cfg.reserved & 2)) || (p.cfg.reserved & 4);
     if (!split) {
@@ -1859,9 +1867,16 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         p.group = (2 * ((n + 31) / 32) <= warp_slots) ? 16 : 32;
         const int64_t groups = (n + p.group - 1) / p.group;
         const unsigned grid = (unsigned)(groups < resident_ctas ? groups : resident_ctas);
-        k_step<KIND, 3><<<grid, StepCfg<3>::WPC * 32, step_smem_bytes<3>(), s>>>(p);
+        cudaLaunchConfig_t lf = {};
+        lf.gridDim = dim3(grid);
+        lf.blockDim = dim3(StepCfg<3>::WPC * 32);
+        lf.dynamicSmemBytes = step_smem_bytes<3>();
+        lf.stream = s;
+        lf.attrs = pdl;
+        lf.numAttrs = 1;
+        const int rcf = check(cudaLaunchKernelEx(&lf, k_step<KIND, 3>, p));
         ctx->last_launches = 1;
-        return check(cudaPeekAtLastError());
+        return rcf ? rcf : check(cudaPeekAtLastError());
     }
     // launch 1: physics, one thread per env, 32-env groups, 4-warp CTAs
     p.group = 32;
