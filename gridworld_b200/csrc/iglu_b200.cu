@@ -217,11 +217,11 @@ __device__ __noinline__ void pool_fetch(const iglu_task_pool &pool, int cap, int
 #define IGLU_OBS_DYN_GROUP 8   // envs per dynamically scheduled group of the observe launch
 #endif
 #ifndef IGLU_PHYS_WARPS
-#define IGLU_PHYS_WARPS 4      // warps per CTA of the physics launch
+#define IGLU_PHYS_WARPS 2      // warps per CTA of the physics launch (small CTAs fill the registers k_widen leaves best)
 #endif
 #ifndef IGLU_PHYS_CTAS
-#define IGLU_PHYS_CTAS 5       // 4-warp CTAs of the physics launch per SM the register budget is set for (5: 96 registers,
-                               // no spills; 4: 128 registers -- same speed alone, one CTA fewer next to k_widen)
+#define IGLU_PHYS_CTAS 10      // physics CTAs per SM the register budget is set for (10 x 64 threads: 96 registers, no
+                               // spills; 128 registers run at the same speed alone but leave fewer CTAs next to k_widen)
 #endif
 template <int PHASES> struct StepCfg {
     static constexpr int WPC = PHASES == 2 ? IGLU_OBS_WARPS : (PHASES == 1 ? IGLU_PHYS_WARPS : WARPS_PER_CTA);
@@ -979,9 +979,15 @@ struct Ring {
 };
 
 #ifndef IGLU_WIDEN_REGS
-#define IGLU_WIDEN_REGS 56     // 16 warps x 56 registers + three 4-warp physics CTAs x 96 registers = the register file
+#define IGLU_WIDEN_REGS 56     // with evaluations: 16 warps x 56 registers + 96-register physics CTAs fill the register file
 #endif
-__global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ StepParams p) {
+#ifndef IGLU_WIDEN_REGS_NOEVAL
+#define IGLU_WIDEN_REGS_NOEVAL 32   // reward on change: no evaluation code in the widen launch (no spills at 32), so the
+                                    // whole physics grid fits next to it in one wave: 0.078 -> 0.074 ms
+#endif
+// EVAL = false is the instantiation for reward_mode on_change (the widen launch never evaluates there)
+template <bool EVAL>
+__global__ void __maxnreg__(EVAL ? IGLU_WIDEN_REGS : IGLU_WIDEN_REGS_NOEVAL) k_widen(const __grid_constant__ StepParams p) {
     constexpr int NBUF = IGLU_WIDEN_RING;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem_raw);
@@ -1005,7 +1011,7 @@ __global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ Ste
     const int64_t n = p.st.n;
     const int GS = p.group;
     const int64_t ngroups = (n + GS - 1) / GS;
-    const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    const bool every_step = EVAL && p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
     Ring<NBUF, WidenWarp, true> ring(p, ws, lut, lane);
     const int total_warps = (int)gridDim.x * WIDEN_WARPS;
     // every warp's first group is its static index; the counter st.sched[0] (left at zero by k_commit) deals the rest
@@ -1039,7 +1045,7 @@ __global__ void __maxnreg__(IGLU_WIDEN_REGS) k_widen(const __grid_constant__ Ste
             const int64_t ej = e0 + j;
             ObsSlot &sl = ring.wait();
             write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
-            if ((em >> j) & 1u) ring.evaluate(sl, ej, (hm >> j) & 1u, __shfl_sync(0xffffffffu, nblk, j));
+            if (EVAL && ((em >> j) & 1u)) ring.evaluate(sl, ej, (hm >> j) & 1u, __shfl_sync(0xffffffffu, nblk, j));
             ring.release();
             if (pend) {
                 const int jn = __ffs(pend) - 1;
@@ -1655,7 +1661,8 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes()));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_widen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
     if (!rc) rc = check(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes()));
     c->tracing = 0;
     for (int i = 0; i < 6; i++) c->trace[i] = nullptr;
@@ -1826,7 +1833,8 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         lw.stream = s;
         lw.attrs = ap;
         lw.numAttrs = tr ? 0 : 1;   // (a timing event in front of the launch: nothing to overlap with)
-        int rc = check(cudaLaunchKernelEx(&lw, k_widen, p));
+        int rc = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP ? check(cudaLaunchKernelEx(&lw, k_widen<true>, p))
+                                                             : check(cudaLaunchKernelEx(&lw, k_widen<false>, p));
         if (rc) return rc;
         StepParams pa = p;
         pa.group = 32;
