@@ -1131,3 +1131,29 @@ def test_render_pov_dropin_surface():
     assert np.array_equal(env.render(), obs['pov'])
     fake = gw.GridWorld(render=True, fake=True, vector_state=True, discretize=True)
     assert 'pov' in fake.observation_space.spaces
+
+
+def test_overlapped_step_counts_every_evaluation_once():
+    """The device evaluation counter under the overlapped step (bench.py's evaluated_frac): k_widen evaluates every env
+    that holds blocks when the step starts (and is not being reset), k_commit re-evaluates the envs whose block count
+    changed and counts only those k_widen did not look at."""
+    import gridworld_b200 as gw
+    from bench import synth_targets
+    n, steps = 1024, 60
+    T = synth_targets(n, 0.2, 'compact', 9)
+    rng = np.random.RandomState(4)
+    env = gw.make_vec(n, max_steps=25, reward_mode='every_step', _sched_bits=OVERLAP)
+    env.set_tasks(T)
+    env.reset()
+    env.reset_evaluation_counter()
+    expected = 0
+    p = np.array([1, 5, 2, 2, 2, 3, 2, 2, 2, 2, 2, 2, 2, 2, 5, 2, 4, 6], float)
+    for t in range(steps):
+        ist = env._istate.cpu().numpy()
+        dsize_pre, resetting = ist[5].copy(), ((ist[3] >> 16) & 0xFF) != 0
+        env.step(rng.choice(18, n, p=p / p.sum()).astype(np.int32))
+        ist = env._istate.cpu().numpy()
+        dsize_post, changed = ist[5], ist[7] != 0
+        expected += int(((dsize_pre != 0) & ~resetting).sum())
+        expected += int((changed & (dsize_post != 0) & ((dsize_pre == 0) | resetting)).sum())
+    assert env.evaluations == expected and expected > 2000
