@@ -86,15 +86,15 @@ __device__ __forceinline__ uint32_t keep_below(int n) { return n >= 4 ? 0xFFFFFF
 // bit 8 j + 7 <-> byte j of x is non-zero
 __device__ __forceinline__ uint32_t nz_bytes(uint32_t x) { return (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u; }
 
-// grid ^ init of window word w, non-cell bytes cleared (EDGE: w may hold bytes that are not cells)
-template <bool EDGE>
+// grid ^ init of window word w, non-cell bytes cleared. EDGE says which non-cell bytes w may hold: 0 none, 1 bytes before
+// cell 0 (words 0..3), 2 bytes after the last cell (words 272..275), 3 either.
+template <int EDGE>
 __device__ __forceinline__ uint32_t diff_word(const uint32_t *win, int off, const uint32_t *init32, int w) {
     uint32_t x = win[w];
     if (init32) x ^= init32[w];
-    if (EDGE) {
-        const int lo = off - 4 * w;   // bytes [lo, lo + CELLS) of this word are cells
-        x &= keep_from(lo) & keep_below(lo + CELLS);
-    }
+    const int lo = off - 4 * w;   // bytes [lo, lo + CELLS) of this word are cells
+    if (EDGE & 1) x &= keep_from(lo);
+    if (EDGE & 2) x &= keep_below(lo + CELLS);
     return x;
 }
 
@@ -111,7 +111,8 @@ __device__ __forceinline__ int word_scan(const uint32_t *win, int off, const int
         const int w = lane + 32 * q;
         uint32_t x = 0;
         if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS)   // only words 0..3 and the last ones can hold non-cell bytes
-            x = (q == 0 || 32 * q + 32 > ROW_WORDS - 4) ? diff_word<true>(win, off, i32, w) : diff_word<false>(win, off, i32, w);
+            x = q == 0 ? diff_word<1>(win, off, i32, w)
+                       : (32 * q + 32 > ROW_WORDS - 4 ? diff_word<2>(win, off, i32, w) : diff_word<0>(win, off, i32, w));
         const unsigned b = __ballot_sync(0xffffffffu, x != 0);
         if (b) {   // (warp-uniform: sparse rows skip most rounds)
             if (COUNT) nb += __popc(nz_bytes(x));
@@ -134,8 +135,11 @@ __device__ __forceinline__ int block_emit(const uint32_t *win, int off, const in
         w = wl[lane];
         g = win[w];
         if (init) s = reinterpret_cast<const uint32_t *>(init)[w];
+        uint32_t x = g ^ s;
         const int lo = off - 4 * w;
-        m = nz_bytes((g ^ s) & keep_from(lo) & keep_below(lo + CELLS));
+        if (w < 4) x &= keep_from(lo);                                // only the first / last words hold non-cell bytes
+        else if (w >= (CELLS >> 2)) x &= keep_below(lo + CELLS);
+        m = nz_bytes(x);
     }
     const int cnt = __popc(m);   // 0..4
     const unsigned lt = (1u << lane) - 1u;
@@ -143,12 +147,13 @@ __device__ __forceinline__ int block_emit(const uint32_t *win, int off, const in
                    b2 = __ballot_sync(0xffffffffu, cnt & 4);
     int pos = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
     const int cell0 = 4 * w - off;
+    // the four codes at once (code_of per byte): d = g - s bytewise; valid iff d + 6 <= 12 (unsigned byte compare)
+    const uint32_t d4 = __vsub4(g, s);
+    const uint32_t ok = __vcmpleu4(__vadd4(d4, 0x06060606u), 0x0C0C0C0Cu);   // 0xFF per valid byte
+    const uint32_t codes = (d4 & 0x0F0F0F0Fu & ok) | (0x08080808u & ~ok);
 #pragma unroll
     for (int b = 0; b < 4; b++) {
-        if (m & (0x80u << (8 * b))) {
-            const int d = (int)(int8_t)(g >> (8 * b)) - (int)(int8_t)(s >> (8 * b));
-            gl[pos++] = (uint16_t)((cell0 + b) | (code_of(d) << 11));
-        }
+        if (m & (0x80u << (8 * b))) gl[pos++] = (uint16_t)((cell0 + b) | (((codes >> (8 * b)) & 15u) << 11));
     }
     return __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
 }
@@ -160,7 +165,7 @@ __device__ __forceinline__ int count_blocks(const uint32_t *win, int off, const 
 #pragma unroll
     for (int q = 0; q < (ROW_WORDS + 31) / 32; q++) {
         const int w = lane + 32 * q;
-        if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS) nb += __popc(nz_bytes(diff_word<true>(win, off, i32, w)));
+        if (32 * q + 32 <= ROW_WORDS || w < ROW_WORDS) nb += __popc(nz_bytes(diff_word<3>(win, off, i32, w)));
     }
     return __reduce_add_sync(0xffffffffu, nb);
 }
