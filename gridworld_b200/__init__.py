@@ -5,7 +5,7 @@ render=False, vector_state=True, ...), env.set_task / reset / step. Batched surf
 """
 from .tasks import Task, Tasks, enumerate_tasks, load_goals, load_tasks_dataset, pool_arrays  # noqa: F401
 from .env import Actions, GridWorld, SizeReward, Wrapper, create_env, make  # noqa: F401
-from .vec_env import IGLUVecEnv, make_vec, max_intersection, sample_tasks  # noqa: F401
+from .vec_env import IGLUVecEnv, load_texture, make_vec, max_intersection, sample_tasks  # noqa: F401
 
 __all__ = ['Task', 'Tasks', 'enumerate_tasks', 'load_goals', 'load_tasks_dataset', 'pool_arrays', 'Actions', 'GridWorld', 'SizeReward',
-           'Wrapper', 'create_env', 'make', 'IGLUVecEnv', 'make_vec', 'max_intersection', 'sample_tasks']
+           'Wrapper', 'create_env', 'make', 'IGLUVecEnv', 'make_vec', 'max_intersection', 'sample_tasks', 'load_texture']

@@ -71,9 +71,10 @@ class GridWorld:
     def __init__(self, render=True, max_steps=250, select_and_place=False, discretize=False,
                  right_placement_scale=1., wrong_placement_scale=0.1, render_size=(64, 64),
                  target_in_obs=False, action_space='walking', vector_state=True, fake=False, name='',
-                 device='cuda', texture=None):
+                 device='cuda', texture='auto'):
         # render=True: obs['pov'] comes from the CUDA voxel ray caster (csrc/iglu_render.cuh), the stand-in for the
-        # reference's pyglet / OpenGL renderer; `texture` = the reference's texture atlas as an array (None = flat colours)
+        # reference's pyglet / OpenGL renderer; `texture` = the reference's texture atlas (array / PNG path / 'auto' = the
+        # texture.png of an installed reference package when there is one; None = flat colours)
         self._vec = IGLUVecEnv(1, device=device, action_space=action_space, discretize=discretize,
                                render=bool(render) and not fake, render_size=render_size, texture=texture,
                                select_and_place=select_and_place, max_steps=max_steps,

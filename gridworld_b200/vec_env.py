@@ -79,8 +79,8 @@ class IGLUVecEnv:
       observation/reward as two launches or one fused launch; False = always one fused launch; 'force' = always two), max_target_blocks (capacity of the per-env target block list),
       render / render_size / texture (render=True adds obs['pov'], uint8 [n, h, w, 3]: the reference's OpenGL frame
       (render.py) restated as a voxel ray caster, one more launch per step / reset; texture = the reference's
-      128 x 128 RGBA atlas as an array (e.g. np.asarray(PIL.Image.open('gridworld/texture.png'))), None = flat
-      colours per block id).
+      128 x 128 RGBA atlas as an array [128, 128, 4], a PNG path, or 'auto' = the texture.png of an installed reference
+      package if there is one (load_texture); None = flat colours per block id).
 
     step() returns device tensors that alias persistent buffers: a policy reads them in place.
     set_tasks / set_task_pool / set_task_generator assign tasks (the latter two keep a device-resident generator
@@ -159,6 +159,8 @@ class IGLUVecEnv:
         self._actions_dev = z(n, dtype=torch.int32)
         self._pov = z(n, self.render_size[1], self.render_size[0], 3, dtype=torch.uint8) if self.do_render else None
         self._atlas = None
+        if self.do_render and isinstance(texture, str):
+            texture = load_texture(texture)
         if self.do_render and texture is not None:
             a = torch.as_tensor(np.ascontiguousarray(np.asarray(texture, dtype=np.uint8)))
             if tuple(a.shape) != (128, 128, 4):
@@ -664,6 +666,33 @@ class IGLUVecEnv:
             self._obs_grid.view(self.num_envs, _lib.CELLS).copy_(self._grid[:, :_lib.CELLS])
         if self._obs_target is not None:
             self._obs_target.view(self.num_envs, _lib.CELLS).copy_(self._target[:, :_lib.CELLS])
+
+
+def load_texture(path='auto'):
+    """The 128 x 128 RGBA texture atlas as a uint8 array [128, 128, 4] (rows top-down), or None.
+
+    path: a PNG file, or 'auto' = the `texture.png` that ships inside an installed reference package
+    (`gridworld/texture.png`, reference render.py:54, 64-67) if that package can be located -- it is NOT imported --
+    else None (the ray caster then uses flat colours). Needs Pillow; returns None without it."""
+    import importlib.util
+    import os
+    if path == 'auto':
+        try:
+            spec = importlib.util.find_spec('gridworld')
+        except (ImportError, ValueError):
+            spec = None
+        roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+        path = next((os.path.join(r, 'texture.png') for r in roots if os.path.exists(os.path.join(r, 'texture.png'))), None)
+        if path is None:
+            return None
+    try:
+        from PIL import Image
+    except ImportError:
+        return None
+    a = np.asarray(Image.open(path).convert('RGBA'), dtype=np.uint8)
+    if a.shape != (128, 128, 4):
+        raise ValueError(f'{path}: expected a 128 x 128 texture atlas, got {a.shape}')
+    return a
 
 
 def make_vec(num_envs, device='cuda', **kwargs):

@@ -1118,7 +1118,7 @@ def test_render_pov_vs_oracle(with_atlas, size):
 def test_render_pov_dropin_surface():
     """gym surface with render=True (reference env.py:93-94, 257-258, 299-300): obs['pov'] uint8 (64, 64, 3)."""
     import gridworld_b200 as gw
-    env = gw.GridWorld(render=True, vector_state=True, discretize=True, select_and_place=True, max_steps=20)
+    env = gw.GridWorld(render=True, vector_state=True, discretize=True, select_and_place=True, max_steps=20, texture=None)
     assert env.observation_space['pov'].shape == (64, 64, 3)
     env.set_task(gw.Task('', gw.Tasks.to_dense([(0, 0, -3, 3)]), starting_grid=[(0, 0, -3, 3), (1, 0, -2, 5)]))
     obs = env.reset()

@@ -262,3 +262,25 @@ def test_bench_reference_arm_contract():
     assert d['cpu_port']['kind'] == 'port' and d['cpu_port']['value'] > 0
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+def test_load_texture_locates_an_installed_reference(tmp_path, monkeypatch):
+    """load_texture('auto') finds gridworld/texture.png of an installed reference package without importing it, and
+    answers None when there is none."""
+    import sys
+    import gridworld_b200 as gw
+    pytest.importorskip('PIL')
+    from PIL import Image
+    monkeypatch.setattr(sys, 'path', [p for p in sys.path if not os.path.isdir(os.path.join(p, 'gridworld'))])
+    sys.modules.pop('gridworld', None)
+    assert gw.load_texture('auto') is None
+    pkg = tmp_path / 'gridworld'
+    pkg.mkdir()
+    (pkg / '__init__.py').write_text('raise RuntimeError("must not be imported")\n')
+    rng = np.random.RandomState(0)
+    atlas = rng.randint(0, 256, (128, 128, 4)).astype(np.uint8)
+    Image.fromarray(atlas, 'RGBA').save(pkg / 'texture.png')
+    monkeypatch.syspath_prepend(str(tmp_path))
+    got = gw.load_texture('auto')
+    assert got is not None and got.shape == (128, 128, 4) and np.array_equal(got, atlas)
+    assert np.array_equal(gw.load_texture(str(pkg / 'texture.png')), atlas)
