@@ -922,10 +922,13 @@ struct __align__(16) WidenWarp {
     unsigned long long bar[IGLU_WIDEN_RING];
 };
 #ifndef IGLU_WIDEN_WARPS
-#define IGLU_WIDEN_WARPS 16
+#define IGLU_WIDEN_WARPS 20          // warps of the widen launch's one CTA per SM when it evaluates (every-step reward)
 #endif
-constexpr int WIDEN_WARPS = IGLU_WIDEN_WARPS;
-constexpr size_t widen_smem_bytes() { return TABLE_BYTES + WIDEN_WARPS * sizeof(WidenWarp); }
+#ifndef IGLU_WIDEN_WARPS_NOEVAL
+#define IGLU_WIDEN_WARPS_NOEVAL 16   // ... and when it does not (reward on change)
+#endif
+constexpr int widen_warps(bool eval) { return eval ? IGLU_WIDEN_WARPS : IGLU_WIDEN_WARPS_NOEVAL; }
+constexpr size_t widen_smem_bytes(bool eval) { return TABLE_BYTES + widen_warps(eval) * sizeof(WidenWarp); }
 
 // Shared by k_widen / k_commit: ring producer and consumer over a warp's slots (see k_observe).
 template <int NBUF, class Warp, bool SAFE>
@@ -979,7 +982,7 @@ struct Ring {
 };
 
 #ifndef IGLU_WIDEN_REGS
-#define IGLU_WIDEN_REGS 56     // with evaluations: 16 warps x 56 registers + 96-register physics CTAs fill the register file
+#define IGLU_WIDEN_REGS 48     // with evaluations: 20 warps x 48 registers (no spills) + five 2-warp physics CTAs
 #endif
 #ifndef IGLU_WIDEN_REGS_NOEVAL
 #define IGLU_WIDEN_REGS_NOEVAL 32   // reward on change: no evaluation code in the widen launch (no spills at 32), so the
@@ -994,6 +997,7 @@ __global__ void __maxnreg__(EVAL ? IGLU_WIDEN_REGS : IGLU_WIDEN_REGS_NOEVAL) k_w
     WidenWarp *scratch = reinterpret_cast<WidenWarp *>(smem_raw + TABLE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     WidenWarp &ws = scratch[wid];
+    constexpr int WIDEN_WARPS = EVAL ? IGLU_WIDEN_WARPS : IGLU_WIDEN_WARPS_NOEVAL;
     for (int q = tid; q < CELL_LUT_N / 2; q += WIDEN_WARPS * 32)
         reinterpret_cast<uint32_t *>(lut)[q] = reinterpret_cast<const uint32_t *>(g_cell_lut)[q];
     for (int q = lane; q < NKEY; q += 32) ws.es.kmask[q] = 0u;
@@ -1661,8 +1665,8 @@ extern "C" int iglu_ctx_create(const iglu_config *cfg, iglu_ctx **out) {
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_step<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, s2));
     if (!rc) rc = check(cudaFuncSetAttribute(k_observe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)observe_smem_bytes()));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
-    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes()));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes(true)));
+    if (!rc) rc = check(cudaFuncSetAttribute(k_widen<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)widen_smem_bytes(false)));
     if (!rc) rc = check(cudaFuncSetAttribute(k_commit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)commit_smem_bytes()));
     c->tracing = 0;
     for (int i = 0; i < 6; i++) c->trace[i] = nullptr;
@@ -1811,6 +1815,8 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     // big enough for the overlap to pay for the third launch (measured, profiles/). reserved bit 6 = 1 turns it off.
     if (p.cfg.write_grid_obs == 1 && p.obs.grid && p.st.worklist && p.st.sched && (n >= 8192 || (p.cfg.reserved & 128)) &&
         !(p.cfg.reserved & (64 | 2 | 4))) {
+        const bool w_eval = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+        const int WIDEN_WARPS = widen_warps(w_eval);
         int64_t chunk = (n + (int64_t)ctx->num_sms * WIDEN_WARPS - 1) / ((int64_t)ctx->num_sms * WIDEN_WARPS);
         chunk /= 6;
         chunk = chunk < 2 ? 2 : (chunk > IGLU_OBS_DYN_GROUP ? IGLU_OBS_DYN_GROUP : chunk);
@@ -1829,12 +1835,11 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         cudaLaunchConfig_t lw = {};
         lw.gridDim = dim3((unsigned)(ctas_w < ctx->num_sms ? ctas_w : ctx->num_sms));
         lw.blockDim = dim3(WIDEN_WARPS * 32);
-        lw.dynamicSmemBytes = widen_smem_bytes();
+        lw.dynamicSmemBytes = widen_smem_bytes(w_eval);
         lw.stream = s;
         lw.attrs = ap;
         lw.numAttrs = tr ? 0 : 1;   // (a timing event in front of the launch: nothing to overlap with)
-        int rc = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP ? check(cudaLaunchKernelEx(&lw, k_widen<true>, p))
-                                                             : check(cudaLaunchKernelEx(&lw, k_widen<false>, p));
+        int rc = w_eval ? check(cudaLaunchKernelEx(&lw, k_widen<true>, p)) : check(cudaLaunchKernelEx(&lw, k_widen<false>, p));
         if (rc) return rc;
         StepParams pa = p;
         pa.group = 32;
