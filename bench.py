@@ -661,14 +661,16 @@ def run_b200_arm(args):
                            auto_reset=True, reward_mode='on_change', grid_obs=False, max_target_blocks=64)
         env5.set_tasks(synth_targets(n5, DENSITY, 'compact', 99 + rank, device=dev))
         torch.manual_seed(rank)
-        w1 = torch.randn(1089 + 5 + 6, 64, device=dev, dtype=torch.bfloat16) * 0.05
+        w1 = torch.randint(-8, 9, (1104, 64), device=dev, dtype=torch.int8)   # K = the padded state row (pad cells are 0)
+        w1s = torch.randn(5 + 6, 64, device=dev, dtype=torch.bfloat16) * 0.05
         w2 = torch.randn(64, 18, device=dev, dtype=torch.bfloat16) * 0.5
 
         def policy(o):   # the policy of examples/policy_loop.py: reads the int8 voxel state and the small obs in place
-            x = torch.cat([o['grid'].reshape(n5, -1).to(torch.bfloat16), o['agentPos'].to(torch.bfloat16),
-                           o['inventory'].to(torch.bfloat16) * 0.05], dim=1)
-            logits = torch.relu(x @ w1) @ w2
-            return torch.distributions.Categorical(logits=logits.float()).sample().to(torch.int32)
+            h = torch._int_mm(env5.grid_rows, w1).to(torch.bfloat16) * 0.006   # int8 tensor cores on the int8 state itself
+            h = h + torch.cat([o['agentPos'], o['inventory'] * 0.05], dim=1).to(torch.bfloat16) @ w1s
+            logits = (torch.relu(h) @ w2).float()
+            gumbel = -torch.log(-torch.log(torch.rand_like(logits).clamp_min(1e-20)))
+            return (logits + gumbel).argmax(dim=1).to(torch.int32)   # a sample of Categorical(logits)
         obs5 = [env5.reset()]
         a5 = torch.randint(0, 18, (n5,), device=dev, dtype=torch.int32, generator=gen)
         ph5 = torch.as_tensor(phases(n5, 13 + rank), device=dev)
@@ -686,7 +688,7 @@ def run_b200_arm(args):
         if rank == 0:
             line['config5'] = {
                 'workload': 'configs[4]: walking, 1,048,576 envs/GPU, reward on change (reference gate), observations '
-                            'consumed IN PLACE by a torch bf16 MLP policy on the device (int8 voxel state + agentPos + '
+                            'consumed IN PLACE by a torch MLP policy on the device (int8 first layer on the int8 voxel state rows + agentPos + '
                             'inventory -> Categorical over 18 actions), desynchronised steady state',
                 'envs_per_gpu': n5, 'steps': K5, 'ms_per_step': ms5, 'value': n5 * world / (ms5 * 1e-3),
                 'env_only_ms_per_step': ms5e, 'env_only_value': n5 * world / (ms5e * 1e-3),

@@ -554,6 +554,12 @@ class IGLUVecEnv:
         return self._grid[:, :_lib.CELLS].view(self.num_envs, 9, 11, 11)
 
     @property
+    def grid_rows(self):
+        """int8 [n, 1104]: the resident voxel state as it lies in HBM -- 1089 cells + zero pad per env, rows 16-byte
+        aligned. What the first matmul of an on-device policy wants (K = 1104; no gather of the [n, 9, 11, 11] view)."""
+        return self._grid
+
+    @property
     def target_grid(self):
         return self._target[:, :_lib.CELLS].view(self.num_envs, 9, 11, 11)
 
