@@ -1098,6 +1098,7 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
     if ((int64_t)k0 < p.st.n) { r0 = recs[2 * (int64_t)k0]; r1 = recs[2 * (int64_t)k0 + 1]; }   // valid iff k0 < count
     const int64_t n = p.st.n;
     const bool every_step = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    const bool grid_full = p.cfg.write_grid_obs == 1 && p.obs.grid != nullptr;   // else obs['grid'] is not this launch's business
     Ring<2, CommitWarp, false> ring(p, ws, lut, lane);
     int counted = 0;
     if (k0 < count) ring.issue(r0.x, true);   // grid row + rectangle header of this warp's first env
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
         int mi_eval = 0;
         {
             ObsSlot &sl = ring.wait();
-            if (reset) write_grid_obs(p.obs.grid, e * CELLS, sl.grid, lane);   // the row k_widen wrote predates the reset
+            if (reset && grid_full) write_grid_obs(p.obs.grid, e * CELLS, sl.grid, lane);   // the row k_widen wrote predates the reset
             if (ev) {
                 mi_eval = ring.evaluate(sl, e, has_start != 0, nblk);
                 // evaluations k_widen did not already count for this env (it skips empty grids and reset envs)
@@ -1127,7 +1128,7 @@ __global__ void __launch_bounds__(COMMIT_WARPS * 32, 7) k_commit(const __grid_co
             ring.release();
         }
         if (lane == 0) {
-            if (!reset && edit_cell >= 0) p.obs.grid[e * CELLS + edit_cell] = edit_val;
+            if (grid_full && !reset && edit_cell >= 0) p.obs.grid[e * CELLS + edit_cell] = edit_val;
             const int mi = wrong != 0 ? mi_eval : max_int;                           // task.py:112
             bool done = mi == target_size;                                          // task.py:113
             const int right = mi - max_int;                                         // task.py:115
@@ -1813,7 +1814,12 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     // rewritten obs['grid'] (its ring prefetch hides behind the physics); everything else is faster split
     // Overlapped step (k_widen || physics, then k_commit): whenever obs['grid'] is rewritten in full and the batch is
     // big enough for the overlap to pay for the third launch (measured, profiles/). reserved bit 6 = 1 turns it off.
-    if (p.cfg.write_grid_obs == 1 && p.obs.grid && p.st.worklist && p.st.sched && (n >= 8192 || (p.cfg.reserved & 128)) &&
+    // The same physics + k_commit pair WITHOUT the widen launch serves reward on change when obs['grid'] is not rewritten
+    // in full (in-place / incremental observations, BASELINE config 5): the physics launch finishes every env it neither
+    // edited nor reset, k_commit evaluates the few others -- no pass over all envs after the physics.
+    const bool widen = p.cfg.write_grid_obs == 1 && p.obs.grid;
+    const bool commit_only = !widen && p.cfg.reward_mode != IGLU_REWARD_EVERY_STEP;
+    if ((widen || commit_only) && p.st.worklist && p.st.sched && (n >= (widen ? 8192 : 2048) || (p.cfg.reserved & 128)) &&
         !(p.cfg.reserved & (64 | 2 | 4))) {
         const bool w_eval = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
         const int WIDEN_WARPS = widen_warps(w_eval);
@@ -1839,7 +1845,8 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         lw.stream = s;
         lw.attrs = ap;
         lw.numAttrs = tr ? 0 : 1;   // (a timing event in front of the launch: nothing to overlap with)
-        int rc = w_eval ? check(cudaLaunchKernelEx(&lw, k_widen<true>, p)) : check(cudaLaunchKernelEx(&lw, k_widen<false>, p));
+        int rc = IGLU_OK;
+        if (widen) rc = w_eval ? check(cudaLaunchKernelEx(&lw, k_widen<true>, p)) : check(cudaLaunchKernelEx(&lw, k_widen<false>, p));
         if (rc) return rc;
         StepParams pa = p;
         pa.group = 32;
@@ -1849,7 +1856,7 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         lp.dynamicSmemBytes = 0;
         lp.stream = s;
         lp.attrs = ap;
-        lp.numAttrs = 1;
+        lp.numAttrs = widen ? 1 : 0;   // (without a widen launch in front the physics launch is a normal one)
         rc = check(cudaLaunchKernelEx(&lp, k_step<KIND, 1>, pa));
         if (rc) return rc;
         if (tr) { cudaEventRecord(ctx->trace[1], s); cudaEventRecord(ctx->trace[2], s); cudaEventRecord(ctx->trace[3], s); }
@@ -1866,7 +1873,7 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
         rc = check(cudaLaunchKernelEx(&lcm, k_commit, p));
         if (rc) return rc;
         if (tr) cudaEventRecord(ctx->trace[5], s);
-        ctx->last_launches = 3;
+        ctx->last_launches = widen ? 3 : 2;
         return check(cudaPeekAtLastError());
     }
     cudaLaunchAttribute pdl[1];   // every step launch may overlap its set-up with the tail of the kernel before it

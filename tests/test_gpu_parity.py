@@ -269,6 +269,9 @@ SMALL_COMMIT = 32768   # 3-CTA commit launch: every warp works through a dozen r
                                                                  ('every_step', True, 'incremental', 0),
                                                                  ('every_step', True, 'incremental', GROUPWISE),
                                                                  ('every_step', True, False, 0),
+                                                                 ('on_change', True, False, 0),
+                                                                 ('on_change', True, False, NO_OVERLAP),
+                                                                 ('on_change', True, 'incremental', NO_OVERLAP),
                                                                  ('on_change', True, True, OVERLAP),
                                                                  ('every_step', True, True, OVERLAP),
                                                                  ('every_step', True, True, OVERLAP | SMALL_COMMIT)])
