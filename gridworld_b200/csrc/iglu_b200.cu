@@ -1016,6 +1016,7 @@ __global__ void __maxnreg__(EVAL ? IGLU_WIDEN_REGS : IGLU_WIDEN_REGS_NOEVAL) k_w
     const int GS = p.group;
     const int64_t ngroups = (n + GS - 1) / GS;
     const bool every_step = EVAL && p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    const bool wr = p.cfg.write_grid_obs == 1 && p.obs.grid != nullptr;   // false: evaluations only (in-place observations)
     Ring<NBUF, WidenWarp, true> ring(p, ws, lut, lane);
     const int total_warps = (int)gridDim.x * WIDEN_WARPS;
     // every warp's first group is its static index; the counter st.sched[0] (left at zero by k_commit) deals the rest
@@ -1035,7 +1036,7 @@ __global__ void __maxnreg__(EVAL ? IGLU_WIDEN_REGS : IGLU_WIDEN_REGS_NOEVAL) k_w
         const bool ev = valid && every_step && nblk > 0 && nblk <= p.cfg.tlist_cap - TL_HDR && dsize != 0 &&
                         !(p.cfg.auto_reset && ((w3 >> 16) & 0xFF));
         const unsigned em = __ballot_sync(0xffffffffu, ev);
-        const unsigned nm = __ballot_sync(0xffffffffu, valid);
+        const unsigned nm = wr ? __ballot_sync(0xffffffffu, valid) : em;   // envs staged: all when obs['grid'] is rewritten
         const unsigned hm = __ballot_sync(0xffffffffu, has_start != 0);
         unsigned pend = nm, todo = nm;
         for (int f = 0; f < NBUF && pend; f++) {
@@ -1048,7 +1049,7 @@ __global__ void __maxnreg__(EVAL ? IGLU_WIDEN_REGS : IGLU_WIDEN_REGS_NOEVAL) k_w
             todo &= todo - 1;
             const int64_t ej = e0 + j;
             ObsSlot &sl = ring.wait();
-            write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
+            if (wr) write_grid_obs(p.obs.grid, ej * CELLS, sl.grid, lane);
             if (EVAL && ((em >> j) & 1u)) ring.evaluate(sl, ej, (hm >> j) & 1u, __shfl_sync(0xffffffffu, nblk, j));
             ring.release();
             if (pend) {
@@ -1817,8 +1818,10 @@ static int launch_step(iglu_ctx *ctx, StepParams &p, void *stream) {
     // The same physics + k_commit pair WITHOUT the widen launch serves reward on change when obs['grid'] is not rewritten
     // in full (in-place / incremental observations, BASELINE config 5): the physics launch finishes every env it neither
     // edited nor reset, k_commit evaluates the few others -- no pass over all envs after the physics.
-    const bool widen = p.cfg.write_grid_obs == 1 && p.obs.grid;
-    const bool commit_only = !widen && p.cfg.reward_mode != IGLU_REWARD_EVERY_STEP;
+    // (With every-step reward and in-place observations the widen launch still runs next to the physics -- it then only
+    // stages and evaluates the envs that hold blocks.)
+    const bool widen = (p.cfg.write_grid_obs == 1 && p.obs.grid) || p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
+    const bool commit_only = !widen;
     if ((widen || commit_only) && p.st.worklist && p.st.sched && (n >= (widen ? 8192 : 2048) || (p.cfg.reserved & 128)) &&
         !(p.cfg.reserved & (64 | 2 | 4))) {
         const bool w_eval = p.cfg.reward_mode == IGLU_REWARD_EVERY_STEP;
