@@ -1534,6 +1534,8 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         WindowTargets tg(ps, T, toff, lut, word_scan<false>(T, toff, nullptr, lane, 0, ps.twl, nullptr), lane);
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = 1;
+        PackedCols tp;               // the target's columns, packed (crowded targets only)
+        bool tpacked = false;
         if (invariant) {  // bounding box of the target (or of full_grid: task.py:63-64) -> admissible rectangles
             int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
             auto grow = [&](int cell) {
@@ -1545,7 +1547,9 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
                 for (int c = lane; c < CELLS; c += 32)
                     if (f[c] != 0) grow(c);
             } else if (tg.rounds() > 1) {   // crowded target: look at its columns instead of compacting round after round
-                column_bbox(reinterpret_cast<const int8_t *>(T) + toff, lane, x0, x1, z0, z1);
+                pack_columns(reinterpret_cast<const int8_t *>(T) + toff, lane, tp);
+                tpacked = true;
+                packed_bbox(tp, lane, x0, x1, z0, z1);
             } else {
                 for (int r = tg.rounds() - 1; r >= 0; r--) {   // backwards: round 0 stays loaded for the evaluation
                     const int nt = tg.load(r);
@@ -1559,9 +1563,16 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         }
         int key = -1, best;
         if (single_shift_rects(rc, n_rot) && zero_shift_rects(rc, n_rot) && tg.rounds() > 1) {   // more than 32 non-zero words
-            // zone-spanning target with many blocks: dense cell-by-cell comparison under the four rotations
-            best = eval_zero_shift_dense<WANT_KEY>(reinterpret_cast<const int8_t *>(T) + toff,
-                                                   reinterpret_cast<const int8_t *>(G) + goff, n_rot, lane, &key);
+            // zone-spanning target with many blocks: dense comparison under the four rotations, whole columns at a time
+            // when both rows hold colour differences only (else cell by cell)
+            if (!tpacked) pack_columns(reinterpret_cast<const int8_t *>(T) + toff, lane, tp);
+            PackedCols gp;
+            pack_columns(reinterpret_cast<const int8_t *>(G) + goff, lane, gp);
+            if (__all_sync(0xffffffffu, tp.in_range() && gp.in_range()))
+                best = eval_zero_shift_packed<WANT_KEY>(tp, gp, n_rot, lane, reinterpret_cast<uint2 *>(ps.es.hist), &key);
+            else
+                best = eval_zero_shift_dense<WANT_KEY>(reinterpret_cast<const int8_t *>(T) + toff,
+                                                       reinterpret_cast<const int8_t *>(G) + goff, n_rot, lane, &key);
         } else if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
             auto each = [&](auto f) {
                 for (int r = 0; r < tg.rounds(); r++) {

@@ -455,24 +455,108 @@ __device__ __forceinline__ int eval_zero_shift_dense(const int8_t *t8, const int
     return best;
 }
 
-// x / z extent of the non-zero cells of a staged row, by columns (for crowded rows: no compaction). Warp-uniform result.
-__device__ __forceinline__ void column_bbox(const int8_t *t8, int lane, int &x0, int &x1, int &z0, int &z1) {
+// ---- packed columns (round 2, second form of the dense zero-shift path) ----------------------------------------------
+// The rotations permute the 121 (x, z) columns of the zone as a whole, so a column's nine levels can be compared in one
+// go once they sit in one register pair: nibble y of `lo` (levels 0..7) / `hi` (level 8) holds value + 8, i.e. 2..14 for
+// the colour differences -6..6 and 8 for an empty cell. A lane owns the columns lane, lane + 32, lane + 64, lane + 96
+// (conflict-free byte loads: a warp reads 32 consecutive bytes per level), the sum is built with one multiply-add per
+// byte (borrows of negative values cancel against the +8 bias), and the running min / max of the bytes tells whether
+// the row holds anything outside -6..6 (then the nibbles are meaningless and the caller takes the byte-wise path).
+struct PackedCols {
+    uint32_t lo[4], hi[4];
+    int mn, mx;
+    __device__ __forceinline__ bool in_range() const { return mn >= -6 && mx <= 6; }   // per lane
+};
+
+__device__ __forceinline__ void pack_columns(const int8_t *r8, int lane, PackedCols &p) {
+    p.mn = 0; p.mx = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int col = lane + 32 * q;
+        uint32_t lo = 0x88888888u, hi = 8u;
+        if (q < 3 || col < 121) {
+#pragma unroll
+            for (int y = 0; y < 8; y++) {
+                const int v = r8[121 * y + col];
+                lo += (uint32_t)v << (4 * y);
+                p.mn = min(p.mn, v); p.mx = max(p.mx, v);
+            }
+            const int v = r8[121 * 8 + col];
+            hi += (uint32_t)v;
+            p.mn = min(p.mn, v); p.mx = max(p.mx, v);
+        }
+        p.lo[q] = lo; p.hi[q] = hi;
+    }
+}
+
+// x / z extent of the occupied columns of a packed row. Warp-uniform result.
+__device__ __forceinline__ void packed_bbox(const PackedCols &p, int lane, int &x0, int &x1, int &z0, int &z1) {
     x0 = 10; x1 = 0; z0 = 10; z1 = 0;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int col = lane + 32 * q;
-        if (col < 121) {
-            int any = 0;
-#pragma unroll
-            for (int y = 0; y < 9; y++) any |= t8[121 * y + col];
-            if (any != 0) {
-                const int x = (col * 373) >> 12, z = col - 11 * x;
-                x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-            }
+        if (p.lo[q] != 0x88888888u || p.hi[q] != 8u) {
+            const int x = (col * 373) >> 12, z = col - 11 * x;
+            x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
         }
     }
     x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
     z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+}
+
+// bit 4 y set <-> nibble y of x is non-zero
+__device__ __forceinline__ uint32_t nz_nibbles(uint32_t x) {
+    const uint32_t a = x | (x >> 1);
+    return (a | (a >> 2)) & 0x11111111u;
+}
+
+// eval_zero_shift_dense on packed rows (both in range): `xch` is per-warp shared scratch of >= 121 uint2 through which
+// the lanes hand each other the grid columns their target columns rotate onto. Same result, same tie-break.
+template <bool WANT_KEY>
+__device__ __forceinline__ int eval_zero_shift_packed(const PackedCols &t, const PackedCols &g, int n_rot, int lane,
+                                                      uint2 *xch, int *key_out) {
+    if (n_rot > 1) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int col = lane + 32 * q;
+            if (q < 3 || col < 121) xch[col] = make_uint2(g.lo[q], g.hi[q]);
+        }
+        __syncwarp();
+    }
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int col = lane + 32 * q;
+        if (q < 3 || col < 121) {
+            const uint32_t tl = t.lo[q], th = t.hi[q];
+            const uint32_t on = nz_nibbles(tl ^ 0x88888888u);   // levels where the target column holds a block
+            const bool on8 = th != 8u;
+            auto count = [&](uint32_t gl, uint32_t gh) {
+                const uint32_t a = tl ^ gl, b = a | (a >> 1);
+                return __popc(on & ~(b | (b >> 2))) + (int)(on8 && gh == th);
+            };
+            c0 += count(g.lo[q], g.hi[q]);
+            if (n_rot > 1) {
+                const int x = (col * 373) >> 12, z = col - 11 * x;
+                const uint2 g1 = xch[11 * z + 10 - x], g2 = xch[120 - col], g3 = xch[11 * (10 - z) + x];
+                c1 += count(g1.x, g1.y);
+                c2 += count(g2.x, g2.y);
+                c3 += count(g3.x, g3.y);
+            }
+        }
+    }
+    c0 = __reduce_add_sync(0xffffffffu, c0);
+    int best = c0, kbest = 0;
+    if (n_rot > 1) {
+        c1 = __reduce_add_sync(0xffffffffu, c1);
+        c2 = __reduce_add_sync(0xffffffffu, c2);
+        c3 = __reduce_add_sync(0xffffffffu, c3);
+        if (c1 > best) { best = c1; kbest = 1; }          // strict: the first rotation reaching the max wins
+        if (c2 > best) { best = c2; kbest = 2; }
+        if (c3 > best) { best = c3; kbest = 3; }
+    }
+    if (WANT_KEY) *key_out = best > 0 ? kbest * 441 + 10 * 21 + 10 : -1;
+    return best;
 }
 
 // true when every evaluated rotation's single shift is (0, 0)

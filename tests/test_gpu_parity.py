@@ -209,6 +209,37 @@ def test_reward_vs_oracle_random(rho, support):
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+def test_reward_zone_spanning_rows_with_values_outside_colour_range():
+    """Zone-spanning crowded targets take the packed-column comparison only when both rows hold colour differences
+    (-6..6) and the byte-wise one otherwise. Values outside that range match nothing here; with disjoint
+    stray values in grid and target the reference's raw-integer comparison (the oracle) gives the same answer."""
+    import gridworld_b200 as gw
+    rng = np.random.RandomState(77)
+    n = 1200
+    T = _synth(rng, n, 0.3, 'full')
+    G = _synth(rng, n, 0.3, 'full')
+    for i in range(0, n, 2):
+        G[i] = np.rot90(T[i], k=-rng.randint(4), axes=(1, 2))
+    S = _synth(rng, n, 0.1, 'full')
+    T = (T.astype(np.int16) - S).astype(np.int8)       # difference grids: negative classes too
+    G = (G.astype(np.int16) - S).astype(np.int8)
+    want0, warg0 = O.max_intersection(G, T, threads=8, return_argmax=True)
+    got0, garg0 = gw.max_intersection(G, T, return_argmax=True)   # all in range: packed columns
+    assert np.array_equal(got0.cpu().numpy(), want0) and np.array_equal(garg0.cpu().numpy(), warg0)
+    Gs, Ts = G.copy(), T.copy()
+    for i in range(n):                                   # every third pair stays in range
+        if i % 3 == 0:
+            Gs[i].reshape(-1)[rng.randint(1089, size=3)] = rng.choice([100, 17, 7, -7, -128])
+        if i % 3 == 1:
+            Ts[i].reshape(-1)[rng.randint(1089, size=3)] = rng.choice([-100, -17, 8, -8, 127])
+    want, warg = O.max_intersection(Gs, Ts, threads=8, return_argmax=True)
+    got, garg = gw.max_intersection(Gs, Ts, return_argmax=True)
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(garg.cpu().numpy(), warg)
+    got = gw.max_intersection(Gs, Ts, invariant=False)
+    assert np.array_equal(got.cpu().numpy(), O.max_intersection(Gs, Ts, invariant=False, threads=8))
+
+
 def test_reward_properties_full_size():
     """1M pairs (BASELINE config 4 size): size-independent properties of maximal_intersection."""
     import gridworld_b200 as gw
