@@ -62,6 +62,14 @@ G = rnd(0.2)
 gw.max_intersection(G, T, return_argmax=True)
 gw.max_intersection(G, T, T)
 gw.max_intersection(G, T, invariant=False)
+# crowded zone-spanning pairs: packed-column comparison, and the byte-wise one for rows with stray values
+Tf, Gf = rnd(0.3), rnd(0.3)
+Gf[::2] = np.rot90(Tf[::2], k=1, axes=(2, 3))
+gw.max_intersection(Gf, Tf, return_argmax=True)
+Gf[::5, 3, 4, 5] = 100
+Tf[1::5, 2, 1, 7] = -100
+gw.max_intersection(Gf, Tf, return_argmax=True)
+gw.max_intersection(Gf, Tf, invariant=False)
 fenv = gw.make_vec(n, action_space='flying', target_in_obs=True)
 fenv.set_tasks(T, S)
 for t in range(5):
