@@ -534,6 +534,59 @@ def run_b200_arm(args):
         e2e_graph = None
         sys.stderr.write(f'bench.py: graph-replayed e2e loop unavailable: {exc}\n')
     del env_s
+    # both at once: two half-size groups in flight, each group's step call replayed from CUDA graphs on its own stream
+    e2e_pgraph = None
+    try:
+        pgroups = []
+        for lo, hi in ((0, h), (h, n)):
+            e = make(hi - lo)
+            e.load_state_dict(shard_state(steady, lo, hi))
+            s = torch.cuda.Stream(dev)
+            a = acts_host[:, lo:hi].contiguous().pin_memory()
+            r = torch.zeros(hi - lo, dtype=torch.float64).pin_memory()
+            d = torch.zeros(hi - lo, dtype=torch.uint8).pin_memory()
+            s.wait_stream(torch.cuda.current_stream(dev))
+            gl = []
+            with torch.cuda.stream(s):
+                e.step_host(a[0], r, d, wait=False)
+                e.wait()
+                for t in range(P):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s):
+                        e.step_host(a[t], r, d, wait=False)
+                    gl.append(g)
+            pgroups.append((e, s, gl, r, d, a))   # the graphs hold raw pointers into a, r, d: keep them alive
+    except Exception as exc:   # reported, not fatal
+        pgroups = None
+        sys.stderr.write(f'bench.py: graph-replayed pipelined e2e loop unavailable: {exc}\n')
+    if D.sum_over_ranks(0.0 if pgroups is None else 1.0, dev) == world:   # every rank captured its graphs
+
+        def pg_issue(g, t):
+            with torch.cuda.stream(g[1]):
+                g[2][t % P].replay()
+
+        def pg_consume(g):
+            g[1].synchronize()
+            ret[0] += float(g[3][0])
+
+        def pg_loop(steps):
+            for g in pgroups:
+                pg_issue(g, 0)
+            for t in range(1, steps):
+                for g in pgroups:
+                    pg_consume(g)
+                    pg_issue(g, t)
+            for g in pgroups:
+                pg_consume(g)
+        pg_loop(max(3, W))
+        barrier()
+        t0 = time.perf_counter()
+        pg_loop(Ke)
+        torch.cuda.synchronize(dev)
+        e2e_pgraph = n * world * Ke / D.max_over_ranks(time.perf_counter() - t0, dev)
+        for g in pgroups:
+            torch.cuda.current_stream(dev).wait_stream(g[1])
+    del pgroups
 
     # ---- dense: every world holds a half-built target, no episode limit -> every env is evaluated every step ----
     Kd = min(K, 200)
@@ -573,15 +626,17 @@ def run_b200_arm(args):
                              '(inputs larger than L2, no flush needed)',
                        'actions': f'{P} pre-generated device batches cycled'},
             'clocks': clocks,
-            'e2e': {'value': max(e2e_value, e2e_sync, e2e_graph or 0.0), 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * n,
+            'e2e': {'value': max(e2e_value, e2e_sync, e2e_graph or 0.0, e2e_pgraph or 0.0), 'unit': 'env-steps/s', 'h2d_bytes_per_step': 4 * n,
                     'd2h_bytes_per_step': 9 * n, 'steps': Ke,
                     'api': 'IGLUVecEnv.step_host -> iglu_step_walking_host[_async] / iglu_wait: pinned host actions in, '
                            'reward / done out, read / written by the step kernels over PCIe; the host reads a step\'s '
-                           'results before it issues the next actions. value = the best of three host loops: '
+                           'results before it issues the next actions. value = the best of four host loops: '
                            f'pipelined_value (two groups of {h} envs in flight, each waits for its own results), '
                            'sync_value (one group, synchronise every step), graph_value (one group, the step call '
-                           'captured into one CUDA graph per pinned action buffer and replayed, synchronise every step)',
+                           'captured into one CUDA graph per pinned action buffer and replayed, synchronise every step), '
+                           'pipelined_graph_value (the two groups, each replaying its graphs on its own stream)',
                     'pipelined_value': e2e_value, 'sync_value': e2e_sync, 'graph_value': e2e_graph,
+                    'pipelined_graph_value': e2e_pgraph,
                     'gpu_launches': int(e2e_launches)},
             'gpu_launches': int(launches),
             'dense': {'ms_per_step': dense_ms, 'value': n * world / (dense_ms * 1e-3), 'evaluated_frac': dense_frac,
