@@ -1493,6 +1493,28 @@ struct WindowTargets {
     }
 };
 
+// The dense comparison of a crowded pair (iglu_reward.cuh, packed columns). from_bbox: the admissible rectangles come
+// from the target's occupied columns and are written to *rc; returns -1 when that target does not span the zone (more
+// than one admissible shift: the caller carries on with *rc). Otherwise the caller has checked that every rotation's
+// single shift is (0, 0). Whole columns at a time when both rows hold colour differences only, else cell by cell.
+template <bool WANT_KEY>
+__device__ __forceinline__ int dense_try(const int8_t *t8, const int8_t *g8, bool from_bbox, int n_rot, int lane, uint2 *xch,
+                                      int4 *rc, int *key_out) {
+    PackedCols tp, gp;
+    pack_columns(t8, lane, tp);
+    if (from_bbox) {
+        int x0, x1, z0, z1;
+        packed_bbox(tp, lane, x0, x1, z0, z1);
+        const int4 r = rects_from_bbox(x0, x1, z0, z1);
+        *rc = r;
+        if (!(single_shift_rects(r, n_rot) && zero_shift_rects(r, n_rot))) return -1;
+    }
+    pack_columns(g8, lane, gp);
+    if (__all_sync(0xffffffffu, tp.in_range() && gp.in_range()))
+        return eval_zero_shift_packed<WANT_KEY>(tp, gp, n_rot, lane, xch, key_out);
+    return eval_zero_shift_dense<WANT_KEY>(t8, g8, n_rot, lane, key_out);
+}
+
 template <bool WANT_KEY>
 __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(const int8_t *__restrict__ grids,
                                                                      const int8_t *__restrict__ targets,
@@ -1530,62 +1552,79 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         const int goff = (int)(reinterpret_cast<uintptr_t>(grids + pr * gstride) & 15);
         const int toff = (int)(reinterpret_cast<uintptr_t>(targets + pr * tstride) & 15);
         const uint32_t *G = ps.grid[b], *T = ps.tgt[b];
-        // ---- target: its non-zero words (first round in ps.twl), then blocks round by round ----
-        WindowTargets tg(ps, T, toff, lut, word_scan<false>(T, toff, nullptr, lane, 0, ps.twl, nullptr), lane);
+        const int8_t *t8 = reinterpret_cast<const int8_t *>(T) + toff, *g8 = reinterpret_cast<const int8_t *>(G) + goff;
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
-        int n_rot = 1;
-        PackedCols tp;               // the target's columns, packed (crowded targets only)
-        bool tpacked = false;
-        if (invariant) {  // bounding box of the target (or of full_grid: task.py:63-64) -> admissible rectangles
+        int n_rot = invariant ? 4 : 1;
+        bool have_rc = !invariant;
+        bool done = false;
+        int key = -1, best = 0;
+        // zone-spanning target with many blocks: dense comparison under the four rotations (one scope: its
+        // registers are live on this path only). from_bbox: the rectangles come from the target's occupied columns.
+        auto dense = [&](bool from_bbox) {
+            int4 r;
+            int k = -1;
+            best = dense_try<WANT_KEY>(t8, g8, from_bbox, n_rot, lane, reinterpret_cast<uint2 *>(ps.es.hist), &r, &k);
+            if (from_bbox) { rc = r; have_rc = true; }
+            key = k;
+            return best >= 0;
+        };
+        auto full_rects = [&]() {   // rectangles from full_grid (task.py:63-64); rare: read straight from global memory
             int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
-            auto grow = [&](int cell) {
-                const int l = lut[cell], x = lut_x(l), z = (l & 0xFF) - HROW * x;
-                x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
-            };
-            if (fulls) {  // rare: read straight from global memory
-                const int8_t *f = fulls + pr * fstride;
-                for (int c = lane; c < CELLS; c += 32)
-                    if (f[c] != 0) grow(c);
-            } else if (tg.rounds() > 1) {   // crowded target: look at its columns instead of compacting round after round
-                pack_columns(reinterpret_cast<const int8_t *>(T) + toff, lane, tp);
-                tpacked = true;
-                packed_bbox(tp, lane, x0, x1, z0, z1);
-            } else {
-                for (int r = tg.rounds() - 1; r >= 0; r--) {   // backwards: round 0 stays loaded for the evaluation
-                    const int nt = tg.load(r);
-                    for (int i = lane; i < nt; i += 32) grow(ps.tl[i] & 0x7FF);
+            const int8_t *f = fulls + pr * fstride;
+            for (int c = lane; c < CELLS; c += 32)
+                if (f[c] != 0) {
+                    const int l = lut[c], x = lut_x(l), z = (l & 0xFF) - HROW * x;
+                    x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
                 }
-            }
             x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
             z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
             rc = rects_from_bbox(x0, x1, z0, z1);
-            n_rot = 4;
+            have_rc = true;
+        };
+        // ---- target: its non-zero words (first round in ps.twl); -1 = crowded from the start, no list made ----
+        int nw = word_scan<false, true>(T, toff, nullptr, lane, 0, ps.twl, nullptr);
+        if (nw < 0 && fulls) nw = word_scan<false>(T, toff, nullptr, lane, 0, ps.twl, nullptr);
+        if (nw < 0 || nw > WL_CAP) {   // crowded (more than 32 non-zero words): if it spans the zone, no block list is needed
+            bool attempt = true, from_bbox = false;
+            if (!have_rc && fulls) full_rects();
+            if (!have_rc) from_bbox = true;   // the target's own bounding box: from its packed columns
+            else attempt = single_shift_rects(rc, n_rot) && zero_shift_rects(rc, n_rot);
+            if (attempt) done = dense(from_bbox);
         }
-        int key = -1, best;
-        if (single_shift_rects(rc, n_rot) && zero_shift_rects(rc, n_rot) && tg.rounds() > 1) {   // more than 32 non-zero words
-            // zone-spanning target with many blocks: dense comparison under the four rotations, whole columns at a time
-            // when both rows hold colour differences only (else cell by cell)
-            if (!tpacked) pack_columns(reinterpret_cast<const int8_t *>(T) + toff, lane, tp);
-            PackedCols gp;
-            pack_columns(reinterpret_cast<const int8_t *>(G) + goff, lane, gp);
-            if (__all_sync(0xffffffffu, tp.in_range() && gp.in_range()))
-                best = eval_zero_shift_packed<WANT_KEY>(tp, gp, n_rot, lane, reinterpret_cast<uint2 *>(ps.es.hist), &key);
-            else
-                best = eval_zero_shift_dense<WANT_KEY>(reinterpret_cast<const int8_t *>(T) + toff,
-                                                       reinterpret_cast<const int8_t *>(G) + goff, n_rot, lane, &key);
-        } else if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
-            auto each = [&](auto f) {
-                for (int r = 0; r < tg.rounds(); r++) {
-                    const int nt = tg.load(r);
-                    for (int i = lane; i < nt; i += 32) {
-                        const int e = ps.tl[i], l = lut[e & 0x7FF], x = lut_x(l);
-                        f((l >> 8) / NCLS, x, (l & 0xFF) - HROW * x, e >> 11);
+        if (!done) {
+            if (nw < 0) nw = word_scan<false>(T, toff, nullptr, lane, 0, ps.twl, nullptr);
+            WindowTargets tg(ps, T, toff, lut, nw, lane);   // blocks round by round
+            if (!have_rc) {  // bounding box of the target (or of full_grid) -> admissible rectangles
+                if (fulls) {
+                    full_rects();
+                } else {
+                    int x0 = 10, x1 = 0, z0 = 10, z1 = 0;
+                    for (int r = tg.rounds() - 1; r >= 0; r--) {   // backwards: round 0 stays loaded for the evaluation
+                        const int nt = tg.load(r);
+                        for (int i = lane; i < nt; i += 32) {
+                            const int l = lut[ps.tl[i] & 0x7FF], x = lut_x(l), z = (l & 0xFF) - HROW * x;
+                            x0 = min(x0, x); x1 = max(x1, x); z0 = min(z0, z); z1 = max(z1, z);
+                        }
                     }
+                    x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+                    z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
+                    rc = rects_from_bbox(x0, x1, z0, z1);
                 }
-            };
-            best = eval_single_shift<WANT_KEY>(reinterpret_cast<const int8_t *>(G) + goff, nullptr, each, rc, n_rot, &key);
-        } else {
-            best = eval_votes<WANT_KEY>(ps.es, G, goff, nullptr, lut, tg, rc, n_rot, lane, &key);
+            }
+            if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
+                auto each = [&](auto f) {
+                    for (int r = 0; r < tg.rounds(); r++) {
+                        const int nt = tg.load(r);
+                        for (int i = lane; i < nt; i += 32) {
+                            const int e = ps.tl[i], l = lut[e & 0x7FF], x = lut_x(l);
+                            f((l >> 8) / NCLS, x, (l & 0xFF) - HROW * x, e >> 11);
+                        }
+                    }
+                };
+                best = eval_single_shift<WANT_KEY>(g8, nullptr, each, rc, n_rot, &key);
+            } else {
+                best = eval_votes<WANT_KEY>(ps.es, G, goff, nullptr, lut, tg, rc, n_rot, lane, &key);
+            }
         }
         if (lane == 0) {
             out[pr] = best;

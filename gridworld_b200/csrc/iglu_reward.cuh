@@ -100,7 +100,10 @@ __device__ __forceinline__ uint32_t diff_word(const uint32_t *win, int off, cons
 
 // Returns the number of non-zero words of the row (warp-uniform); the indices of those with slots [w0, w0 + WL_CAP)
 // are written to wl. COUNT: *nblocks = number of blocks (non-zero cells) of the row.
-template <bool COUNT>
+// EARLY (stateless sweep, w0 = 0): give up with -1 when the first 64 words already hold EARLY_WORDS non-zero ones -- a
+// crowded row, for which the caller first tries the packed-column comparison that needs no word list.
+constexpr int EARLY_WORDS = 24;
+template <bool COUNT, bool EARLY = false>
 __device__ __forceinline__ int word_scan(const uint32_t *win, int off, const int8_t *init, int lane, int w0,
                                          uint16_t *wl, int *nblocks) {
     const uint32_t *i32 = reinterpret_cast<const uint32_t *>(init);
@@ -120,6 +123,7 @@ __device__ __forceinline__ int word_scan(const uint32_t *win, int off, const int
             if (x != 0 && (unsigned)slot < (unsigned)WL_CAP) wl[slot] = (uint16_t)w;
             base += __popc(b);
         }
+        if (EARLY && q == 1 && base >= EARLY_WORDS) return -1;
     }
     if (COUNT) *nblocks = __reduce_add_sync(0xffffffffu, nb);
     return base + w0;
@@ -486,6 +490,7 @@ __device__ __forceinline__ void pack_columns(const int8_t *r8, int lane, PackedC
             p.mn = min(p.mn, v); p.mx = max(p.mx, v);
         }
         p.lo[q] = lo; p.hi[q] = hi;
+        asm volatile("" ::: "memory");   // one column's nine loads in flight at a time: hoisting all 36 costs spills
     }
 }
 
