@@ -1494,8 +1494,8 @@ struct WindowTargets {
 };
 
 // The dense comparison of a crowded pair (iglu_reward.cuh, packed columns). from_bbox: the admissible rectangles come
-// from the target's occupied columns and are written to *rc; returns -1 when that target does not span the zone (more
-// than one admissible shift: the caller carries on with *rc). Otherwise the caller has checked that every rotation's
+// from the target's occupied columns; returns -1 when that target does not span the zone (more than one admissible
+// shift: the rectangles are written to *rc and the caller carries on with them). Otherwise the caller has checked that every rotation's
 // single shift is (0, 0). Whole columns at a time when both rows hold colour differences only, else cell by cell.
 template <bool WANT_KEY>
 __device__ __forceinline__ int dense_try(const int8_t *t8, const int8_t *g8, bool from_bbox, int n_rot, int lane, uint2 *xch,
@@ -1505,9 +1505,10 @@ __device__ __forceinline__ int dense_try(const int8_t *t8, const int8_t *g8, boo
     if (from_bbox) {
         int x0, x1, z0, z1;
         packed_bbox(tp, lane, x0, x1, z0, z1);
-        const int4 r = rects_from_bbox(x0, x1, z0, z1);
-        *rc = r;
-        if (!(single_shift_rects(r, n_rot) && zero_shift_rects(r, n_rot))) return -1;
+        if (!(x0 == 0 && x1 == 10 && z0 == 0 && z1 == 10)) {   // room to shift under some rotation (task.py:67-72)
+            *rc = rects_from_bbox(x0, x1, z0, z1);
+            return -1;
+        }
     }
     pack_columns(g8, lane, gp);
     if (__all_sync(0xffffffffu, tp.in_range() && gp.in_range()))
@@ -1564,7 +1565,7 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             int4 r;
             int k = -1;
             best = dense_try<WANT_KEY>(t8, g8, from_bbox, n_rot, lane, reinterpret_cast<uint2 *>(ps.es.hist), &r, &k);
-            if (from_bbox) { rc = r; have_rc = true; }
+            if (from_bbox && best < 0) { rc = r; have_rc = true; }
             key = k;
             return best >= 0;
         };
