@@ -259,6 +259,19 @@ def test_reward_properties_full_size():
     assert bool((mi <= size).all()) and bool((mi >= 0).all())
     assert bool((mi <= (Gd != 0).flatten(1).sum(1)).all())
     assert int(gw.max_intersection(torch.zeros_like(T[:1000]), T[:1000]).abs().sum()) == 0
+    # (7) a target that spans the zone in x and z admits the shift (0, 0) only (task.py:67-72): the score is the best of
+    #     the four rotations' cell-wise agreement, which torch can count directly -- an exact check of all 1 M pairs
+    occ = (T != 0).any(dim=1)                                   # [n, x, z]
+    spans = occ.any(dim=2)[:, 0] & occ.any(dim=2)[:, 10] & occ.any(dim=1)[:, 0] & occ.any(dim=1)[:, 10]
+    assert int(spans.sum()) > n - 10
+    for G in (Gd, R):
+        want = torch.zeros(n, dtype=torch.int32, device='cuda')
+        for k in range(4):
+            Tk = torch.rot90(T, k=k, dims=(2, 3))
+            want = torch.maximum(want, ((Tk != 0) & (Tk == G)).flatten(1).sum(1).to(torch.int32))
+        got = gw.max_intersection(G, T)
+        assert torch.equal(got[spans], want[spans])
+    del occ, want, got
     # (5) the score only depends on the target up to an in-zone XZ translation (the admissible shifts
     #     enumerate every in-zone translate of every rotation): move a compact target, same result
     m = torch.zeros(9, 11, 11, dtype=torch.bool, device='cuda')
