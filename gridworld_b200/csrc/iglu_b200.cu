@@ -1557,6 +1557,7 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
         int4 rc = rects_identity();  // task.py:59-60 admissible = [[(0, 0)]]
         int n_rot = invariant ? 4 : 1;
         bool have_rc = !invariant;
+        bool spans = !invariant;     // every evaluated rotation admits the shift (0, 0) only (bounding box = the zone)
         bool done = false;
         int key = -1, best = 0;
         // zone-spanning target with many blocks: dense comparison under the four rotations (one scope: its
@@ -1565,7 +1566,8 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             int4 r;
             int k = -1;
             best = dense_try<WANT_KEY>(t8, g8, from_bbox, n_rot, lane, reinterpret_cast<uint2 *>(ps.es.hist), &r, &k);
-            if (from_bbox && best < 0) { rc = r; have_rc = true; }
+            if (from_bbox) { have_rc = true; spans = best >= 0; }
+            if (from_bbox && best < 0) rc = r;
             key = k;
             return best >= 0;
         };
@@ -1580,6 +1582,7 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
             z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
             rc = rects_from_bbox(x0, x1, z0, z1);
+            spans = x1 - x0 == 10 && z1 - z0 == 10;
             have_rc = true;
         };
         // ---- target: its non-zero words (first round in ps.twl); -1 = crowded from the start, no list made ----
@@ -1589,7 +1592,7 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
             bool attempt = true, from_bbox = false;
             if (!have_rc && fulls) full_rects();
             if (!have_rc) from_bbox = true;   // the target's own bounding box: from its packed columns
-            else attempt = single_shift_rects(rc, n_rot) && zero_shift_rects(rc, n_rot);
+            else attempt = spans;
             if (attempt) done = dense(from_bbox);
         }
         if (!done) {
@@ -1610,9 +1613,10 @@ __global__ void __launch_bounds__(MI_WARPS * 32, MI_CTAS) k_max_intersection(con
                     x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
                     z0 = __reduce_min_sync(0xffffffffu, z0); z1 = __reduce_max_sync(0xffffffffu, z1);
                     rc = rects_from_bbox(x0, x1, z0, z1);
+                    spans = x1 - x0 == 10 && z1 - z0 == 10;
                 }
             }
-            if (single_shift_rects(rc, n_rot)) {  // one shift per rotation: compare grid bytes directly
+            if (spans) {  // one shift per rotation: compare grid bytes directly
                 auto each = [&](auto f) {
                     for (int r = 0; r < tg.rounds(); r++) {
                         const int nt = tg.load(r);

@@ -564,14 +564,4 @@ __device__ __forceinline__ int eval_zero_shift_packed(const PackedCols &t, const
     return best;
 }
 
-// true when every evaluated rotation's single shift is (0, 0)
-__device__ __forceinline__ bool zero_shift_rects(int4 rc, int n_rot) {
-    const int rw[4] = {rc.x, rc.y, rc.z, rc.w};
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (k < n_rot) ok = ok && (rw[k] & 0x00FF00FF) == 0;
-    return ok;
-}
-
 }  // namespace iglu
