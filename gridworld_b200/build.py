@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO = os.path.join(CSRC, 'libiglu_b200.so')
 SOURCES = ['iglu_b200.cu']
-HEADERS = ['iglu_physics.cuh', 'iglu_reward.cuh', os.path.join('..', '..', 'include', 'iglu_b200.h')]
+HEADERS = ['iglu_physics.cuh', 'iglu_reward.cuh', 'iglu_render.cuh', os.path.join('..', '..', 'include', 'iglu_b200.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
