@@ -27,7 +27,8 @@
 //     16-byte stores before every evaluation; the scan runs over (rotation, dx) rows with __reduce_max_sync at
 //     the end (and the reference's first-max tie-break encoded in the key when argmax is wanted).
 // Tasks whose every rotation admits exactly ONE shift (zone-spanning targets, invariant=False) keep the direct
-// byte-compare path (eval_single_shift).
+// byte-compare path (eval_single_shift); in the stateless sweep, crowded ones compare whole (x, z) columns packed into
+// nibbles under the four rotations (pack_columns / eval_zero_shift_packed).
 #pragma once
 #include <cstdint>
 
